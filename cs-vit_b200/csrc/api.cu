@@ -1,0 +1,135 @@
+// C ABI of libcsvit_sm100.so (declared in include/csvit.h).
+#include <cstdarg>
+#include <cstdio>
+
+#include "../../include/csvit.h"
+#include "errors.h"
+#include "gemm.cuh"
+#include "rowops.cuh"
+
+namespace csvit {
+
+static thread_local char g_err[1024] = "";
+
+int set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return 1;
+}
+const char* last_error() { return g_err; }
+
+}  // namespace csvit
+
+using namespace csvit;
+
+static_assert(int(CSVIT_F32) == int(DT_F32) && int(CSVIT_BF16) == int(DT_BF16), "dtype codes");
+static_assert(int(CSVIT_ACT_GELU) == int(ACT_GELU) && int(CSVIT_ACT_RELU) == int(ACT_RELU), "activation codes");
+static_assert(int(CSVIT_LN_WINDOW) == int(LN_WINDOW) && int(CSVIT_LN_MERGE2X2) == int(LN_MERGE2X2), "layernorm modes");
+static_assert(int(CSVIT_GEMM_SIMT_FP32) == int(GEMM_SIMT), "gemm impl codes");
+
+static inline cudaStream_t S(void* s) { return static_cast<cudaStream_t>(s); }
+
+extern "C" {
+
+int csvit_abi_version(void) { return CSVIT_ABI_VERSION; }
+const char* csvit_last_error(void) { return last_error(); }
+
+int csvit_window_index_map(int H, int W, int ws, int shift, int32_t* out, void* stream) {
+  CSVIT_REQUIRE(ws > 0 && H % ws == 0 && W % ws == 0, "window_index_map: %dx%d not divisible by window %d", H, W, ws);
+  CSVIT_REQUIRE(shift >= 0 && shift < ws, "window_index_map: shift %d outside [0,%d)", shift, ws);
+  return launch_window_index_map(H, W, ws, shift, out, S(stream));
+}
+int csvit_shift_mask(int H, int W, int ws, int shift, float* out, void* stream) {
+  CSVIT_REQUIRE(ws > 0 && H % ws == 0 && W % ws == 0, "shift_mask: %dx%d not divisible by window %d", H, W, ws);
+  CSVIT_REQUIRE(shift >= 0 && shift < ws, "shift_mask: shift %d outside [0,%d)", shift, ws);
+  return launch_shift_mask(H, W, ws, shift, out, S(stream));
+}
+int csvit_rel_pos_index(int ws, int32_t* out, void* stream) {
+  CSVIT_REQUIRE(ws > 0, "rel_pos_index: window %d", ws);
+  return launch_rel_index(ws, out, S(stream));
+}
+int csvit_merge_index_map(int H, int W, int32_t* out, void* stream) {
+  CSVIT_REQUIRE(H % 2 == 0 && W % 2 == 0, "merge_index_map: %dx%d must be even", H, W);
+  return launch_merge_index_map(H, W, out, S(stream));
+}
+int csvit_expand_rel_bias(const float* table, float* out, int heads, int ws, void* stream) {
+  CSVIT_REQUIRE(heads > 0 && ws > 0, "expand_rel_bias: heads=%d ws=%d", heads, ws);
+  return launch_expand_rel_bias(table, out, heads, ws, S(stream));
+}
+
+int csvit_layernorm(const float* x, const float* gamma, const float* beta, float eps, void* out, int out_dtype,
+                    long long ldo, int rows, int C, int mode, int H, int W, int ws, int shift, void* stream) {
+  CSVIT_REQUIRE(out_dtype == DT_F32 || out_dtype == DT_BF16, "layernorm: bad out_dtype %d", out_dtype);
+  WinGeom g = make_geom(H > 0 ? H : 1, W > 0 ? W : 1, ws > 0 ? ws : 1, shift);
+  if (mode == LN_WINDOW) {
+    CSVIT_REQUIRE(ws > 0 && H % ws == 0 && W % ws == 0, "layernorm(window): %dx%d not divisible by window %d", H, W, ws);
+    CSVIT_REQUIRE(shift >= 0 && shift < ws, "layernorm(window): shift %d outside [0,%d)", shift, ws);
+    CSVIT_REQUIRE(rows % (H * W) == 0, "layernorm(window): rows %d not a multiple of %d tokens", rows, H * W);
+  } else if (mode == LN_MERGE2X2) {
+    CSVIT_REQUIRE(H % 2 == 0 && W % 2 == 0, "layernorm(merge): %dx%d must be even", H, W);
+    CSVIT_REQUIRE(rows % ((H / 2) * (W / 2)) == 0, "layernorm(merge): rows %d not a multiple of %d", rows, (H / 2) * (W / 2));
+  } else {
+    CSVIT_REQUIRE(mode == LN_IDENTITY, "layernorm: unknown mode %d", mode);
+  }
+  return launch_layernorm(x, gamma, beta, eps, out, out_dtype, ldo, rows, C, mode, g, S(stream));
+}
+
+int csvit_affine_rows(const float* x, const float* scale, const float* shift, void* out, int out_dtype, long long rows,
+                      int C, void* stream) {
+  CSVIT_REQUIRE(out_dtype == DT_F32 || out_dtype == DT_BF16, "affine_rows: bad out_dtype %d", out_dtype);
+  return launch_affine_rows(x, scale, shift, out, out_dtype, rows, C, S(stream));
+}
+
+int csvit_patch_im2col(const float* img, void* out, int out_dtype, int B, int S_, const float* mean3, const float* std3,
+                       void* stream) {
+  CSVIT_REQUIRE(out_dtype == DT_F32 || out_dtype == DT_BF16, "patch_im2col: bad out_dtype %d", out_dtype);
+  return launch_patch_im2col(img, out, out_dtype, B, S_, mean3, std3, S(stream));
+}
+
+int csvit_linear(const void* A, long long lda, const void* W, long long ldw, int in_dtype, int M, int N, int K,
+                 const float* bias, int act, const float* resid, long long ldr, void* out, long long ldo, int out_dtype,
+                 int scatter_H, int scatter_W, int scatter_ws, int scatter_shift, int impl, void* stream) {
+  CSVIT_REQUIRE(in_dtype == DT_F32 || in_dtype == DT_BF16, "linear: bad in_dtype %d", in_dtype);
+  CSVIT_REQUIRE(out_dtype == DT_F32 || out_dtype == DT_BF16, "linear: bad out_dtype %d", out_dtype);
+  CSVIT_REQUIRE(act >= ACT_NONE && act <= ACT_RELU, "linear: bad activation %d", act);
+  CSVIT_REQUIRE(lda >= K && ldw >= K && ldo >= N, "linear: pitches smaller than the logical widths");
+  EpiParams ep{};
+  ep.bias = bias; ep.resid = resid; ep.out = out; ep.ldo = ldo; ep.ldr = ldr;
+  ep.out_dtype = out_dtype; ep.act = act;
+  ep.map_mode = ROWMAP_IDENTITY;
+  ep.geom = make_geom(1, 1, 1, 0);
+  if (scatter_ws > 0) {
+    CSVIT_REQUIRE(scatter_H % scatter_ws == 0 && scatter_W % scatter_ws == 0, "linear: scatter grid %dx%d vs window %d",
+                  scatter_H, scatter_W, scatter_ws);
+    CSVIT_REQUIRE(M % (scatter_H * scatter_W) == 0, "linear: M=%d not a multiple of %d tokens", M, scatter_H * scatter_W);
+    ep.map_mode = ROWMAP_WINDOW;
+    ep.geom = make_geom(scatter_H, scatter_W, scatter_ws, scatter_shift);
+  }
+  return launch_gemm(A, lda, W, ldw, in_dtype, M, N, K, ep, impl, 0, S(stream));
+}
+
+int csvit_window_attention(const void* qkv, const float* bias, void* out, int dtype, int B, int H, int W, int C, int heads,
+                           int ws, int shift, void* stream) {
+  CSVIT_REQUIRE(bias != nullptr, "window_attention: bias table required");
+  if (dtype == DT_BF16)
+    return launch_window_attention_mma(static_cast<const __nv_bfloat16*>(qkv), bias, static_cast<__nv_bfloat16*>(out), B, H,
+                                       W, C, heads, ws, shift, S(stream));
+  CSVIT_REQUIRE(dtype == DT_F32, "window_attention: bad dtype %d", dtype);
+  CSVIT_REQUIRE(C == heads * 32, "window_attention: head_dim must be 32 (C=%d heads=%d)", C, heads);
+  CSVIT_REQUIRE(H % ws == 0 && W % ws == 0, "window_attention: %dx%d not divisible by window %d", H, W, ws);
+  const int L = ws * ws, nW = (H / ws) * (W / ws);
+  const float* q = static_cast<const float*>(qkv);
+  return launch_attention_simt(q, q + C, q + 2 * C, out, DT_F32, 3ll * C, 3ll * C, 3ll * C, C, B * nW, L, L, heads,
+                               0.17677669529663687f, bias, H, W, ws, shift, S(stream));
+}
+
+int csvit_attention(const void* q, const void* k, const void* v, void* out, int dtype, long long ldq, long long ldk,
+                    long long ldv, long long ldo, int n_seq, int Lq, int S_, int heads, float scale, void* stream) {
+  CSVIT_REQUIRE(dtype == DT_F32 || dtype == DT_BF16, "attention: bad dtype %d", dtype);
+  return launch_attention_simt(q, k, v, out, dtype, ldq, ldk, ldv, ldo, n_seq, Lq, S_, heads, scale, nullptr, 0, 0, 0, 0,
+                               S(stream));
+}
+
+}  // extern "C"

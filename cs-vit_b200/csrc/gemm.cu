@@ -1,0 +1,288 @@
+// GEMM engine: persistent warp-specialised TMA + tcgen05/TMEM kernel (bf16 and tf32 operands, fp32
+// accumulate) and an exact-fp32 SIMT kernel used by the fp32 validation mode.
+//
+// Every Linear on the CS-ViT hot path goes through here: Swin Q/K/V, attention out-proj, MLP fc1/fc2, patch
+// merging reduction, patch embedding (K1, K4, K10, K12, K13 of SURVEY.md §2.3) and the head's projections
+// (K15-K18).  The reference runs each as an `addmm` (HF:swin/modeling_swin.py:404-406,479,514,527,347;
+// ref:cs_vit/net/transformer_module.py:262-264,282,290-294).
+#include <cudaTypedefs.h>
+
+#include "errors.h"
+#include "gemm.cuh"
+
+namespace csvit {
+
+// ----------------------------------------------------------------------------------------------------
+// tcgen05 kernel
+//   warp 0      : TMA producer (one elected lane)
+//   warp 1      : MMA issuer   (one elected lane) - owns the TMEM allocation
+//   warps 2..9  : epilogue, 2 warps per TMEM lane quadrant, each taking half of the tile's columns
+// Pipelines: smem ring full/empty (TMA <-> MMA) and a 2-deep TMEM accumulator ring (MMA <-> epilogue), so
+// the epilogue of tile i overlaps the MMAs of tile i+1.
+// ----------------------------------------------------------------------------------------------------
+constexpr int kBM = 128;
+constexpr int kGemmThreads = 320;
+constexpr int kEpiWarps = 8;
+
+template <int BN>
+struct TcCfg {
+  static constexpr int STAGES = BN == 256 ? 4 : (BN == 128 ? 6 : 5);
+  static constexpr uint32_t A_BYTES = kBM * 128;
+  static constexpr uint32_t B_BYTES = BN * 128;
+  static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr uint32_t TMEM_COLS = 2 * BN <= 256 ? 256 : 512;  // two accumulator buffers, power of 2
+  static constexpr size_t SMEM = 1024 + size_t(STAGES) * STAGE_BYTES + 256;
+};
+
+template <int BN, bool TF32>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int K, EpiParams ep) {
+  using Cfg = TcCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  constexpr int BK = TF32 ? 32 : 64;  // elements per 128-byte swizzled row
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
+  uint8_t* tiles = smem;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + size_t(STAGES) * Cfg::STAGE_BYTES);
+  uint64_t* full = bars;                     // [STAGES]
+  uint64_t* empty = bars + STAGES;           // [STAGES]
+  uint64_t* tfull = bars + 2 * STAGES;       // [2]
+  uint64_t* tempty = bars + 2 * STAGES + 2;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int num_m = (ep.M + kBM - 1) / kBM;
+  const int num_n = (ep.N + BN - 1) / BN;
+  const int num_tiles = num_m * num_n;
+  const int num_kb = (K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], kEpiWarps); }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ---------------- TMA producer ----------------
+    if (lane == 0) {
+      int s = 0; uint32_t ph = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int m_blk = t / num_n, n_blk = t - m_blk * num_n;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty[s], ph ^ 1u);
+          mbar_arrive_expect_tx(&full[s], Cfg::STAGE_BYTES);
+          uint8_t* sa = tiles + size_t(s) * Cfg::STAGE_BYTES;
+          tma_load_2d(sa, &tmA, &full[s], kb * BK, m_blk * kBM);
+          tma_load_2d(sa + Cfg::A_BYTES, &tmB, &full[s], kb * BK, n_blk * BN);
+          if (++s == STAGES) { s = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------- MMA issuer ----------------
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(TF32, kBM, BN);
+      int s = 0; uint32_t ph = 0;
+      int as = 0; uint32_t aph = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        mbar_wait(&tempty[as], aph ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + uint32_t(as * BN);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          const uint32_t sa = base + uint32_t(s) * Cfg::STAGE_BYTES;
+          const uint64_t adesc = make_sw128_kmajor_desc(sa);
+          const uint64_t bdesc = make_sw128_kmajor_desc(sa + Cfg::A_BYTES);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)  // 4 x 32-byte K slices per 128-byte row; +32 B = +2 in the >>4 field
+            umma_ss<TF32>(d_tmem, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), idesc, (kb | k) ? 1u : 0u);
+          umma_commit(&empty[s]);
+          if (kb == num_kb - 1) umma_commit(&tfull[as]);
+          if (++s == STAGES) { s = 0; ph ^= 1u; }
+        }
+        if (++as == 2) { as = 0; aph ^= 1u; }
+      }
+    }
+  } else {
+    // ---------------- epilogue ----------------
+    const int e = warp - 2;
+    const int quad = warp & 3;            // TMEM lane quadrant this warp may read
+    const int half = e >> 2;              // which half of the tile's columns
+    const int row_in_tile = quad * 32 + lane;
+    int as = 0; uint32_t aph = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      const int m_blk = t / num_n, n_blk = t - m_blk * num_n;
+      const int row = m_blk * kBM + row_in_tile;
+      const bool row_ok = row < ep.M;
+      const long long orow = row_ok ? epi_out_row(ep, row) : 0;
+      mbar_wait(&tfull[as], aph);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < BN / 2; c += 32) {
+        const int col_local = half * (BN / 2) + c;
+        const int gcol = n_blk * BN + col_local;
+        if (gcol >= ep.N) break;  // warp-uniform
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(as * BN + col_local), r);
+        tmem_ld_wait();
+        if (row_ok) epi_store_chunk32(ep, orow, gcol, r);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[as]);
+      if (++as == 2) { as = 0; aph ^= 1u; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+// ----------------------------------------------------------------------------------------------------
+// Exact fp32 SIMT kernel (validation mode; also the on-device cross-check for the tensor-core path)
+// ----------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+gemm_simt_f32_kernel(const float* __restrict__ A, long long lda, const float* __restrict__ W, long long ldw, int K, EpiParams ep) {
+  __shared__ float As[16][64 + 4];
+  __shared__ float Ws[16][64 + 4];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+  float acc[4][4] = {};
+  for (int k0 = 0; k0 < K; k0 += 16) {
+    for (int i = threadIdx.x; i < 64 * 16; i += 256) {
+      int r = i >> 4, k = i & 15;
+      int gm = m0 + r, gn = n0 + r, gk = k0 + k;
+      As[k][r] = (gm < ep.M && gk < K) ? A[gm * lda + gk] : 0.0f;
+      Ws[k][r] = (gn < ep.N && gk < K) ? W[gn * ldw + gk] : 0.0f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { a[i] = As[k][ty * 4 + i]; b[i] = Ws[k][tx * 4 + i]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int row = m0 + ty * 4 + i;
+    if (row >= ep.M) continue;
+    long long orow = epi_out_row(ep, row);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int col = n0 + tx * 4 + j;
+      if (col < ep.N) epi_store_scalar(ep, orow, col, acc[i][j]);
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------------------------------
+// Host side
+// ----------------------------------------------------------------------------------------------------
+static PFN_cuTensorMapEncodeTiled_v12000 get_tmap_encoder() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+  }
+  return fn;
+}
+
+// rows x K row-major operand, box = box_rows x 128 bytes, 128-byte swizzle, OOB zero fill.
+static int make_operand_tmap(CUtensorMap* tm, const void* ptr, long long ld, int rows, int K, int dtype, int box_rows) {
+  auto enc = get_tmap_encoder();
+  if (!enc) return set_error("cuTensorMapEncodeTiled entry point not available (driver too old?)");
+  const size_t es = dtype == DT_BF16 ? 2 : 4;
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || ((ld * es) & 15))
+    return set_error("GEMM operand must be 16-byte aligned with a 16-byte-multiple row pitch (ptr=%p ld=%lld)", ptr, ld);
+  cuuint64_t gdim[2] = {cuuint64_t(K), cuuint64_t(rows)};
+  cuuint64_t gstr[1] = {cuuint64_t(ld * es)};
+  cuuint32_t box[2] = {cuuint32_t(128 / es), cuuint32_t(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, dtype == DT_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 2,
+                   const_cast<void*>(ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%d K=%d ld=%lld)", int(r), rows, K, ld);
+  return 0;
+}
+
+static int g_num_sms = 0;
+static int num_sms() {
+  if (!g_num_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+
+template <int BN, bool TF32>
+static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, int K, const EpiParams& ep, int max_ctas, cudaStream_t stream) {
+  using Cfg = TcCfg<BN>;
+  static bool configured = false;
+  auto kern = gemm_tc_kernel<BN, TF32>;
+  if (!configured) {
+    CSVIT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(Cfg::SMEM)));
+    configured = true;
+  }
+  const int tiles = ((ep.M + kBM - 1) / kBM) * ((ep.N + BN - 1) / BN);
+  int ctas = max_ctas > 0 ? max_ctas : num_sms();
+  if (ctas > tiles) ctas = tiles;
+  kern<<<ctas, kGemmThreads, Cfg::SMEM, stream>>>(tmA, tmB, K, ep);
+  CSVIT_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_gemm(const void* A, long long lda, const void* W, long long ldw, int in_dtype, int M, int N, int K,
+                const EpiParams& ep_in, int impl, int max_ctas, cudaStream_t stream) {
+  if (M <= 0 || N <= 0 || K <= 0) return 0;
+  EpiParams ep = ep_in;
+  ep.M = M; ep.N = N;
+  const size_t oes = ep.out_dtype == DT_BF16 ? 2 : 4;
+  ep.vec_ok = (N % 8 == 0) && ((ep.ldo * oes) % 16 == 0) && ((reinterpret_cast<uintptr_t>(ep.out) & 15) == 0) &&
+              (!ep.resid || ((ep.ldr % 4 == 0) && (reinterpret_cast<uintptr_t>(ep.resid) & 15) == 0)) &&
+              (!ep.bias || (reinterpret_cast<uintptr_t>(ep.bias) & 15) == 0);
+  if (impl == GEMM_SIMT) {
+    if (in_dtype != DT_F32) return set_error("SIMT GEMM takes fp32 operands only");
+    dim3 grid((N + 63) / 64, (M + 63) / 64);
+    gemm_simt_f32_kernel<<<grid, 256, 0, stream>>>(static_cast<const float*>(A), lda, static_cast<const float*>(W), ldw, K, ep);
+    CSVIT_CUDA(cudaGetLastError());
+    return 0;
+  }
+  // Tile width: 256 halves the per-MMA shared-memory operand traffic; narrower tiles only where N is small
+  // or 256 would leave most SMs idle.
+  int BN = 256;
+  if (N <= 128 || (N % 256 != 0 && N % 128 == 0)) BN = 128;
+  const int tiles256 = ((M + kBM - 1) / kBM) * ((N + 255) / 256);
+  if (BN == 256 && tiles256 < num_sms()) BN = 128;
+  CUtensorMap tmA, tmB;
+  if (int e = make_operand_tmap(&tmA, A, lda, M, K, in_dtype, kBM)) return e;
+  if (int e = make_operand_tmap(&tmB, W, ldw, N, K, in_dtype, BN)) return e;
+  const bool tf32 = in_dtype == DT_F32;
+  if (BN == 256) return tf32 ? launch_tc<256, true>(tmA, tmB, K, ep, max_ctas, stream) : launch_tc<256, false>(tmA, tmB, K, ep, max_ctas, stream);
+  return tf32 ? launch_tc<128, true>(tmA, tmB, K, ep, max_ctas, stream) : launch_tc<128, false>(tmA, tmB, K, ep, max_ctas, stream);
+}
+
+}  // namespace csvit

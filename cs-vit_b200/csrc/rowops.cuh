@@ -1,0 +1,28 @@
+#pragma once
+#include "common.cuh"
+#include "gemm.cuh"
+
+namespace csvit {
+
+enum : int { LN_IDENTITY = 0, LN_WINDOW = 1, LN_MERGE2X2 = 2 };
+
+int launch_layernorm(const float* x, const float* gamma, const float* beta, float eps, void* out, int out_dtype,
+                     long long ldo, int rows, int C, int mode, const WinGeom& g, cudaStream_t stream);
+int launch_affine_rows(const float* x, const float* scale, const float* shift, void* out, int out_dtype, long long rows,
+                       int C, cudaStream_t stream);
+int launch_patch_im2col(const float* img, void* out, int out_dtype, int B, int S, const float* mean3, const float* std3,
+                        cudaStream_t stream);
+int launch_window_index_map(int H, int W, int ws, int shift, int* out, cudaStream_t stream);
+int launch_shift_mask(int H, int W, int ws, int shift, float* out, cudaStream_t stream);
+int launch_rel_index(int ws, int* out, cudaStream_t stream);
+int launch_merge_index_map(int H, int W, int* out, cudaStream_t stream);
+int launch_expand_rel_bias(const float* table, float* out, int heads, int ws, cudaStream_t stream);
+
+// attention.cu
+int launch_window_attention_mma(const __nv_bfloat16* qkv, const float* bias_exp, __nv_bfloat16* out, int B, int H, int W,
+                                int C, int heads, int ws, int shift, cudaStream_t stream);
+int launch_attention_simt(const void* q, const void* k, const void* v, void* out, int dtype, long long ldq, long long ldk,
+                          long long ldv, long long ldo, int n_seq, int Lq, int S, int heads, float scale,
+                          const float* bias, int mH, int mW, int mws, int mshift, cudaStream_t stream);
+
+}  // namespace csvit

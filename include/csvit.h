@@ -1,0 +1,113 @@
+/* csvit.h - C ABI of libcsvit_sm100.so, the B200 (sm_100a) kernels behind cs_vit.net.
+ *
+ * The reference (Mine268/CS-ViT) has no FFI: its hot path is PyTorch eager code that delegates the backbone
+ * to HuggingFace `transformers` (ref:cs_vit/net/ti_poser.py:246,426).  The drop-in boundary is therefore the
+ * Python surface of `cs_vit.net`; this header is the seam one level below it, the set
+ * of entry points a maintainer binds (ctypes stub in INTEGRATION.md) to replace the ATen op sequences listed
+ * per function.  "HF:" = transformers/models/swin/modeling_swin.py, "ref:" = the reference repository.
+ *
+ * Conventions
+ *   - Plain C types only.  Pointers are CUDA device pointers owned by the caller (PyTorch); the library
+ *     never allocates, frees or retains device memory.  `stream` is a cudaStream_t passed as void*.
+ *   - Every function is asynchronous on `stream`, re-entrant, and returns 0 on success.  On failure it
+ *     returns non-zero and csvit_last_error() (thread-local) describes why.  Nothing throws.
+ *   - dtype codes: CSVIT_F32 = 0, CSVIT_BF16 = 1.  Row-major; `ld*` are row pitches in ELEMENTS.
+ *   - There is no CPU path: a missing GPU or a non-sm_100 device surfaces as a CUDA error code.
+ */
+#ifndef CSVIT_H_
+#define CSVIT_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CSVIT_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define CSVIT_API __attribute__((visibility("default")))
+#else
+#define CSVIT_API
+#endif
+
+enum { CSVIT_F32 = 0, CSVIT_BF16 = 1 };
+enum { CSVIT_ACT_NONE = 0, CSVIT_ACT_GELU = 1, CSVIT_ACT_RELU = 2 };
+enum { CSVIT_LN_IDENTITY = 0, CSVIT_LN_WINDOW = 1, CSVIT_LN_MERGE2X2 = 2 };
+enum { CSVIT_GEMM_TENSORCORE = 0, CSVIT_GEMM_SIMT_FP32 = 1 };
+
+CSVIT_API int csvit_abi_version(void);
+CSVIT_API const char* csvit_last_error(void);
+
+/* ---- integer maps (bit-exact contract) -------------------------------------------
+ * Dumps of the closed-form maps the kernels use internally, for tests.
+ * window_index_map: out[w*ws*ws + i] = flat token id that window w / slot i reads and writes
+ *     = LN -> pad -> torch.roll(-shift) -> window_partition           HF:141-150, 608-622
+ *     (same address for window_reverse -> roll(+shift)                 HF:153-160, 631-636)
+ * shift_mask: out[nW, L, L] in {0, -100}                                HF:556-582 get_attn_mask
+ * rel_pos_index: out[L, L]                                              HF:461-473 create_relative_position_index
+ * merge_index_map: out[(H/2)*(W/2), 4] source tokens in concat order    HF:338-345 SwinPatchMerging.forward
+ */
+CSVIT_API int csvit_window_index_map(int H, int W, int ws, int shift, int32_t* out, void* stream);
+CSVIT_API int csvit_shift_mask(int H, int W, int ws, int shift, float* out, void* stream);
+CSVIT_API int csvit_rel_pos_index(int ws, int32_t* out, void* stream);
+CSVIT_API int csvit_merge_index_map(int H, int W, int32_t* out, void* stream);
+
+/* bias[h, i, j] = table[rel_pos_index(i, j), h]; table is [(2ws-1)^2, heads] fp32.      HF:428-434 */
+CSVIT_API int csvit_expand_rel_bias(const float* table, float* out, int heads, int ws, void* stream);
+
+/* ---- row kernels (HBM-bound) ----------------------------------------------------------------------------
+ * LayerNorm over the last dim of fp32 x[B, H*W, C], eps inside the sqrt, output fp32 or bf16.
+ *   CSVIT_LN_IDENTITY : out row r <- x row r                            HF:606/648 layernorm_*, HF:882 final norm
+ *   CSVIT_LN_WINDOW   : out rows in window order (shift + partition folded into the read address)
+ *                       replaces layernorm_before + F.pad + torch.roll + window_partition   HF:606-622
+ *   CSVIT_LN_MERGE2X2 : out row (b,Y,X) = LN over the 4C concat of the 2x2 neighbourhood    HF:338-346
+ * rows = number of OUTPUT rows (B*H*W, or B*(H/2)*(W/2) for MERGE2X2).  gamma/beta have the output width. */
+CSVIT_API int csvit_layernorm(const float* x, const float* gamma, const float* beta, float eps, void* out, int out_dtype,
+                    long long ldo, int rows, int C, int mode, int H, int W, int ws, int shift, void* stream);
+
+/* y[r, c] = x[r, c] * scale[c] + shift[c]: eval-mode BatchNorm1d folded to an affine map.
+ * Replaces norm(x.transpose(-1,-2)).transpose(-1,-2)   ref:cs_vit/net/transformer_module.py:312,316,341,345,349 */
+CSVIT_API int csvit_affine_rows(const float* x, const float* scale, const float* shift, void* out, int out_dtype,
+                      long long rows, int C, void* stream);
+
+/* out[(b,py,px), c*16+ky*4+kx] = (img[b,c,4py+ky,4px+kx] - mean[c]) / std[c]; img fp32 NCHW [B,3,S,S].
+ * Replaces transforms.Normalize + the unfold half of the 4x4/stride-4 conv.
+ * ref:cs_vit/net/ti_poser.py:239-243,425   HF:286-295.   mean/std are HOST pointers to 3 floats. */
+CSVIT_API int csvit_patch_im2col(const float* img, void* out, int out_dtype, int B, int S, const float* mean3,
+                       const float* std3, void* stream);
+
+/* ---- GEMM engine (tcgen05 + TMEM + TMA) ----------------------------------------------------------------
+ * out[orow, :N] = act(A[M,K] @ W[N,K]^T + bias) + resid[orow, :N]
+ *   in_dtype CSVIT_BF16: A and W bf16, kind::f16 MMA;  CSVIT_F32: A and W fp32, kind::tf32 MMA
+ *   (or exact fp32 FMA with impl = CSVIT_GEMM_SIMT_FP32).  fp32 accumulation in all cases.
+ *   bias, resid may be NULL.  resid is fp32 with pitch ldr and may alias out (in-place residual add).
+ *   scatter_ws > 0: GEMM rows are window-ordered tokens; orow = window_index_map(row) per image of
+ *   scatter_H x scatter_W tokens (window_reverse + roll(+shift) folded into the store).  Else orow = row.
+ * Replaces nn.Linear / addmm call sites: HF:404-406 (Q,K,V as one N=3C GEMM), HF:479, HF:514, HF:527,
+ * HF:347 (reduction), HF:286 (projection as GEMM over csvit_patch_im2col), the residual adds HF:646,650,
+ * and ref:cs_vit/net/transformer_module.py:262-264,282,290-294. */
+CSVIT_API int csvit_linear(const void* A, long long lda, const void* W, long long ldw, int in_dtype, int M, int N, int K,
+                 const float* bias, int act, const float* resid, long long ldr, void* out, long long ldo,
+                 int out_dtype, int scatter_H, int scatter_W, int scatter_ws, int scatter_shift, int impl,
+                 void* stream);
+
+/* ---- attention cores -------------------------------------------------------------------------------------
+ * Swin window attention on window-ordered qkv[B*H*W, 3C] (Q|K|V column blocks, head h at columns 32h..):
+ *   out[B*H*W, C] = softmax(Q K^T / sqrt(32) + bias[h] + shift_mask) V, heads merged.       HF:410-459
+ * bf16: tensor-core kernel (window 7, head_dim 32).  fp32: exact kernel (validation mode).
+ * bias is the expanded [heads, L, L] fp32 table from csvit_expand_rel_bias. */
+CSVIT_API int csvit_window_attention(const void* qkv, const float* bias, void* out, int dtype, int B, int H, int W, int C,
+                           int heads, int ws, int shift, void* stream);
+
+/* Dense multi-head attention for short sequences (S <= 64, head_dim 32), exact fp32 math:
+ *   out[s, i, h*32:(h+1)*32] = softmax_j(q[s,i,h] . k[s,j,h] * scale) v[s,j,h]
+ * q rows: n_seq*Lq, k/v rows: n_seq*S.  `scale` multiplies the logits (the reference passes sqrt(head_dim),
+ * ref:cs_vit/net/transformer_module.py:243,273).  dtype applies to q, k, v and out. */
+CSVIT_API int csvit_attention(const void* q, const void* k, const void* v, void* out, int dtype, long long ldq, long long ldk,
+                    long long ldv, long long ldo, int n_seq, int Lq, int S, int heads, float scale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CSVIT_H_ */

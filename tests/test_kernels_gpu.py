@@ -1,0 +1,142 @@
+"""Per-kernel GPU checks through the C ABI: each CUDA kernel against plain fp32 torch math on the same
+device tensors (tolerances: bf16 operands -> 1e-2 relative, tf32 -> 2e-3, fp32 SIMT -> 1e-5)."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    a, b = a.float(), b.float()
+    return ((a - b).norm() / b.norm().clamp_min(1e-12)).item()
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from cs_vit import ops as o
+    return o
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 256, 128), (1000, 384, 128), (12544, 1024, 1024),
+                                   (6272, 512, 2048), (200, 96, 48), (77, 10, 1024), (3136 * 2, 1536, 512)])
+@pytest.mark.parametrize("dtype", ["bf16", "tf32", "fp32"])
+def test_linear_plain(ops, M, N, K, dtype):
+    g = torch.Generator(device="cuda").manual_seed(M * 7 + N * 3 + K)
+    a = torch.randn(M, K, device="cuda", generator=g)
+    w = torch.randn(N, K, device="cuda", generator=g) * 0.05
+    b = torch.randn(N, device="cuda", generator=g)
+    if dtype == "bf16":
+        a_, w_ = a.bfloat16(), w.bfloat16()
+        ref = a_.float() @ w_.float().T + b
+        out = ops.linear(a_, w_, b, out_dtype=torch.float32)
+        tol = 1e-5
+    elif dtype == "tf32":
+        ref = a.double() @ w.double().T + b.double()
+        out = ops.linear(a, w, b)
+        tol = 2e-3
+    else:
+        ref = a.double() @ w.double().T + b.double()
+        out = ops.linear(a, w, b, impl=ops.GEMM_SIMT)
+        tol = 1e-5
+    torch.cuda.synchronize()
+    assert out.shape == (M, N)
+    assert rel(out, ref) < tol, (dtype, M, N, K, rel(out, ref))
+
+
+def test_linear_epilogues(ops):
+    g = torch.Generator(device="cuda").manual_seed(5)
+    B, H, W, C = 3, 14, 14, 256
+    M = B * H * W
+    a = torch.randn(M, C, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(4 * C, C, device="cuda", generator=g) * 0.05).bfloat16()
+    b = torch.randn(4 * C, device="cuda", generator=g)
+    # GELU -> bf16
+    out = ops.linear(a, w, b, act=ops.ACT_GELU, out_dtype=torch.bfloat16)
+    ref = torch.nn.functional.gelu(a.float() @ w.float().T + b)
+    assert rel(out, ref) < 5e-3
+    # residual, in place, with window scatter
+    w2 = (torch.randn(C, C, device="cuda", generator=g) * 0.05).bfloat16()
+    b2 = torch.randn(C, device="cuda", generator=g)
+    x = torch.randn(M, C, device="cuda", generator=g)
+    for shift in (0, 3):
+        idx = ops.window_index_map(H, W, 7, shift).long()
+        full = (torch.arange(B, device="cuda")[:, None] * (H * W) + idx[None]).reshape(-1)
+        y = a.float() @ w2.float().T + b2
+        ref = x.clone()
+        ref[full] += y
+        xi = x.clone()
+        ops.linear(a, w2, b2, resid=xi, out=xi, scatter=(H, W, 7, shift))
+        assert rel(xi, ref) < 1e-5
+
+
+@pytest.mark.parametrize("C,mode", [(96, 0), (128, 1), (512, 1), (1024, 0), (256, 2), (512, 2)])
+def test_layernorm(ops, C, mode):
+    g = torch.Generator(device="cuda").manual_seed(C + mode)
+    B, H, W = 2, 14, 14
+    x = torch.randn(B * H * W, C, device="cuda", generator=g) * 2 + 0.5
+    width = 4 * C if mode == 2 else C
+    gamma = torch.randn(width, device="cuda", generator=g)
+    beta = torch.randn(width, device="cuda", generator=g)
+    for shift in ((0, 3) if mode == 1 else (0,)):
+        if mode == 0:
+            src = x
+        elif mode == 1:
+            idx = ops.window_index_map(H, W, 7, shift).long()
+            src = x.view(B, H * W, C)[:, idx].reshape(-1, C)
+        else:
+            idx = ops.merge_index_map(H, W).long()  # [No,4]
+            src = x.view(B, H * W, C)[:, idx].reshape(B * idx.shape[0], 4 * C)
+        ref = torch.nn.functional.layer_norm(src, (width,), gamma, beta, 1e-5)
+        out = ops.layernorm(x, gamma, beta, 1e-5, mode=mode, grid=(H, W), ws=7, shift=shift)
+        assert rel(out, ref) < 1e-5
+        outb = ops.layernorm(x, gamma, beta, 1e-5, mode=mode, grid=(H, W), ws=7, shift=shift, out_dtype=torch.bfloat16)
+        assert rel(outb, ref) < 4e-3
+
+
+def test_patch_im2col(ops):
+    g = torch.Generator(device="cuda").manual_seed(3)
+    img = torch.rand(2, 3, 224, 224, device="cuda", generator=g)
+    out = ops.patch_im2col(img, out_dtype=torch.float32)
+    mean = torch.tensor([0.485, 0.456, 0.406], device="cuda")[None, :, None, None]
+    std = torch.tensor([0.229, 0.224, 0.225], device="cuda")[None, :, None, None]
+    n = (img - mean) / std
+    ref = torch.nn.functional.unfold(n, kernel_size=4, stride=4).transpose(1, 2).reshape(-1, 48)
+    assert rel(out, ref) < 1e-6
+
+
+@pytest.mark.parametrize("H,heads,shift", [(14, 16, 0), (14, 16, 3), (28, 8, 3), (56, 4, 3), (7, 32, 0)])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_window_attention(ops, H, heads, shift, dtype):
+    g = torch.Generator(device="cuda").manual_seed(H * heads + shift)
+    B, W, C, ws, L = 2, H, heads * 32, 7, 49
+    nW = (H // ws) * (W // ws)
+    qkv = torch.randn(B * H * W, 3 * C, device="cuda", generator=g).to(dtype)
+    table = torch.randn(169, heads, device="cuda", generator=g)
+    bias = ops.expand_rel_bias(table, ws)
+    out = ops.window_attention(qkv, bias, B, H, W, heads, ws, shift)
+    q, k, v = qkv.float().view(B * nW, L, 3, heads, 32).permute(2, 0, 3, 1, 4)
+    s = q @ k.transpose(-1, -2) / math.sqrt(32) + bias[None]
+    if shift:
+        s = s.view(B, nW, heads, L, L) + ops.shift_mask(H, W, ws, shift)[None, :, None]
+        s = s.view(B * nW, heads, L, L)
+    ref = (s.softmax(-1) @ v).transpose(1, 2).reshape(B * H * W, C)
+    assert rel(out, ref) < (1e-2 if dtype == torch.bfloat16 else 1e-5)
+
+
+@pytest.mark.parametrize("Lq,S", [(52, 52), (3, 49), (3, 3), (1, 8)])
+def test_dense_attention(ops, Lq, S):
+    g = torch.Generator(device="cuda").manual_seed(Lq + S)
+    n, heads = 5, 24
+    D = heads * 32
+    q = torch.randn(n * Lq, D, device="cuda", generator=g)
+    kv = torch.randn(n * S, 2 * D, device="cuda", generator=g)
+    k, v = kv[:, :D], kv[:, D:]
+    scale = math.sqrt(32.0) * 0.1
+    out = ops.attention(q, k, v, n, Lq, S, heads, scale)
+    qh = q.view(n, Lq, heads, 32).transpose(1, 2)
+    kh = k.reshape(n, S, heads, 32).transpose(1, 2)
+    vh = v.reshape(n, S, heads, 32).transpose(1, 2)
+    ref = ((qh @ kh.transpose(-1, -2) * scale).softmax(-1) @ vh).transpose(1, 2).reshape(n * Lq, D)
+    assert rel(out, ref) < 1e-5

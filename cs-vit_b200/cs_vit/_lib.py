@@ -19,6 +19,10 @@ SIGNATURES = {
     "csvit_shift_mask": [c_int, c_int, c_int, c_int, c_void_p, c_void_p],
     "csvit_rel_pos_index": [c_int, c_void_p, c_void_p],
     "csvit_merge_index_map": [c_int, c_int, c_void_p, c_void_p],
+    "csvit_host_window_index_map": [c_int, c_int, c_int, c_int, c_void_p],
+    "csvit_host_shift_mask": [c_int, c_int, c_int, c_int, c_void_p],
+    "csvit_host_rel_pos_index": [c_int, c_void_p],
+    "csvit_host_merge_index_map": [c_int, c_int, c_void_p],
     "csvit_expand_rel_bias": [c_void_p, c_void_p, c_int, c_int, c_void_p],
     "csvit_layernorm": [c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_int, c_longlong, c_int, c_int, c_int,
                         c_int, c_int, c_int, c_int, c_void_p],

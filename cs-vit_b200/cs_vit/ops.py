@@ -200,3 +200,28 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, n_seq: int, Lq:
     _call("csvit_attention", q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), _code(q.dtype), ldq, ldk, ldv, D,
           n_seq, Lq, S, heads, float(scale), _stream())
     return out
+
+
+# ---------------------------------------------------------------------------------------------- host-side maps
+def host_maps(H: int, W: int, ws: int, shift: int):
+    """CPU evaluation of the kernels' closed-form integer maps (same inline functions, compiled for the host).
+    Returns ``(window_index_map [H*W] int32, shift_mask [nW,L,L] fp32)`` as CPU tensors; needs no GPU."""
+    nW, L = (H // ws) * (W // ws), ws * ws
+    idx = torch.empty(H * W, dtype=torch.int32)
+    mask = torch.empty(nW, L, L, dtype=torch.float32)
+    lib = _lib.load()
+    _lib.check(lib.csvit_host_window_index_map(H, W, ws, shift, idx.data_ptr()))
+    _lib.check(lib.csvit_host_shift_mask(H, W, ws, shift, mask.data_ptr()))
+    return idx, mask
+
+
+def host_rel_pos_index(ws: int) -> torch.Tensor:
+    out = torch.empty(ws * ws, ws * ws, dtype=torch.int32)
+    _lib.check(_lib.load().csvit_host_rel_pos_index(ws, out.data_ptr()))
+    return out
+
+
+def host_merge_index_map(H: int, W: int) -> torch.Tensor:
+    out = torch.empty((H // 2) * (W // 2), 4, dtype=torch.int32)
+    _lib.check(_lib.load().csvit_host_merge_index_map(H, W, out.data_ptr()))
+    return out

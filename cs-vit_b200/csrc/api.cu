@@ -54,6 +54,38 @@ int csvit_merge_index_map(int H, int W, int32_t* out, void* stream) {
   CSVIT_REQUIRE(H % 2 == 0 && W % 2 == 0, "merge_index_map: %dx%d must be even", H, W);
   return launch_merge_index_map(H, W, out, S(stream));
 }
+int csvit_host_window_index_map(int H, int W, int ws, int shift, int32_t* out) {
+  CSVIT_REQUIRE(ws > 0 && H % ws == 0 && W % ws == 0, "window_index_map: %dx%d not divisible by window %d", H, W, ws);
+  CSVIT_REQUIRE(shift >= 0 && shift < ws, "window_index_map: shift %d outside [0,%d)", shift, ws);
+  WinGeom g = make_geom(H, W, ws, shift);
+  for (int r = 0; r < g.N; ++r) out[r] = win_row_to_token(g, r);
+  return 0;
+}
+int csvit_host_shift_mask(int H, int W, int ws, int shift, float* out) {
+  CSVIT_REQUIRE(ws > 0 && H % ws == 0 && W % ws == 0, "shift_mask: %dx%d not divisible by window %d", H, W, ws);
+  CSVIT_REQUIRE(shift >= 0 && shift < ws, "shift_mask: shift %d outside [0,%d)", shift, ws);
+  WinGeom g = make_geom(H, W, ws, shift);
+  const int nW = (H / ws) * (W / ws);
+  for (int w = 0; w < nW; ++w)
+    for (int i = 0; i < g.L; ++i)
+      for (int j = 0; j < g.L; ++j)
+        out[(w * g.L + i) * g.L + j] = (shift > 0 && win_region(g, w, i) != win_region(g, w, j)) ? -100.0f : 0.0f;
+  return 0;
+}
+int csvit_host_rel_pos_index(int ws, int32_t* out) {
+  CSVIT_REQUIRE(ws > 0, "rel_pos_index: window %d", ws);
+  const int L = ws * ws;
+  for (int i = 0; i < L; ++i)
+    for (int j = 0; j < L; ++j) out[i * L + j] = rel_pos_index(ws, i, j);
+  return 0;
+}
+int csvit_host_merge_index_map(int H, int W, int32_t* out) {
+  CSVIT_REQUIRE(H % 2 == 0 && W % 2 == 0, "merge_index_map: %dx%d must be even", H, W);
+  for (int t = 0; t < (H / 2) * (W / 2); ++t)
+    for (int q = 0; q < 4; ++q) out[t * 4 + q] = merge_src_token(W, t / (W / 2), t % (W / 2), q);
+  return 0;
+}
+
 int csvit_expand_rel_bias(const float* table, float* out, int heads, int ws, void* stream) {
   CSVIT_REQUIRE(heads > 0 && ws > 0, "expand_rel_bias: heads=%d ws=%d", heads, ws);
   return launch_expand_rel_bias(table, out, heads, ws, S(stream));

@@ -53,6 +53,13 @@ CSVIT_API int csvit_shift_mask(int H, int W, int ws, int shift, float* out, void
 CSVIT_API int csvit_rel_pos_index(int ws, int32_t* out, void* stream);
 CSVIT_API int csvit_merge_index_map(int H, int W, int32_t* out, void* stream);
 
+/* Host evaluation of the very same inline functions (HOST output pointers, no GPU needed): lets the CPU test
+ * suite pin the integer logic that the kernels compile in. */
+CSVIT_API int csvit_host_window_index_map(int H, int W, int ws, int shift, int32_t* out);
+CSVIT_API int csvit_host_shift_mask(int H, int W, int ws, int shift, float* out);
+CSVIT_API int csvit_host_rel_pos_index(int ws, int32_t* out);
+CSVIT_API int csvit_host_merge_index_map(int H, int W, int32_t* out);
+
 /* bias[h, i, j] = table[rel_pos_index(i, j), h]; table is [(2ws-1)^2, heads] fp32.      HF:428-434 */
 CSVIT_API int csvit_expand_rel_bias(const float* table, float* out, int heads, int ws, void* stream);
 

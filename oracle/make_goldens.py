@@ -54,13 +54,15 @@ OUT_KEYS = ("joint_cam", "verts_cam", "pose_aa", "shape", "root_transl_norm", "r
 
 
 def state_checksum(sd) -> str:
-    """Order-independent digest of a state_dict (float tensors rounded through float64 sums)."""
+    """Digest of a dict of tensors that is exact and independent of reduction order / thread count:
+    float tensors are summed as their int32 bit patterns in int64."""
     h = hashlib.sha256()
     for k in sorted(sd):
-        v = sd[k].detach().double()
+        v = sd[k].detach().cpu().contiguous()
+        bits = v.float().view(torch.int32) if v.is_floating_point() else v
         h.update(k.encode())
-        h.update(np.float64(v.sum().item()).tobytes())
-        h.update(np.float64(v.abs().sum().item()).tobytes())
+        h.update(str(int(bits.to(torch.int64).sum().item())).encode())
+        h.update(str(int((bits.to(torch.int64) & 0xFFFF).mul(3).sum().item())).encode())
     return h.hexdigest()[:16]
 
 
@@ -126,9 +128,10 @@ def pass_reference(workdir: str) -> None:
     assert torch.equal(rel_index, swin.relative_position_index(7))
     ints["rel_index_7"] = rel_index.numpy().astype(np.int32)
     for H in (56, 28, 14):
-        x = torch.arange(H * H, dtype=torch.float32).reshape(1, H * H, 1)
-        g = x.reshape(1, H, H, 1)
-        cat = torch.cat([g[:, 0::2, 0::2], g[:, 1::2, 0::2], g[:, 0::2, 1::2], g[:, 1::2, 1::2]], -1).reshape(-1, 4)
+        # HF's own SwinPatchMerging with its norm and reduction replaced by identities exposes the concat order
+        pm = hf.SwinPatchMerging((H, H), dim=1)
+        pm.norm, pm.reduction = torch.nn.Identity(), torch.nn.Identity()
+        cat = pm(torch.arange(H * H, dtype=torch.float32).reshape(1, H * H, 1), (H, H)).reshape(-1, 4)
         assert torch.equal(cat.long(), swin.merge_gather_index(H, H))
         ints[f"merge_{H}"] = cat.numpy().astype(np.int32)
     np.savez_compressed(os.path.join(GOLDEN, "integer_maps.npz"), **ints)

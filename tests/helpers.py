@@ -28,12 +28,15 @@ def backbone_dir(variant: str) -> str:
 
 
 def state_checksum(sd) -> str:
+    """Digest of a dict of tensors that is exact and independent of reduction order / thread count:
+    float tensors are summed as their int32 bit patterns in int64."""
     h = hashlib.sha256()
     for k in sorted(sd):
-        v = sd[k].detach().double().cpu()
+        v = sd[k].detach().cpu().contiguous()
+        bits = v.float().view(torch.int32) if v.is_floating_point() else v
         h.update(k.encode())
-        h.update(np.float64(v.sum().item()).tobytes())
-        h.update(np.float64(v.abs().sum().item()).tobytes())
+        h.update(str(int(bits.to(torch.int64).sum().item())).encode())
+        h.update(str(int((bits.to(torch.int64) & 0xFFFF).mul(3).sum().item())).encode())
     return h.hexdigest()[:16]
 
 

@@ -201,8 +201,8 @@ class CrossAttnDecoder(_KernelModule):
 
 
 def set_precision(module: nn.Module, precision: str) -> None:
-    if precision not in ("bf16", "fp32"):
-        raise ValueError(f"precision must be 'bf16' or 'fp32', got {precision!r}")
+    if precision not in ("bf16", "fp16", "fp32"):
+        raise ValueError(f"precision must be 'bf16', 'fp16' or 'fp32', got {precision!r}")
     for m in module.modules():
         if isinstance(m, _KernelModule) or hasattr(m, "precision"):
             m.precision = precision

@@ -226,7 +226,8 @@ class Poser(nn.Module):
 
     # ------------------------------------------------------------------------------------------ modes
     def set_precision(self, precision: str) -> None:
-        """"bf16": bf16 backbone operands + TF32 head (production).  "fp32": exact fp32 everywhere (validation)."""
+        """"bf16" / "fp16": that operand format in the backbone's tensor-core GEMMs + TF32 head (production).
+        "fp32": exact fp32 everywhere (validation)."""
         set_precision(self, precision)
         self.backbone.precision = precision
         self.precision = precision

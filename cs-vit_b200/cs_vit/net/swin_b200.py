@@ -10,8 +10,10 @@ ATen math: per block it issues
     LN+shift+partition gather -> QKV GEMM -> window attention -> out-proj GEMM with un-shift scatter + residual
     LN -> fc1 GEMM with GELU epilogue -> fc2 GEMM with residual epilogue
 
-on ``libcsvit_sm100.so``.  The residual stream stays fp32 in HBM; GEMM operands are bf16 (``precision="bf16"``)
-or everything is exact fp32 (``precision="fp32"``, the validation mode for the 1e-4 bar).
+on ``libcsvit_sm100.so``.  The residual stream, LayerNorm statistics, softmax and GELU stay fp32.  ``precision``
+picks the tensor-core operand format: ``"bf16"`` (8-bit mantissa) or ``"fp16"`` (11-bit mantissa, identical MMA
+rate; features land ~8x closer to the fp32 reference, which the sharp-softmax head needs, DESIGN.md "Numerics"),
+or ``"fp32"`` = exact fp32 FMA everywhere (validation mode for the 1e-4 bar).
 """
 from __future__ import annotations
 
@@ -25,6 +27,9 @@ import torch.nn as nn
 
 from .. import ops
 from ._pack import PackCache
+
+
+PRECISIONS = {"bf16": torch.bfloat16, "fp16": torch.float16, "fp32": torch.float32}
 
 
 class SwinConfigLite(SimpleNamespace):
@@ -143,15 +148,20 @@ class SwinBackboneB200(nn.Module):
     # ------------------------------------------------------------------------------------------ packing
     @property
     def _fp32(self) -> bool:
-        if self.precision not in ("bf16", "fp32"):
-            raise ValueError(f"precision must be 'bf16' or 'fp32', got {self.precision!r}")
+        if self.precision not in PRECISIONS:
+            raise ValueError(f"precision must be one of {sorted(PRECISIONS)}, got {self.precision!r}")
         return self.precision == "fp32"
+
+    @property
+    def _act_dtype(self) -> torch.dtype:
+        _ = self._fp32
+        return PRECISIONS[self.precision]
 
     def _w(self, key: str, tensors, build):
         return self._pack.get(f"{self.precision}/{key}", tensors, build)
 
     def _weight(self, key: str, lin_weight: torch.Tensor) -> torch.Tensor:
-        dt = torch.float32 if self._fp32 else torch.bfloat16
+        dt = self._act_dtype
         return self._w(key, [lin_weight], lambda: lin_weight.detach().reshape(lin_weight.shape[0], -1).to(dt).contiguous())
 
     def _f32(self, key: str, t: torch.Tensor) -> torch.Tensor:
@@ -164,7 +174,7 @@ class SwinBackboneB200(nn.Module):
         ws = cfg.window_size
         if min(H, W) <= ws:  # HF:548-554
             ws, shift = min(H, W), 0
-        act = torch.float32 if self._fp32 else torch.bfloat16
+        act = self._act_dtype
         impl = ops.GEMM_SIMT if self._fp32 else ops.GEMM_TC
         sa = blk.attention.self
         qkv_src = [sa.query.weight, sa.key.weight, sa.value.weight]
@@ -200,7 +210,7 @@ class SwinBackboneB200(nn.Module):
         n, _, S, S2 = images.shape
         if S != S2 or S % (32 * cfg.window_size) != 0:
             raise ValueError(f"image side {S} must be a multiple of {32 * cfg.window_size} (no padding path, SURVEY.md §8b)")
-        act = torch.float32 if self._fp32 else torch.bfloat16
+        act = self._act_dtype
         impl = ops.GEMM_SIMT if self._fp32 else ops.GEMM_TC
         eps = cfg.layer_norm_eps
         H = W = S // 4

@@ -12,12 +12,12 @@ import torch
 
 from . import _lib
 
-F32, BF16 = 0, 1
+F32, BF16, F16 = 0, 1, 2
 ACT_NONE, ACT_GELU, ACT_RELU = 0, 1, 2
 LN_IDENTITY, LN_WINDOW, LN_MERGE2X2 = 0, 1, 2
 GEMM_TC, GEMM_SIMT = 0, 1
 
-_DT = {torch.float32: F32, torch.bfloat16: BF16}
+_DT = {torch.float32: F32, torch.bfloat16: BF16, torch.float16: F16}
 
 # Count of kernel launches issued through this module (bench.py reports it as `gpu_launches`).
 launch_count = 0
@@ -27,7 +27,7 @@ def _code(dtype: torch.dtype) -> int:
     try:
         return _DT[dtype]
     except KeyError:
-        raise TypeError(f"cs_vit kernels take float32 or bfloat16 tensors, got {dtype}") from None
+        raise TypeError(f"cs_vit kernels take float32, bfloat16 or float16 tensors, got {dtype}") from None
 
 
 def _dev(*tensors: Optional[torch.Tensor]) -> None:

@@ -24,7 +24,8 @@ const char* last_error() { return g_err; }
 
 using namespace csvit;
 
-static_assert(int(CSVIT_F32) == int(DT_F32) && int(CSVIT_BF16) == int(DT_BF16), "dtype codes");
+static_assert(int(CSVIT_F32) == int(DT_F32) && int(CSVIT_BF16) == int(DT_BF16) && int(CSVIT_F16) == int(DT_F16), "dtype codes");
+static inline bool ok_dtype(int d) { return d == DT_F32 || d == DT_BF16 || d == DT_F16; }
 static_assert(int(CSVIT_ACT_GELU) == int(ACT_GELU) && int(CSVIT_ACT_RELU) == int(ACT_RELU), "activation codes");
 static_assert(int(CSVIT_LN_WINDOW) == int(LN_WINDOW) && int(CSVIT_LN_MERGE2X2) == int(LN_MERGE2X2), "layernorm modes");
 static_assert(int(CSVIT_GEMM_SIMT_FP32) == int(GEMM_SIMT), "gemm impl codes");
@@ -93,7 +94,7 @@ int csvit_expand_rel_bias(const float* table, float* out, int heads, int ws, voi
 
 int csvit_layernorm(const float* x, const float* gamma, const float* beta, float eps, void* out, int out_dtype,
                     long long ldo, int rows, int C, int mode, int H, int W, int ws, int shift, void* stream) {
-  CSVIT_REQUIRE(out_dtype == DT_F32 || out_dtype == DT_BF16, "layernorm: bad out_dtype %d", out_dtype);
+  CSVIT_REQUIRE(ok_dtype(out_dtype), "layernorm: bad out_dtype %d", out_dtype);
   WinGeom g = make_geom(H > 0 ? H : 1, W > 0 ? W : 1, ws > 0 ? ws : 1, shift);
   if (mode == LN_WINDOW) {
     CSVIT_REQUIRE(ws > 0 && H % ws == 0 && W % ws == 0, "layernorm(window): %dx%d not divisible by window %d", H, W, ws);
@@ -110,21 +111,21 @@ int csvit_layernorm(const float* x, const float* gamma, const float* beta, float
 
 int csvit_affine_rows(const float* x, const float* scale, const float* shift, void* out, int out_dtype, long long rows,
                       int C, void* stream) {
-  CSVIT_REQUIRE(out_dtype == DT_F32 || out_dtype == DT_BF16, "affine_rows: bad out_dtype %d", out_dtype);
+  CSVIT_REQUIRE(ok_dtype(out_dtype), "affine_rows: bad out_dtype %d", out_dtype);
   return launch_affine_rows(x, scale, shift, out, out_dtype, rows, C, S(stream));
 }
 
 int csvit_patch_im2col(const float* img, void* out, int out_dtype, int B, int S_, const float* mean3, const float* std3,
                        void* stream) {
-  CSVIT_REQUIRE(out_dtype == DT_F32 || out_dtype == DT_BF16, "patch_im2col: bad out_dtype %d", out_dtype);
+  CSVIT_REQUIRE(ok_dtype(out_dtype), "patch_im2col: bad out_dtype %d", out_dtype);
   return launch_patch_im2col(img, out, out_dtype, B, S_, mean3, std3, S(stream));
 }
 
 int csvit_linear(const void* A, long long lda, const void* W, long long ldw, int in_dtype, int M, int N, int K,
                  const float* bias, int act, const float* resid, long long ldr, void* out, long long ldo, int out_dtype,
                  int scatter_H, int scatter_W, int scatter_ws, int scatter_shift, int impl, void* stream) {
-  CSVIT_REQUIRE(in_dtype == DT_F32 || in_dtype == DT_BF16, "linear: bad in_dtype %d", in_dtype);
-  CSVIT_REQUIRE(out_dtype == DT_F32 || out_dtype == DT_BF16, "linear: bad out_dtype %d", out_dtype);
+  CSVIT_REQUIRE(ok_dtype(in_dtype), "linear: bad in_dtype %d", in_dtype);
+  CSVIT_REQUIRE(ok_dtype(out_dtype), "linear: bad out_dtype %d", out_dtype);
   CSVIT_REQUIRE(act >= ACT_NONE && act <= ACT_RELU, "linear: bad activation %d", act);
   CSVIT_REQUIRE(lda >= K && ldw >= K && ldo >= N, "linear: pitches smaller than the logical widths");
   EpiParams ep{};
@@ -145,9 +146,8 @@ int csvit_linear(const void* A, long long lda, const void* W, long long ldw, int
 int csvit_window_attention(const void* qkv, const float* bias, void* out, int dtype, int B, int H, int W, int C, int heads,
                            int ws, int shift, void* stream) {
   CSVIT_REQUIRE(bias != nullptr, "window_attention: bias table required");
-  if (dtype == DT_BF16)
-    return launch_window_attention_mma(static_cast<const __nv_bfloat16*>(qkv), bias, static_cast<__nv_bfloat16*>(out), B, H,
-                                       W, C, heads, ws, shift, S(stream));
+  if (dtype == DT_BF16 || dtype == DT_F16)
+    return launch_window_attention_mma(qkv, bias, out, dtype, B, H, W, C, heads, ws, shift, S(stream));
   CSVIT_REQUIRE(dtype == DT_F32, "window_attention: bad dtype %d", dtype);
   CSVIT_REQUIRE(C == heads * 32, "window_attention: head_dim must be 32 (C=%d heads=%d)", C, heads);
   CSVIT_REQUIRE(H % ws == 0 && W % ws == 0, "window_attention: %dx%d not divisible by window %d", H, W, ws);
@@ -159,7 +159,7 @@ int csvit_window_attention(const void* qkv, const float* bias, void* out, int dt
 
 int csvit_attention(const void* q, const void* k, const void* v, void* out, int dtype, long long ldq, long long ldk,
                     long long ldv, long long ldo, int n_seq, int Lq, int S_, int heads, float scale, void* stream) {
-  CSVIT_REQUIRE(dtype == DT_F32 || dtype == DT_BF16, "attention: bad dtype %d", dtype);
+  CSVIT_REQUIRE(ok_dtype(dtype), "attention: bad dtype %d", dtype);
   return launch_attention_simt(q, k, v, out, dtype, ldq, ldk, ldv, ldo, n_seq, Lq, S_, heads, scale, nullptr, 0, 0, 0, 0,
                                S(stream));
 }

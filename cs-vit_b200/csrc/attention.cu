@@ -10,6 +10,8 @@
 //     the CS-ViT head's MHA (ref:cs_vit/net/transformer_module.py:250-282) whose logits are MULTIPLIED by
 //     sqrt(head_dim) (line 273, quirk Q1: near-argmax softmax, kept in fp32 on purpose), and the fp32
 //     validation mode of (1).
+#include <type_traits>
+
 #include "errors.h"
 #include "rowops.cuh"
 
@@ -28,21 +30,29 @@ __device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], const void* p) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(smem_u32(p)));
 }
-__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+template <typename T>
+__device__ __forceinline__ void mma_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  if constexpr (sizeof(T) == 2 && std::is_same<T, __half>::value) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+  } else {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+  }
 }
 
 // One CTA (4 warps) per (window, head) work item, grid-stride.  Warp w owns query rows 16w..16w+15.
 // qkv: window-ordered tokens [B*N, 3C] (Q | K | V column blocks), out: [B*N, C] window-ordered.
+template <typename T>
 __global__ void __launch_bounds__(128)
-win_attn_mma_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restrict__ bias_exp,
-                    __nv_bfloat16* __restrict__ out, int num_items, int C, int heads, WinGeom g, int nW, float scale) {
+win_attn_mma_kernel(const T* __restrict__ qkv, const float* __restrict__ bias_exp,
+                    T* __restrict__ out, int num_items, int C, int heads, WinGeom g, int nW, float scale) {
   constexpr int L = 49;
-  __shared__ __align__(16) __nv_bfloat16 Qs[64 * WA_LD];
-  __shared__ __align__(16) __nv_bfloat16 Ks[64 * WA_LD];
-  __shared__ __align__(16) __nv_bfloat16 Vs[64 * WA_LD];
+  __shared__ __align__(16) T Qs[64 * WA_LD];
+  __shared__ __align__(16) T Ks[64 * WA_LD];
+  __shared__ __align__(16) T Vs[64 * WA_LD];
   __shared__ int region_s[64];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -64,7 +74,7 @@ win_attn_mma_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restri
       int which = idx / (L * 4), rem = idx - which * (L * 4);
       int r = rem >> 2, ch = rem & 3;
       const uint4 v = *reinterpret_cast<const uint4*>(qkv + (row0 + r) * ld_qkv + which * C + h * 32 + ch * 8);
-      __nv_bfloat16* dst = which == 0 ? Qs : (which == 1 ? Ks : Vs);
+      T* dst = which == 0 ? Qs : (which == 1 ? Ks : Vs);
       *reinterpret_cast<uint4*>(dst + r * WA_LD + ch * 8) = v;
     }
     if (g.shift > 0 && tid < L) region_s[tid] = win_region(g, w, tid);
@@ -82,8 +92,8 @@ win_attn_mma_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restri
       s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
       uint32_t kb[4];
       ldsm_x4(kb, Ks + (j * 8 + (lane & 7)) * WA_LD + (lane >> 3) * 8);
-      mma_bf16_16816(s[j], qa[0], kb[0], kb[1]);
-      mma_bf16_16816(s[j], qa[1], kb[2], kb[3]);
+      mma_16816<T>(s[j], qa[0], kb[0], kb[1]);
+      mma_16816<T>(s[j], qa[1], kb[2], kb[3]);
     }
     // ---- scale + bias + mask, softmax over the 49 keys (fp32) ----
     const int r0 = m0 + (lane >> 2), r1 = r0 + 8;
@@ -132,11 +142,11 @@ win_attn_mma_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restri
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) {
       uint32_t pa[4];
-      pa[0] = pack_bf16x2(s[2 * kk][0] * inv0, s[2 * kk][1] * inv0);
-      pa[1] = pack_bf16x2(s[2 * kk][2] * inv1, s[2 * kk][3] * inv1);
+      pa[0] = Half16<T>::pack(s[2 * kk][0] * inv0, s[2 * kk][1] * inv0);
+      pa[1] = Half16<T>::pack(s[2 * kk][2] * inv1, s[2 * kk][3] * inv1);
       if (2 * kk + 1 < 7) {
-        pa[2] = pack_bf16x2(s[2 * kk + 1][0] * inv0, s[2 * kk + 1][1] * inv0);
-        pa[3] = pack_bf16x2(s[2 * kk + 1][2] * inv1, s[2 * kk + 1][3] * inv1);
+        pa[2] = Half16<T>::pack(s[2 * kk + 1][0] * inv0, s[2 * kk + 1][1] * inv0);
+        pa[3] = Half16<T>::pack(s[2 * kk + 1][2] * inv1, s[2 * kk + 1][3] * inv1);
       } else {
         pa[2] = 0u; pa[3] = 0u;
       }
@@ -144,21 +154,21 @@ win_attn_mma_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restri
       for (int np = 0; np < 2; ++np) {
         uint32_t vb[4];
         ldsm_x4_t(vb, Vs + (kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * WA_LD + np * 16 + (lane >> 4) * 8);
-        mma_bf16_16816(o[2 * np], pa, vb[0], vb[1]);
-        mma_bf16_16816(o[2 * np + 1], pa, vb[2], vb[3]);
+        mma_16816<T>(o[2 * np], pa, vb[0], vb[1]);
+        mma_16816<T>(o[2 * np + 1], pa, vb[2], vb[3]);
       }
     }
     // ---- store (head merge folded into the column offset) ----
 #pragma unroll
     for (int n = 0; n < 4; ++n) {
       const int col = h * 32 + n * 8 + (lane & 3) * 2;
-      if (r0 < L) *reinterpret_cast<uint32_t*>(out + (row0 + r0) * C + col) = pack_bf16x2(o[n][0], o[n][1]);
-      if (r1 < L) *reinterpret_cast<uint32_t*>(out + (row0 + r1) * C + col) = pack_bf16x2(o[n][2], o[n][3]);
+      if (r0 < L) *reinterpret_cast<uint32_t*>(out + (row0 + r0) * C + col) = Half16<T>::pack(o[n][0], o[n][1]);
+      if (r1 < L) *reinterpret_cast<uint32_t*>(out + (row0 + r1) * C + col) = Half16<T>::pack(o[n][2], o[n][3]);
     }
   }
 }
 
-int launch_window_attention_mma(const __nv_bfloat16* qkv, const float* bias_exp, __nv_bfloat16* out, int B, int H, int W,
+int launch_window_attention_mma(const void* qkv, const float* bias_exp, void* out, int dtype, int B, int H, int W,
                                 int C, int heads, int ws, int shift, cudaStream_t stream) {
   CSVIT_REQUIRE(ws == 7, "window_attention(bf16): only window 7 is built (got %d)", ws);
   CSVIT_REQUIRE(C == heads * 32, "window_attention(bf16): head_dim must be 32 (C=%d heads=%d)", C, heads);
@@ -169,8 +179,13 @@ int launch_window_attention_mma(const __nv_bfloat16* qkv, const float* bias_exp,
   CSVIT_REQUIRE(items < (1ll << 31), "window_attention: too many work items");
   WinGeom g = make_geom(H, W, ws, shift);
   int blocks = static_cast<int>(items < 148 * 12 ? items : 148 * 12);
-  win_attn_mma_kernel<<<blocks, 128, 0, stream>>>(qkv, bias_exp, out, static_cast<int>(items), C, heads, g, nW,
-                                                    0.17677669529663687f /* 1/sqrt(32) */);
+  const float scale = 0.17677669529663687f;  // 1/sqrt(32)
+  if (dtype == DT_BF16)
+    win_attn_mma_kernel<__nv_bfloat16><<<blocks, 128, 0, stream>>>(static_cast<const __nv_bfloat16*>(qkv), bias_exp,
+        static_cast<__nv_bfloat16*>(out), static_cast<int>(items), C, heads, g, nW, scale);
+  else
+    win_attn_mma_kernel<__half><<<blocks, 128, 0, stream>>>(static_cast<const __half*>(qkv), bias_exp,
+        static_cast<__half*>(out), static_cast<int>(items), C, heads, g, nW, scale);
   CSVIT_CUDA(cudaGetLastError());
   return 0;
 }
@@ -181,9 +196,11 @@ int launch_window_attention_mma(const __nv_bfloat16* qkv, const float* bias_exp,
 template <typename T> __device__ __forceinline__ float to_f(T v);
 template <> __device__ __forceinline__ float to_f<float>(float v) { return v; }
 template <> __device__ __forceinline__ float to_f<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <> __device__ __forceinline__ float to_f<__half>(__half v) { return __half2float(v); }
 template <typename T> __device__ __forceinline__ T from_f(float v);
 template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
 template <> __device__ __forceinline__ __nv_bfloat16 from_f<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+template <> __device__ __forceinline__ __half from_f<__half>(float v) { return __float2half_rn(v); }
 
 constexpr int SA_MAXS = 64;
 constexpr int SA_HD = 32;
@@ -255,7 +272,11 @@ int launch_attention_simt(const void* q, const void* k, const void* v, void* out
   int nW = mshift > 0 ? (mH / mws) * (mW / mws) : 1;
   if (mshift > 0) CSVIT_REQUIRE(S == mws * mws && Lq == S, "attention_simt: window mask needs Lq == S == ws^2");
   int blocks = static_cast<int>(items < 148 * 16 ? items : 148 * 16);
-  if (dtype == DT_BF16)
+  if (dtype == DT_F16)
+    attention_simt_kernel<__half><<<blocks, 128, 0, stream>>>(
+        static_cast<const __half*>(q), static_cast<const __half*>(k), static_cast<const __half*>(v),
+        static_cast<__half*>(out), ldq, ldk, ldv, ldo, static_cast<int>(items), Lq, S, heads, scale, bias, g, nW);
+  else if (dtype == DT_BF16)
     attention_simt_kernel<__nv_bfloat16><<<blocks, 128, 0, stream>>>(
         static_cast<const __nv_bfloat16*>(q), static_cast<const __nv_bfloat16*>(k), static_cast<const __nv_bfloat16*>(v),
         static_cast<__nv_bfloat16*>(out), ldq, ldk, ldv, ldo, static_cast<int>(items), Lq, S, heads, scale, bias, g, nW);

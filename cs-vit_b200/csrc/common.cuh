@@ -8,6 +8,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -80,6 +81,23 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
 }
+
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  __half2 v = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+// 16-bit operand formats of the tensor-core path: bf16 (8-bit mantissa) and fp16 (11-bit mantissa, same MMA rate).
+template <typename T> struct Half16;
+template <> struct Half16<__nv_bfloat16> {
+  static __device__ __forceinline__ uint32_t pack(float lo, float hi) { return pack_bf16x2(lo, hi); }
+  static __device__ __forceinline__ __nv_bfloat16 from(float v) { return __float2bfloat16_rn(v); }
+  static __device__ __forceinline__ float to(__nv_bfloat16 v) { return __bfloat162float(v); }
+};
+template <> struct Half16<__half> {
+  static __device__ __forceinline__ uint32_t pack(float lo, float hi) { return pack_f16x2(lo, hi); }
+  static __device__ __forceinline__ __half from(float v) { return __float2half_rn(v); }
+  static __device__ __forceinline__ float to(__half v) { return __half2float(v); }
+};
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -215,8 +233,8 @@ __device__ __forceinline__ uint64_t make_sw128_kmajor_desc(uint32_t smem_addr) {
 }
 
 // Instruction descriptor for kind::f16 / kind::tf32, fp32 accumulate, both operands K-major.
-__host__ __device__ constexpr uint32_t make_idesc(bool tf32, int M, int N) {
-  uint32_t fmt = tf32 ? 2u : 1u;  // 1 = BF16, 2 = TF32
+__host__ __device__ constexpr uint32_t make_idesc(uint32_t fmt, int M, int N) {
+  // fmt: 0 = F16, 1 = BF16, 2 = TF32
   return (1u << 4)                 // c_format = F32
          | (fmt << 7)              // a_format
          | (fmt << 10)             // b_format

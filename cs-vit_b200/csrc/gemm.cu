@@ -34,10 +34,11 @@ struct TcCfg {
   static constexpr size_t SMEM = 1024 + size_t(STAGES) * STAGE_BYTES + 256;
 };
 
-template <int BN, bool TF32>
+template <int BN, int FMT>  // FMT: 0 = fp16, 1 = bf16, 2 = tf32 operands (UMMA format codes)
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int K, EpiParams ep) {
   using Cfg = TcCfg<BN>;
+  constexpr bool TF32 = FMT == 2;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int BK = TF32 ? 32 : 64;  // elements per 128-byte swizzled row
 
@@ -92,7 +93,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else if (warp == 1) {
     // ---------------- MMA issuer ----------------
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(TF32, kBM, BN);
+      constexpr uint32_t idesc = make_idesc(uint32_t(FMT), kBM, BN);
       int s = 0; uint32_t ph = 0;
       int as = 0; uint32_t aph = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
@@ -213,14 +214,16 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_tmap_encoder() {
 static int make_operand_tmap(CUtensorMap* tm, const void* ptr, long long ld, int rows, int K, int dtype, int box_rows) {
   auto enc = get_tmap_encoder();
   if (!enc) return set_error("cuTensorMapEncodeTiled entry point not available (driver too old?)");
-  const size_t es = dtype == DT_BF16 ? 2 : 4;
+  const size_t es = dtype_size(dtype);
   if ((reinterpret_cast<uintptr_t>(ptr) & 15) || ((ld * es) & 15))
     return set_error("GEMM operand must be 16-byte aligned with a 16-byte-multiple row pitch (ptr=%p ld=%lld)", ptr, ld);
   cuuint64_t gdim[2] = {cuuint64_t(K), cuuint64_t(rows)};
   cuuint64_t gstr[1] = {cuuint64_t(ld * es)};
   cuuint32_t box[2] = {cuuint32_t(128 / es), cuuint32_t(box_rows)};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(tm, dtype == DT_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 2,
+  const CUtensorMapDataType tdt = dtype == DT_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+                                  : (dtype == DT_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32);
+  CUresult r = enc(tm, tdt, 2,
                    const_cast<void*>(ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%d K=%d ld=%lld)", int(r), rows, K, ld);
@@ -238,11 +241,11 @@ static int num_sms() {
   return g_num_sms;
 }
 
-template <int BN, bool TF32>
+template <int BN, int FMT>
 static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, int K, const EpiParams& ep, int max_ctas, cudaStream_t stream) {
   using Cfg = TcCfg<BN>;
   static bool configured = false;
-  auto kern = gemm_tc_kernel<BN, TF32>;
+  auto kern = gemm_tc_kernel<BN, FMT>;
   if (!configured) {
     CSVIT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(Cfg::SMEM)));
     configured = true;
@@ -260,7 +263,7 @@ int launch_gemm(const void* A, long long lda, const void* W, long long ldw, int 
   if (M <= 0 || N <= 0 || K <= 0) return 0;
   EpiParams ep = ep_in;
   ep.M = M; ep.N = N;
-  const size_t oes = ep.out_dtype == DT_BF16 ? 2 : 4;
+  const size_t oes = dtype_size(ep.out_dtype);
   ep.vec_ok = (N % 8 == 0) && ((ep.ldo * oes) % 16 == 0) && ((reinterpret_cast<uintptr_t>(ep.out) & 15) == 0) &&
               (!ep.resid || ((ep.ldr % 4 == 0) && (reinterpret_cast<uintptr_t>(ep.resid) & 15) == 0)) &&
               (!ep.bias || (reinterpret_cast<uintptr_t>(ep.bias) & 15) == 0);
@@ -280,9 +283,14 @@ int launch_gemm(const void* A, long long lda, const void* W, long long ldw, int 
   CUtensorMap tmA, tmB;
   if (int e = make_operand_tmap(&tmA, A, lda, M, K, in_dtype, kBM)) return e;
   if (int e = make_operand_tmap(&tmB, W, ldw, N, K, in_dtype, BN)) return e;
-  const bool tf32 = in_dtype == DT_F32;
-  if (BN == 256) return tf32 ? launch_tc<256, true>(tmA, tmB, K, ep, max_ctas, stream) : launch_tc<256, false>(tmA, tmB, K, ep, max_ctas, stream);
-  return tf32 ? launch_tc<128, true>(tmA, tmB, K, ep, max_ctas, stream) : launch_tc<128, false>(tmA, tmB, K, ep, max_ctas, stream);
+  if (BN == 256) {
+    if (in_dtype == DT_F32) return launch_tc<256, 2>(tmA, tmB, K, ep, max_ctas, stream);
+    if (in_dtype == DT_BF16) return launch_tc<256, 1>(tmA, tmB, K, ep, max_ctas, stream);
+    return launch_tc<256, 0>(tmA, tmB, K, ep, max_ctas, stream);
+  }
+  if (in_dtype == DT_F32) return launch_tc<128, 2>(tmA, tmB, K, ep, max_ctas, stream);
+  if (in_dtype == DT_BF16) return launch_tc<128, 1>(tmA, tmB, K, ep, max_ctas, stream);
+  return launch_tc<128, 0>(tmA, tmB, K, ep, max_ctas, stream);
 }
 
 }  // namespace csvit

@@ -7,7 +7,8 @@ namespace csvit {
 
 enum : int { ACT_NONE = 0, ACT_GELU = 1, ACT_RELU = 2 };
 enum : int { ROWMAP_IDENTITY = 0, ROWMAP_WINDOW = 1 };
-enum : int { DT_F32 = 0, DT_BF16 = 1 };
+enum : int { DT_F32 = 0, DT_BF16 = 1, DT_F16 = 2 };
+__host__ __device__ inline int dtype_size(int dt) { return dt == DT_F32 ? 4 : 2; }
 
 // What happens to one accumulator row-chunk after the MMA:
 //   v = acc (+ bias[col]) -> act -> (+ resid[orow, col]) -> out[orow, col]  (fp32 or bf16)
@@ -48,6 +49,8 @@ __device__ __forceinline__ void epi_store_scalar(const EpiParams& ep, long long 
   if (ep.resid) v += ep.resid[orow * ep.ldr + col];
   if (ep.out_dtype == DT_BF16)
     reinterpret_cast<__nv_bfloat16*>(ep.out)[orow * ep.ldo + col] = __float2bfloat16_rn(v);
+  else if (ep.out_dtype == DT_F16)
+    reinterpret_cast<__half*>(ep.out)[orow * ep.ldo + col] = __float2half_rn(v);
   else
     reinterpret_cast<float*>(ep.out)[orow * ep.ldo + col] = v;
 }
@@ -81,15 +84,16 @@ __device__ __forceinline__ void epi_store_chunk32(const EpiParams& ep, long long
         v[4 * j + 0] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
       }
     }
-    if (ep.out_dtype == DT_BF16) {
-      uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(ep.out) + orow * ep.ldo + col0);
+    if (ep.out_dtype != DT_F32) {
+      uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(ep.out) + orow * ep.ldo + col0);
+      const bool bf = ep.out_dtype == DT_BF16;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         uint4 q;
-        q.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
-        q.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
-        q.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
-        q.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+        q.x = bf ? pack_bf16x2(v[8 * j + 0], v[8 * j + 1]) : pack_f16x2(v[8 * j + 0], v[8 * j + 1]);
+        q.y = bf ? pack_bf16x2(v[8 * j + 2], v[8 * j + 3]) : pack_f16x2(v[8 * j + 2], v[8 * j + 3]);
+        q.z = bf ? pack_bf16x2(v[8 * j + 4], v[8 * j + 5]) : pack_f16x2(v[8 * j + 4], v[8 * j + 5]);
+        q.w = bf ? pack_bf16x2(v[8 * j + 6], v[8 * j + 7]) : pack_f16x2(v[8 * j + 6], v[8 * j + 7]);
         o[j] = q;
       }
     } else {
@@ -104,7 +108,7 @@ __device__ __forceinline__ void epi_store_chunk32(const EpiParams& ep, long long
   }
 }
 
-// Host launchers (gemm.cu).  a_dtype: DT_BF16 -> tcgen05 kind::f16 (W must be bf16 too);
+// Host launchers (gemm.cu).  in_dtype: DT_BF16 / DT_F16 -> tcgen05 kind::f16 (W in the same format);
 // DT_F32 -> tcgen05 kind::tf32 when impl == GEMM_TC, exact fp32 FMA when impl == GEMM_SIMT.
 enum : int { GEMM_TC = 0, GEMM_SIMT = 1 };
 int launch_gemm(const void* A, long long lda, const void* W, long long ldw, int in_dtype, int M, int N, int K,

@@ -15,6 +15,12 @@ template <typename T> struct Store4;
 template <> struct Store4<float> {
   __device__ static void st(float* p, float a, float b, float c, float d) { *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d); }
 };
+template <> struct Store4<__half> {
+  __device__ static void st(__half* p, float a, float b, float c, float d) {
+    uint2 v; v.x = pack_f16x2(a, b); v.y = pack_f16x2(c, d);
+    *reinterpret_cast<uint2*>(p) = v;
+  }
+};
 template <> struct Store4<__nv_bfloat16> {
   __device__ static void st(__nv_bfloat16* p, float a, float b, float c, float d) {
     uint2 v; v.x = pack_bf16x2(a, b); v.y = pack_bf16x2(c, d);
@@ -107,6 +113,8 @@ int launch_layernorm(const float* x, const float* gamma, const float* beta, floa
   if (rows <= 0) return 0;
   if (out_dtype == DT_BF16)
     return launch_ln_t<__nv_bfloat16>(x, gamma, beta, eps, static_cast<__nv_bfloat16*>(out), ldo, rows, C, mode, g, stream);
+  if (out_dtype == DT_F16)
+    return launch_ln_t<__half>(x, gamma, beta, eps, static_cast<__half*>(out), ldo, rows, C, mode, g, stream);
   return launch_ln_t<float>(x, gamma, beta, eps, static_cast<float*>(out), ldo, rows, C, mode, g, stream);
 }
 
@@ -135,6 +143,8 @@ int launch_affine_rows(const float* x, const float* scale, const float* shift, v
   if (blocks > 148 * 16) blocks = 148 * 16;
   if (out_dtype == DT_BF16)
     affine_rows_kernel<__nv_bfloat16><<<blocks, 256, 0, stream>>>(x, scale, shift, static_cast<__nv_bfloat16*>(out), total4, C / 4);
+  else if (out_dtype == DT_F16)
+    affine_rows_kernel<__half><<<blocks, 256, 0, stream>>>(x, scale, shift, static_cast<__half*>(out), total4, C / 4);
   else
     affine_rows_kernel<float><<<blocks, 256, 0, stream>>>(x, scale, shift, static_cast<float*>(out), total4, C / 4);
   CSVIT_CUDA(cudaGetLastError());
@@ -176,6 +186,8 @@ int launch_patch_im2col(const float* img, void* out, int out_dtype, int B, int S
   const float i0 = 1.0f / std3[0], i1 = 1.0f / std3[1], i2 = 1.0f / std3[2];
   if (out_dtype == DT_BF16)
     patch_im2col_kernel<__nv_bfloat16><<<blocks, 256, 0, stream>>>(img, static_cast<__nv_bfloat16*>(out), B, S, mean3[0], mean3[1], mean3[2], i0, i1, i2);
+  else if (out_dtype == DT_F16)
+    patch_im2col_kernel<__half><<<blocks, 256, 0, stream>>>(img, static_cast<__half*>(out), B, S, mean3[0], mean3[1], mean3[2], i0, i1, i2);
   else
     patch_im2col_kernel<float><<<blocks, 256, 0, stream>>>(img, static_cast<float*>(out), B, S, mean3[0], mean3[1], mean3[2], i0, i1, i2);
   CSVIT_CUDA(cudaGetLastError());

@@ -19,7 +19,7 @@ int launch_merge_index_map(int H, int W, int* out, cudaStream_t stream);
 int launch_expand_rel_bias(const float* table, float* out, int heads, int ws, cudaStream_t stream);
 
 // attention.cu
-int launch_window_attention_mma(const __nv_bfloat16* qkv, const float* bias_exp, __nv_bfloat16* out, int B, int H, int W,
+int launch_window_attention_mma(const void* qkv, const float* bias_exp, void* out, int dtype, int B, int H, int W,
                                 int C, int heads, int ws, int shift, cudaStream_t stream);
 int launch_attention_simt(const void* q, const void* k, const void* v, void* out, int dtype, long long ldq, long long ldk,
                           long long ldv, long long ldo, int n_seq, int Lq, int S, int heads, float scale,

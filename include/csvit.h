@@ -11,7 +11,8 @@
  *     never allocates, frees or retains device memory.  `stream` is a cudaStream_t passed as void*.
  *   - Every function is asynchronous on `stream`, re-entrant, and returns 0 on success.  On failure it
  *     returns non-zero and csvit_last_error() (thread-local) describes why.  Nothing throws.
- *   - dtype codes: CSVIT_F32 = 0, CSVIT_BF16 = 1.  Row-major; `ld*` are row pitches in ELEMENTS.
+ *   - dtype codes: CSVIT_F32 = 0, CSVIT_BF16 = 1, CSVIT_F16 = 2 (the two 16-bit formats are interchangeable
+ *     tensor-core operand formats: same MMA rate, fp16 carries 3 more mantissa bits).  Row-major; `ld*` are row pitches in ELEMENTS.
  *   - There is no CPU path: a missing GPU or a non-sm_100 device surfaces as a CUDA error code.
  */
 #ifndef CSVIT_H_
@@ -31,7 +32,7 @@ extern "C" {
 #define CSVIT_API
 #endif
 
-enum { CSVIT_F32 = 0, CSVIT_BF16 = 1 };
+enum { CSVIT_F32 = 0, CSVIT_BF16 = 1, CSVIT_F16 = 2 };
 enum { CSVIT_ACT_NONE = 0, CSVIT_ACT_GELU = 1, CSVIT_ACT_RELU = 2 };
 enum { CSVIT_LN_IDENTITY = 0, CSVIT_LN_WINDOW = 1, CSVIT_LN_MERGE2X2 = 2 };
 enum { CSVIT_GEMM_TENSORCORE = 0, CSVIT_GEMM_SIMT_FP32 = 1 };
@@ -86,7 +87,7 @@ CSVIT_API int csvit_patch_im2col(const float* img, void* out, int out_dtype, int
 
 /* ---- GEMM engine (tcgen05 + TMEM + TMA) ----------------------------------------------------------------
  * out[orow, :N] = act(A[M,K] @ W[N,K]^T + bias) + resid[orow, :N]
- *   in_dtype CSVIT_BF16: A and W bf16, kind::f16 MMA;  CSVIT_F32: A and W fp32, kind::tf32 MMA
+ *   in_dtype CSVIT_BF16 / CSVIT_F16: A and W in that format, kind::f16 MMA;  CSVIT_F32: A and W fp32, kind::tf32 MMA
  *   (or exact fp32 FMA with impl = CSVIT_GEMM_SIMT_FP32).  fp32 accumulation in all cases.
  *   bias, resid may be NULL.  resid is fp32 with pitch ldr and may alias out (in-place residual add).
  *   scatter_ws > 0: GEMM rows are window-ordered tokens; orow = window_index_map(row) per image of
@@ -102,7 +103,7 @@ CSVIT_API int csvit_linear(const void* A, long long lda, const void* W, long lon
 /* ---- attention cores -------------------------------------------------------------------------------------
  * Swin window attention on window-ordered qkv[B*H*W, 3C] (Q|K|V column blocks, head h at columns 32h..):
  *   out[B*H*W, C] = softmax(Q K^T / sqrt(32) + bias[h] + shift_mask) V, heads merged.       HF:410-459
- * bf16: tensor-core kernel (window 7, head_dim 32).  fp32: exact kernel (validation mode).
+ * bf16 / fp16: tensor-core kernel (window 7, head_dim 32).  fp32: exact kernel (validation mode).
  * bias is the expanded [heads, L, L] fp32 table from csvit_expand_rel_bias. */
 CSVIT_API int csvit_window_attention(const void* qkv, const float* bias, void* out, int dtype, int B, int H, int W, int C,
                            int heads, int ws, int shift, void* stream);

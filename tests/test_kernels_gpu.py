@@ -21,14 +21,15 @@ def ops():
 
 @pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 256, 128), (1000, 384, 128), (12544, 1024, 1024),
                                    (6272, 512, 2048), (200, 96, 48), (77, 10, 1024), (3136 * 2, 1536, 512)])
-@pytest.mark.parametrize("dtype", ["bf16", "tf32", "fp32"])
+@pytest.mark.parametrize("dtype", ["bf16", "fp16", "tf32", "fp32"])
 def test_linear_plain(ops, M, N, K, dtype):
     g = torch.Generator(device="cuda").manual_seed(M * 7 + N * 3 + K)
     a = torch.randn(M, K, device="cuda", generator=g)
     w = torch.randn(N, K, device="cuda", generator=g) * 0.05
     b = torch.randn(N, device="cuda", generator=g)
-    if dtype == "bf16":
-        a_, w_ = a.bfloat16(), w.bfloat16()
+    if dtype in ("bf16", "fp16"):
+        td = torch.bfloat16 if dtype == "bf16" else torch.float16
+        a_, w_ = a.to(td), w.to(td)
         ref = a_.float() @ w_.float().T + b
         out = ops.linear(a_, w_, b, out_dtype=torch.float32)
         tol = 1e-5
@@ -107,7 +108,7 @@ def test_patch_im2col(ops):
 
 
 @pytest.mark.parametrize("H,heads,shift", [(14, 16, 0), (14, 16, 3), (28, 8, 3), (56, 4, 3), (7, 32, 0)])
-@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16, torch.float32])
 def test_window_attention(ops, H, heads, shift, dtype):
     g = torch.Generator(device="cuda").manual_seed(H * heads + shift)
     B, W, C, ws, L = 2, H, heads * 32, 7, 49
@@ -122,7 +123,7 @@ def test_window_attention(ops, H, heads, shift, dtype):
         s = s.view(B, nW, heads, L, L) + ops.shift_mask(H, W, ws, shift)[None, :, None]
         s = s.view(B * nW, heads, L, L)
     ref = (s.softmax(-1) @ v).transpose(1, 2).reshape(B * H * W, C)
-    assert rel(out, ref) < (1e-2 if dtype == torch.bfloat16 else 1e-5)
+    assert rel(out, ref) < {torch.bfloat16: 1e-2, torch.float16: 2e-3, torch.float32: 1e-5}[dtype]
 
 
 @pytest.mark.parametrize("Lq,S", [(52, 52), (3, 49), (3, 3), (1, 8)])

@@ -1,0 +1,335 @@
+#!/usr/bin/env python
+"""Headline benchmark: images/sec of the Swin-B spatial model forward (BASELINE.json configs[1]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision bf16|fp16]
+
+One "step" = one ``Poser.predict_batch`` over a batch of 256 synthetic 224x224 crops per GPU (Swin-B backbone,
+"encoder" spatial head, perspective embedding added to the patches - the ``spatial_dexycb_swinb_spenc_addpat``
+configuration), random-init weights, eval mode.  Data-parallel: every rank owns its own batch, no data-path
+collective, so scaling is weak and ``value`` = all ranks' images / max-over-ranks device time.
+
+Keys beyond the base contract:
+  roofline      the GEMM engine (tcgen05 kernel) timed live with CUDA events on the launch stream in a second,
+                instrumented pass of the same K steps: algorithmic FLOPs (2MNK summed over the launches) /
+                summed launch time, against MEASURED_PEAKS.json's sustained bf16 figure.
+  e2e           same metric through the public API with HOST (pinned) inputs: per step an H2D copy of that
+                step's batch and a D2H read of the predicted joints, double-buffered on a copy stream.
+  cpu_baseline  the oracle port (HF SwinModel + restated head, all six head layers executed like the
+                reference) on the host cores, on a bounded sample, rank 0 at N=1 only.
+  fp16          the same timed loop with fp16 instead of bf16 tensor-core operands (identical MMA rate; the
+                mode whose joints/vertices meet the 1e-2 parity bar, see DESIGN.md "Numerics").
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "cs-vit_b200"))
+
+import torch  # noqa: E402
+
+BATCH = 256
+FLOP_PER_IMAGE = 32.19e9     # BASELINE.md §3 headline numerator (30.860 backbone + 1.320 head layer + 0.010)
+METRIC = "images/sec Swin-B spatial fwd @224^2 bs256"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--precision", choices=["bf16", "fp16"], default="bf16")
+    ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--variant", default="swin_b")
+    ap.add_argument("--cpu-sample", type=int, default=16, help="images per CPU-baseline step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip roofline / e2e / fp16 passes (debug)")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def cpu_reference_rate(variant: str, sample: int, steps: int, warmup: int):
+    """Reference algorithm on the host cores: HF ``SwinModel`` (the third-party code the reference's backbone
+    call executes) + the restated CS-ViT head from oracle/, fp32, inference mode, all available threads."""
+    sys.path.insert(0, ROOT)
+    from cs_vit.net import Poser
+    from cs_vit.synthetic import SWIN_VARIANTS, make_inputs, make_random_backbone_dir, randomize_head_
+    from cs_vit.utils.mano_standin import SyntheticMANO
+    from oracle import head_restated as head
+
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    tmp = tempfile.mkdtemp(prefix="csvit_bench_cpu_")
+    bdir = make_random_backbone_dir(os.path.join(tmp, variant), variant, seed=0)
+    torch.manual_seed(0)
+    model = Poser(bdir, image_size=224, mano_layer=SyntheticMANO(), spatial_layer_type="encoder", persp_decorate="patch")
+    randomize_head_(model)
+    sd = {k: v.detach() for k, v in model.state_dict().items()}
+    _, depths, heads = SWIN_VARIANTS[variant]
+    opt = head.HeadOptions(num_heads=heads[-1], depths=depths, swin_heads=heads, spatial_layer_type="encoder",
+                           persp_decorate="patch", phase="spatial")
+    features_fn, kind_note = None, "oracle restatement of HF Swin"
+    try:
+        import transformers
+        hf = transformers.AutoModel.from_pretrained(bdir).eval()
+        mean = torch.tensor(head.IMAGENET_MEAN)[None, :, None, None]
+        std = torch.tensor(head.IMAGENET_STD)[None, :, None, None]
+        features_fn = lambda x: hf((x - mean) / std).last_hidden_state  # noqa: E731
+        kind_note = f"HF transformers {transformers.__version__} SwinModel"
+    except Exception:
+        pass
+    inputs = make_inputs(sample, 1, 224, seed=0)
+    mano = SyntheticMANO()
+    times = []
+    with torch.inference_mode():
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            head.predict_batch(inputs, sd, opt, mano, features_fn=features_fn, execute_all=True)
+            if i >= warmup:
+                times.append(time.perf_counter() - t0)
+    ms = 1e3 * statistics.median(times)
+    return sample / (ms / 1e3), ms, threads, f"{sample} images/step, fp32, {kind_note} + restated head (6 layers executed), torch {torch.__version__}"
+
+
+def run_reference_arm(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    warm = max(1, min(a.warmup, 2))
+    steps = max(1, min(a.steps, 5))
+    rate, ms, threads, note = cpu_reference_rate(a.variant, a.cpu_sample, steps, warm)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": round(rate, 3), "unit": "images/s", "n_gpus": a.gpus,
+        "steps": steps, "warmup": warm, "ms_per_step": round(ms, 2), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+        "config": {"workload": f"{a.variant} spatial model (encoder head, addpat) forward, CPU sample of {a.cpu_sample} images"},
+        "cpu_baseline": {"value": round(rate, 3), "unit": "images/s", "cores": threads, "kind": "port", "sample": note},
+        "e2e": {"value": round(rate, 3), "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def window(self, t0, t1):
+        sm, mx, reasons = [], 0.0, set()
+        for t, line in self.rows:
+            if t0 <= t <= t1:
+                f = [x.strip() for x in line.split(",")]
+                try:
+                    sm.append(float(f[0])); mx = max(mx, float(f[1]))
+                except (ValueError, IndexError):
+                    continue
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return p["bf16_tflops_sustained"], p["hbm_gbs"], "measured"
+    except Exception:
+        return 1400.0, 6650.0, "fallback"
+
+
+def run_ours(a):
+    import torch.distributed as dist
+    from cs_vit import ops
+    from cs_vit.net import Poser
+    from cs_vit.synthetic import make_inputs, make_random_backbone_dir, randomize_head_
+    from cs_vit.utils.mano_standin import SyntheticMANO
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py (impl ours) needs a CUDA device: there is no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+
+    tmp = tempfile.mkdtemp(prefix=f"csvit_bench_{rank}_")
+    bdir = make_random_backbone_dir(os.path.join(tmp, a.variant), a.variant, seed=0)
+    torch.manual_seed(0)
+    model = Poser(bdir, image_size=224, mano_layer=SyntheticMANO(), spatial_layer_type="encoder", persp_decorate="patch",
+                  precision=a.precision)
+    randomize_head_(model)
+    model.phase(Poser.TrainingPhase.SPATIAL)
+    model.eval()
+    model = model.to(dev)
+
+    host = make_inputs(a.batch, 1, 224, seed=100 + rank)
+    keys = ("patches", "square_bboxes", "timestamp", "focal", "princpt")
+    pinned = {k: host[k].pin_memory() for k in keys}
+    resident = {k: pinned[k].to(dev) for k in keys}
+
+    def step(inp):
+        with torch.no_grad():
+            return model.predict_batch(inp["patches"], inp["square_bboxes"], inp["timestamp"], inp["focal"], inp["princpt"])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed_loop(steps):
+        """K steps on device-resident inputs, CUDA events, max over ranks.  Returns (ms_total, launches)."""
+        barrier()
+        n0 = ops.launch_count
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            step(resident)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        barrier()
+        return ms.item(), ops.launch_count - n0
+
+    for _ in range(a.warmup):
+        step(resident)
+    sampler = ClockSampler(local) if rank == 0 else None
+    t0 = time.perf_counter()
+    ms_total, launches = timed_loop(a.steps)
+    t1 = time.perf_counter()
+    clocks = sampler.window(t0, t1) if sampler else None
+    value = world * a.batch * a.steps / (ms_total / 1e3)
+    peak_tf, peak_gbs, peak_kind = peaks()
+
+    out = {
+        "metric": METRIC, "value": round(value, 1), "unit": "images/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+        "ms_per_step": round(ms_total / a.steps, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": a.precision, "data": "synthetic",
+        "config": {"workload": f"{a.variant} spatial model (encoder head, addpat, dense persp) predict_batch, batch {a.batch}/GPU, 224x224, T=1",
+                   "global_batch": a.batch * world, "parallelism": f"dp{world}",
+                   "l2_policy": "per-step inputs (154 MB) and activations (>1 GB) exceed the 126 MB L2; no explicit flush",
+                   "operands": f"{a.precision} tensor-core operands, fp32 accumulate/residual/LN/softmax, TF32 head"},
+        "gpu_launches": launches,
+        "model_flops_frac_of_peak": round(value / world * FLOP_PER_IMAGE / (peak_tf * 1e12), 4),
+        "clocks": clocks,
+    }
+
+    if not a.no_extras:
+        # ---- roofline of the dominant kernel (GEMM engine), instrumented pass over the same K steps ----------
+        ops.begin_profile("csvit_linear")
+        timed_loop(a.steps)
+        prof = ops.end_profile()
+        if prof["launches"]:
+            ach = prof["flops"] / (prof["ms"] / 1e3) / 1e12
+            out["roofline"] = {"bound": "tensor", "kernel": "gemm_tc_kernel (csvit_linear: every Linear of backbone and head)",
+                               "achieved": round(ach, 1), "peak": peak_tf, "unit": "TFLOP/s", "frac": round(ach / peak_tf, 4),
+                               "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peak_kind})", "traffic": None,
+                               "launches_per_step": prof["launches"] // a.steps,
+                               "share_of_step": round(prof["ms"] / a.steps / (ms_total / a.steps), 3),
+                               "avg_launch_us": round(1e3 * prof["ms"] / prof["launches"], 2)}
+        # ---- end-to-end: host inputs, H2D + D2H inside the timed region, double-buffered ------------------------
+        copy_stream = torch.cuda.Stream(device=dev)
+        bufs = [{k: torch.empty_like(resident[k]) for k in keys} for _ in range(2)]
+        host_out = torch.empty(a.batch, 1, 21, 3).pin_memory()
+        h2d = sum(pinned[k].numel() * pinned[k].element_size() for k in keys)
+
+        def e2e_loop(steps):
+            barrier()
+            main = torch.cuda.current_stream()
+            ready = [torch.cuda.Event(), torch.cuda.Event()]
+            freed = [torch.cuda.Event(), torch.cuda.Event()]
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+
+            def upload(i):
+                with torch.cuda.stream(copy_stream):
+                    if i >= 2:
+                        copy_stream.wait_event(freed[i % 2])
+                    for k in keys:
+                        bufs[i % 2][k].copy_(pinned[k], non_blocking=True)
+                    ready[i % 2].record(copy_stream)
+
+            copy_stream.wait_event(e0)
+            upload(0)
+            for i in range(steps):
+                if i + 1 < steps:
+                    upload(i + 1)
+                main.wait_event(ready[i % 2])
+                res = step(bufs[i % 2])
+                host_out.copy_(res["joint_cam"], non_blocking=True)
+                freed[i % 2].record(main)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+            if world > 1:
+                dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            return ms.item()
+
+        e2e_loop(2)
+        ms_e2e = e2e_loop(a.steps)
+        out["e2e"] = {"value": round(world * a.batch * a.steps / (ms_e2e / 1e3), 1), "unit": "images/s",
+                      "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": host_out.numel() * 4,
+                      "note": "predict_batch on pinned host tensors; H2D on a copy stream overlapped with the previous step's compute"}
+        # ---- the other 16-bit operand format ---------------------------------------------------------------
+        other = "fp16" if a.precision == "bf16" else "bf16"
+        model.set_precision(other)
+        for _ in range(2):
+            step(resident)
+        ms_o, _ = timed_loop(a.steps)
+        out[other] = {"value": round(world * a.batch * a.steps / (ms_o / 1e3), 1), "unit": "images/s",
+                      "ms_per_step": round(ms_o / a.steps, 3)}
+        model.set_precision(a.precision)
+
+    if sampler:
+        sampler.stop()
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        rate, ms, threads, note = cpu_reference_rate(a.variant, a.cpu_sample, 2, 1)
+        out["cpu_baseline"] = {"value": round(rate, 3), "unit": "images/s", "cores": threads, "kind": "port", "sample": note}
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        run_reference_arm(a)
+    else:
+        run_ours(a)
+
+
+if __name__ == "__main__":
+    main()

@@ -44,9 +44,34 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
-def _call(name: str, *args) -> None:
+_profile = None  # {"name": entry point, "events": [(start, stop, flops, bytes)]} while bench.py instruments a kernel
+
+
+def begin_profile(name: str) -> None:
+    """Bracket every launch of C-ABI entry ``name`` with CUDA events on the launch stream (bench.py roofline)."""
+    global _profile
+    _profile = {"name": name, "events": []}
+
+
+def end_profile() -> dict:
+    global _profile
+    prof, _profile = _profile, None
+    torch.cuda.synchronize()
+    ev = prof["events"]
+    return {"launches": len(ev), "ms": sum(a.elapsed_time(b) for a, b, _, _ in ev),
+            "flops": float(sum(f for _, _, f, _ in ev)), "bytes": float(sum(b for _, _, _, b in ev))}
+
+
+def _call(name: str, *args, flops: float = 0.0, nbytes: float = 0.0) -> None:
     global launch_count
     launch_count += 1
+    if _profile is not None and _profile["name"] == name:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _lib.check(getattr(_lib.load(), name)(*args))
+        e1.record()
+        _profile["events"].append((e0, e1, flops, nbytes))
+        return
     _lib.check(getattr(_lib.load(), name)(*args))
 
 
@@ -111,7 +136,8 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: flo
     if out is None:
         out = torch.empty(rows, width, dtype=out_dtype, device=x.device)
     _call("csvit_layernorm", x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), float(eps), out.data_ptr(), _code(out.dtype),
-          out.stride(0), rows, C, mode, H, W, ws, shift, _stream())
+          out.stride(0), rows, C, mode, H, W, ws, shift, _stream(),
+          nbytes=float(rows * width * (4 + out.element_size())))
     return out
 
 
@@ -169,7 +195,7 @@ def linear(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
         raise ValueError("linear: bias must be float32 [N]")
     sH, sW, sws, ssh = scatter if scatter is not None else (0, 0, 0, 0)
     _call("csvit_linear", a.data_ptr(), lda, w.data_ptr(), ldw, _code(a.dtype), M, N, K, _p(bias), act, _p(resid), ldr,
-          out.data_ptr(), ldo, _code(out.dtype), sH, sW, sws, ssh, impl, _stream())
+          out.data_ptr(), ldo, _code(out.dtype), sH, sW, sws, ssh, impl, _stream(), flops=2.0 * M * N * K)
     return out
 
 

@@ -251,3 +251,8 @@ def host_merge_index_map(H: int, W: int) -> torch.Tensor:
     out = torch.empty((H // 2) * (W // 2), 4, dtype=torch.int32)
     _lib.check(_lib.load().csvit_host_merge_index_map(H, W, out.data_ptr()))
     return out
+
+
+def set_gemm_tuning(cluster: int = 0, tma_store: int = -1, max_ctas: int = 0) -> None:
+    """Ablation knobs of the GEMM engine (see ``csvit_set_gemm_tuning``); defaults restore automatic choices."""
+    _lib.check(_lib.load().csvit_set_gemm_tuning(cluster, tma_store, max_ctas))

@@ -1,4 +1,4 @@
-// GEMM engine: persistent warp-specialised TMA + tcgen05/TMEM kernel (bf16 and tf32 operands, fp32
+// GEMM engine: persistent warp-specialised TMA + tcgen05/TMEM kernel (bf16 / fp16 / tf32 operands, fp32
 // accumulate) and an exact-fp32 SIMT kernel used by the fp32 validation mode.
 //
 // Every Linear on the CS-ViT hot path goes through here: Swin Q/K/V, attention out-proj, MLP fc1/fc2, patch
@@ -19,34 +19,51 @@ namespace csvit {
 //   warps 2..9  : epilogue, 2 warps per TMEM lane quadrant, each taking half of the tile's columns
 // Pipelines: smem ring full/empty (TMA <-> MMA) and a 2-deep TMEM accumulator ring (MMA <-> epilogue), so
 // the epilogue of tile i overlaps the MMAs of tile i+1.
+//
+// Cluster mode (CS = 2 or 4): the CS CTAs of a cluster work on CS consecutive 128-row blocks of the SAME
+// column block, so they need the same weight tile.  Each CTA fetches 1/CS of it and TMA-multicasts the slice
+// to all of them; L2 -> SM traffic per MMA drops from 48 KB to 16 + 32/CS KB per 128x256x64 step.  Measured
+// without it (profiles/r1_gemm_baseline.md): the kernel ran at the L2 output cap (~10 TB/s), tensor pipe 42 %.
+//
+// Store path: 16-bit outputs with identity rows are converted in registers, staged in 128-byte-swizzled smem
+// (bank-conflict free) and written by TMA (cp.async.bulk.tensor store) - full 128-byte lines instead of
+// per-thread 16-byte fragments.  Residual / scatter epilogues keep direct stores: there each thread owns a
+// whole 128-byte line of the fp32 residual stream.
 // ----------------------------------------------------------------------------------------------------
 constexpr int kBM = 128;
 constexpr int kGemmThreads = 320;
 constexpr int kEpiWarps = 8;
+constexpr uint32_t kStageBufBytes = 32 * 128;  // per epilogue warp: 32 rows x 64 16-bit columns
 
 template <int BN>
 struct TcCfg {
-  static constexpr int STAGES = BN == 256 ? 4 : (BN == 128 ? 6 : 5);
+  static constexpr int STAGES = BN == 256 ? 4 : 6;
   static constexpr uint32_t A_BYTES = kBM * 128;
   static constexpr uint32_t B_BYTES = BN * 128;
   static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr uint32_t TMEM_COLS = 2 * BN <= 256 ? 256 : 512;  // two accumulator buffers, power of 2
-  static constexpr size_t SMEM = 1024 + size_t(STAGES) * STAGE_BYTES + 256;
+  static constexpr uint32_t TILES_BYTES = STAGES * STAGE_BYTES;
+  static constexpr uint32_t STG_BYTES = kEpiWarps * kStageBufBytes;
+  static constexpr size_t SMEM = 1024 + size_t(TILES_BYTES) + STG_BYTES + 256;
 };
 
-template <int BN, int FMT>  // FMT: 0 = fp16, 1 = bf16, 2 = tf32 operands (UMMA format codes)
+template <int BN, int FMT, int CS>  // FMT: 0 = fp16, 1 = bf16, 2 = tf32 operands (UMMA format codes)
 __global__ void __launch_bounds__(kGemmThreads, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int K, EpiParams ep) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmC, int K, EpiParams ep) {
   using Cfg = TcCfg<BN>;
   constexpr bool TF32 = FMT == 2;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int BK = TF32 ? 32 : 64;  // elements per 128-byte swizzled row
+  constexpr uint16_t kMask = uint16_t((1u << CS) - 1u);
+  constexpr int B_SLICE_ROWS = BN / CS;
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
   uint8_t* tiles = smem;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + size_t(STAGES) * Cfg::STAGE_BYTES);
+  uint8_t* staging = smem + Cfg::TILES_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::TILES_BYTES + Cfg::STG_BYTES);
   uint64_t* full = bars;                     // [STAGES]
   uint64_t* empty = bars + STAGES;           // [STAGES]
   uint64_t* tfull = bars + 2 * STAGES;       // [2]
@@ -55,22 +72,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const int rank = CS > 1 ? int(cluster_ctarank()) : 0;
+  const int cluster_id = blockIdx.x / CS;
+  const int num_clusters = gridDim.x / CS;
 
   const int num_m = (ep.M + kBM - 1) / kBM;
   const int num_n = (ep.N + BN - 1) / BN;
-  const int num_tiles = num_m * num_n;
+  const int num_ctiles = ((num_m + CS - 1) / CS) * num_n;  // cluster tiles: CS row blocks x 1 column block
   const int num_kb = (K + BK - 1) / BK;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    if (ep.tma_store) prefetch_tmap(&tmC);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], CS); }
     for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], kEpiWarps); }
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
   tc_fence_before();
   __syncthreads();
+  if constexpr (CS > 1) cluster_sync_all();  // peers' barriers are initialised before any remote arrive / multicast
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -78,14 +100,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ---------------- TMA producer ----------------
     if (lane == 0) {
       int s = 0; uint32_t ph = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        const int m_blk = t / num_n, n_blk = t - m_blk * num_n;
+      for (int ct = cluster_id; ct < num_ctiles; ct += num_clusters) {
+        const int mg = ct / num_n, n_blk = ct - mg * num_n;
+        const int m_blk = mg * CS + rank;  // may be >= num_m in the last group: TMA zero-fills, epilogue skips
         for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&empty[s], ph ^ 1u);
+          mbar_wait(&empty[s], ph ^ 1u);   // every CTA of the cluster has consumed this slot
           mbar_arrive_expect_tx(&full[s], Cfg::STAGE_BYTES);
           uint8_t* sa = tiles + size_t(s) * Cfg::STAGE_BYTES;
           tma_load_2d(sa, &tmA, &full[s], kb * BK, m_blk * kBM);
-          tma_load_2d(sa + Cfg::A_BYTES, &tmB, &full[s], kb * BK, n_blk * BN);
+          if constexpr (CS == 1) {
+            tma_load_2d(sa + Cfg::A_BYTES, &tmB, &full[s], kb * BK, n_blk * BN);
+          } else {
+            tma_load_2d_mc(sa + Cfg::A_BYTES + rank * B_SLICE_ROWS * 128, &tmB, &full[s], kb * BK,
+                           n_blk * BN + rank * B_SLICE_ROWS, kMask);
+          }
           if (++s == STAGES) { s = 0; ph ^= 1u; }
         }
       }
@@ -96,7 +124,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       constexpr uint32_t idesc = make_idesc(uint32_t(FMT), kBM, BN);
       int s = 0; uint32_t ph = 0;
       int as = 0; uint32_t aph = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      for (int ct = cluster_id; ct < num_ctiles; ct += num_clusters) {
         mbar_wait(&tempty[as], aph ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + uint32_t(as * BN);
@@ -109,7 +137,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
           for (int k = 0; k < 4; ++k)  // 4 x 32-byte K slices per 128-byte row; +32 B = +2 in the >>4 field
             umma_ss<TF32>(d_tmem, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), idesc, (kb | k) ? 1u : 0u);
-          umma_commit(&empty[s]);
+          if constexpr (CS == 1) umma_commit(&empty[s]);
+          else umma_commit_mc(&empty[s], kMask);   // release the slot in every CTA that multicasts into it
           if (kb == num_kb - 1) umma_commit(&tfull[as]);
           if (++s == STAGES) { s = 0; ph ^= 1u; }
         }
@@ -122,33 +151,73 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int quad = warp & 3;            // TMEM lane quadrant this warp may read
     const int half = e >> 2;              // which half of the tile's columns
     const int row_in_tile = quad * 32 + lane;
+    uint8_t* stg = staging + e * kStageBufBytes;
+    const bool bf = ep.out_dtype == DT_BF16;
     int as = 0; uint32_t aph = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-      const int m_blk = t / num_n, n_blk = t - m_blk * num_n;
+    for (int ct = cluster_id; ct < num_ctiles; ct += num_clusters) {
+      const int mg = ct / num_n, n_blk = ct - mg * num_n;
+      const int m_blk = mg * CS + rank;
       const int row = m_blk * kBM + row_in_tile;
       const bool row_ok = row < ep.M;
-      const long long orow = row_ok ? epi_out_row(ep, row) : 0;
       mbar_wait(&tfull[as], aph);
       tc_fence_after();
+      const uint32_t t_addr = tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(as * BN);
+      if (ep.tma_store) {
 #pragma unroll 1
-      for (int c = 0; c < BN / 2; c += 32) {
-        const int col_local = half * (BN / 2) + c;
-        const int gcol = n_blk * BN + col_local;
-        if (gcol >= ep.N) break;  // warp-uniform
-        uint32_t r[32];
-        tmem_ld_32x32(tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(as * BN + col_local), r);
-        tmem_ld_wait();
-        if (row_ok) epi_store_chunk32(ep, orow, gcol, r);
+        for (int c = 0; c < BN / 2; c += 64) {
+          const int col_local = half * (BN / 2) + c;
+          const int gcol = n_blk * BN + col_local;
+          if (gcol >= ep.N) break;  // warp-uniform
+          uint32_t pk[32];          // 64 columns packed to 16 bit
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            uint32_t r[32];
+            tmem_ld_32x32(t_addr + uint32_t(col_local + 32 * hh), r);
+            tmem_ld_wait();
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+            epi_bias_act32(ep, gcol + 32 * hh, v);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) pk[16 * hh + j] = pack16(bf, v[2 * j], v[2 * j + 1]);
+          }
+          if (lane == 0) tma_store_wait_read0();  // the previous TMA store has finished reading the staging buffer
+          __syncwarp();
+#pragma unroll
+          for (int q = 0; q < 8; ++q)  // row `lane`, 16-byte chunk q -> swizzled position q ^ (lane & 7)
+            *reinterpret_cast<uint4*>(stg + lane * 128 + ((q ^ (lane & 7)) << 4)) =
+                make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0 && m_blk * kBM + quad * 32 < ep.M) {
+            tma_store_2d(&tmC, stg, gcol, m_blk * kBM + quad * 32);
+            tma_store_commit();
+          }
+        }
+      } else {
+        const long long orow = row_ok ? epi_out_row(ep, row) : 0;
+#pragma unroll 1
+        for (int c = 0; c < BN / 2; c += 32) {
+          const int col_local = half * (BN / 2) + c;
+          const int gcol = n_blk * BN + col_local;
+          if (gcol >= ep.N) break;  // warp-uniform
+          uint32_t r[32];
+          tmem_ld_32x32(t_addr + uint32_t(col_local), r);
+          tmem_ld_wait();
+          if (row_ok) epi_store_chunk32(ep, orow, gcol, r);
+        }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[as]);
       if (++as == 2) { as = 0; aph ^= 1u; }
     }
+    if (ep.tma_store && lane == 0) tma_store_wait_all();
   }
 
   tc_fence_before();
   __syncthreads();
+  if constexpr (CS > 1) cluster_sync_all();  // no CTA exits while a peer may still multicast into it / signal it
   if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 
@@ -210,23 +279,25 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_tmap_encoder() {
   return fn;
 }
 
-// rows x K row-major operand, box = box_rows x 128 bytes, 128-byte swizzle, OOB zero fill.
-static int make_operand_tmap(CUtensorMap* tm, const void* ptr, long long ld, int rows, int K, int dtype, int box_rows) {
+// rows x cols row-major tensor, box = box_rows x 128 bytes, 128-byte swizzle, OOB zero fill / clipping.
+static int make_tmap(CUtensorMap* tm, const void* ptr, long long ld, long long rows, long long cols, int dtype, int box_rows,
+                     bool as_tf32) {
   auto enc = get_tmap_encoder();
   if (!enc) return set_error("cuTensorMapEncodeTiled entry point not available (driver too old?)");
   const size_t es = dtype_size(dtype);
   if ((reinterpret_cast<uintptr_t>(ptr) & 15) || ((ld * es) & 15))
     return set_error("GEMM operand must be 16-byte aligned with a 16-byte-multiple row pitch (ptr=%p ld=%lld)", ptr, ld);
-  cuuint64_t gdim[2] = {cuuint64_t(K), cuuint64_t(rows)};
+  cuuint64_t gdim[2] = {cuuint64_t(cols), cuuint64_t(rows)};
   cuuint64_t gstr[1] = {cuuint64_t(ld * es)};
   cuuint32_t box[2] = {cuuint32_t(128 / es), cuuint32_t(box_rows)};
   cuuint32_t estr[2] = {1, 1};
   const CUtensorMapDataType tdt = dtype == DT_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
-                                  : (dtype == DT_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32);
-  CUresult r = enc(tm, tdt, 2,
-                   const_cast<void*>(ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                  : (dtype == DT_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16
+                                                     : (as_tf32 ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32));
+  CUresult r = enc(tm, tdt, 2, const_cast<void*>(ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) return set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%d K=%d ld=%lld)", int(r), rows, K, ld);
+  if (r != CUDA_SUCCESS)
+    return set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld cols=%lld ld=%lld)", int(r), rows, cols, ld);
   return 0;
 }
 
@@ -241,25 +312,48 @@ static int num_sms() {
   return g_num_sms;
 }
 
-template <int BN, int FMT>
-static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, int K, const EpiParams& ep, int max_ctas, cudaStream_t stream) {
+template <int BN, int FMT, int CS>
+static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, int K, const EpiParams& ep,
+                     int max_ctas, cudaStream_t stream) {
   using Cfg = TcCfg<BN>;
   static bool configured = false;
-  auto kern = gemm_tc_kernel<BN, FMT>;
+  auto kern = gemm_tc_kernel<BN, FMT, CS>;
   if (!configured) {
     CSVIT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(Cfg::SMEM)));
     configured = true;
   }
-  const int tiles = ((ep.M + kBM - 1) / kBM) * ((ep.N + BN - 1) / BN);
+  const int num_m = (ep.M + kBM - 1) / kBM, num_n = (ep.N + BN - 1) / BN;
+  const int ctiles = ((num_m + CS - 1) / CS) * num_n;
   int ctas = max_ctas > 0 ? max_ctas : num_sms();
-  if (ctas > tiles) ctas = tiles;
-  kern<<<ctas, kGemmThreads, Cfg::SMEM, stream>>>(tmA, tmB, K, ep);
-  CSVIT_CUDA(cudaGetLastError());
+  int clusters = ctas / CS;
+  if (clusters > ctiles) clusters = ctiles;
+  if (clusters < 1) clusters = 1;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(unsigned(clusters * CS));
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = Cfg::SMEM;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CS;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  CSVIT_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, K, ep));
   return 0;
 }
 
+template <int BN, int FMT>
+static int launch_tc_cs(int cs, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c, int K, const EpiParams& ep,
+                        int max_ctas, cudaStream_t st) {
+  if (cs == 4) return launch_tc<BN, FMT, 4>(a, b, c, K, ep, max_ctas, st);
+  if (cs == 2) return launch_tc<BN, FMT, 2>(a, b, c, K, ep, max_ctas, st);
+  return launch_tc<BN, FMT, 1>(a, b, c, K, ep, max_ctas, st);
+}
+
 int launch_gemm(const void* A, long long lda, const void* W, long long ldw, int in_dtype, int M, int N, int K,
-                const EpiParams& ep_in, int impl, int max_ctas, cudaStream_t stream) {
+                const EpiParams& ep_in, int impl, const GemmTuning& tune, cudaStream_t stream) {
   if (M <= 0 || N <= 0 || K <= 0) return 0;
   EpiParams ep = ep_in;
   ep.M = M; ep.N = N;
@@ -267,6 +361,7 @@ int launch_gemm(const void* A, long long lda, const void* W, long long ldw, int 
   ep.vec_ok = (N % 8 == 0) && ((ep.ldo * oes) % 16 == 0) && ((reinterpret_cast<uintptr_t>(ep.out) & 15) == 0) &&
               (!ep.resid || ((ep.ldr % 4 == 0) && (reinterpret_cast<uintptr_t>(ep.resid) & 15) == 0)) &&
               (!ep.bias || (reinterpret_cast<uintptr_t>(ep.bias) & 15) == 0);
+  ep.tma_store = 0;
   if (impl == GEMM_SIMT) {
     if (in_dtype != DT_F32) return set_error("SIMT GEMM takes fp32 operands only");
     dim3 grid((N + 63) / 64, (M + 63) / 64);
@@ -278,19 +373,33 @@ int launch_gemm(const void* A, long long lda, const void* W, long long ldw, int 
   // or 256 would leave most SMs idle.
   int BN = 256;
   if (N <= 128 || (N % 256 != 0 && N % 128 == 0)) BN = 128;
-  const int tiles256 = ((M + kBM - 1) / kBM) * ((N + 255) / 256);
-  if (BN == 256 && tiles256 < num_sms()) BN = 128;
-  CUtensorMap tmA, tmB;
-  if (int e = make_operand_tmap(&tmA, A, lda, M, K, in_dtype, kBM)) return e;
-  if (int e = make_operand_tmap(&tmB, W, ldw, N, K, in_dtype, BN)) return e;
-  if (BN == 256) {
-    if (in_dtype == DT_F32) return launch_tc<256, 2>(tmA, tmB, K, ep, max_ctas, stream);
-    if (in_dtype == DT_BF16) return launch_tc<256, 1>(tmA, tmB, K, ep, max_ctas, stream);
-    return launch_tc<256, 0>(tmA, tmB, K, ep, max_ctas, stream);
+  const int num_m = (M + kBM - 1) / kBM;
+  if (BN == 256 && num_m * ((N + 255) / 256) < num_sms()) BN = 128;
+  // Cluster size: share the weight tile across row blocks when there are enough of them to keep every SM busy.
+  int cs = tune.cluster;
+  if (cs == 0) cs = 1;  // measured (profiles/r1_gemm_sweep.md): multicast does not help - the limit is per-SM ingest, not L2 output
+  if (cs != 1 && cs != 2 && cs != 4) return set_error("gemm: cluster size %d not in {1,2,4}", cs);
+  // TMA store: 16-bit output, plain rows, no residual, whole 64-column chunks.
+  const bool can_tma_store = ep.out_dtype != DT_F32 && !ep.resid && ep.map_mode == ROWMAP_IDENTITY && (N % 64 == 0) &&
+                             ep.vec_ok;
+  ep.tma_store = (tune.tma_store != 0 && can_tma_store) ? 1 : 0;
+  CUtensorMap tmA, tmB, tmC;
+  if (int e = make_tmap(&tmA, A, lda, M, K, in_dtype, kBM, true)) return e;
+  if (int e = make_tmap(&tmB, W, ldw, N, K, in_dtype, BN / cs, true)) return e;
+  if (ep.tma_store) {
+    if (int e = make_tmap(&tmC, ep.out, ep.ldo, M, N, ep.out_dtype, 32, false)) return e;
+  } else {
+    tmC = tmA;
   }
-  if (in_dtype == DT_F32) return launch_tc<128, 2>(tmA, tmB, K, ep, max_ctas, stream);
-  if (in_dtype == DT_BF16) return launch_tc<128, 1>(tmA, tmB, K, ep, max_ctas, stream);
-  return launch_tc<128, 0>(tmA, tmB, K, ep, max_ctas, stream);
+  const int mc = tune.max_ctas;
+  if (BN == 256) {
+    if (in_dtype == DT_F32) return launch_tc_cs<256, 2>(cs, tmA, tmB, tmC, K, ep, mc, stream);
+    if (in_dtype == DT_BF16) return launch_tc_cs<256, 1>(cs, tmA, tmB, tmC, K, ep, mc, stream);
+    return launch_tc_cs<256, 0>(cs, tmA, tmB, tmC, K, ep, mc, stream);
+  }
+  if (in_dtype == DT_F32) return launch_tc_cs<128, 2>(cs, tmA, tmB, tmC, K, ep, mc, stream);
+  if (in_dtype == DT_BF16) return launch_tc_cs<128, 1>(cs, tmA, tmB, tmC, K, ep, mc, stream);
+  return launch_tc_cs<128, 0>(cs, tmA, tmB, tmC, K, ep, mc, stream);
 }
 
 }  // namespace csvit

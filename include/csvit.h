@@ -100,6 +100,12 @@ CSVIT_API int csvit_linear(const void* A, long long lda, const void* W, long lon
                  int out_dtype, int scatter_H, int scatter_W, int scatter_ws, int scatter_shift, int impl,
                  void* stream);
 
+/* Process-wide tuning knobs of the GEMM engine (benchmarking / ablation; defaults are automatic):
+ *   cluster   0 = auto, 1 / 2 / 4 = CTAs per cluster sharing the weight tile by TMA multicast
+ *   tma_store -1 = auto, 0 = direct register stores, 1 = smem-staged TMA stores where legal
+ *   max_ctas  0 = one CTA per SM */
+CSVIT_API int csvit_set_gemm_tuning(int cluster, int tma_store, int max_ctas);
+
 /* ---- attention cores -------------------------------------------------------------------------------------
  * Swin window attention on window-ordered qkv[B*H*W, 3C] (Q|K|V column blocks, head h at columns 32h..):
  *   out[B*H*W, C] = softmax(Q K^T / sqrt(32) + bias[h] + shift_mask) V, heads merged.       HF:410-459

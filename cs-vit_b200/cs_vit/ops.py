@@ -117,6 +117,16 @@ def expand_rel_bias(table: torch.Tensor, ws: int) -> torch.Tensor:
     return out
 
 
+def expand_rel_bias_mma(table: torch.Tensor, ws: int = 7) -> torch.Tensor:
+    """Bias table in MMA accumulator-fragment order for the 16-bit window-attention kernel."""
+    _dev(table)
+    table = table.contiguous().float()
+    heads = table.shape[1]
+    out = torch.empty(heads, 4, 7, 32, 4, dtype=torch.float32, device=table.device)
+    _call("csvit_expand_rel_bias_mma", table.data_ptr(), out.data_ptr(), heads, ws, _stream())
+    return out
+
+
 # ---------------------------------------------------------------------------------------------- row kernels
 def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float, *, out_dtype=torch.float32,
               mode: int = LN_IDENTITY, grid: Tuple[int, int] = (0, 0), ws: int = 0, shift: int = 0,
@@ -202,14 +212,18 @@ def linear(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
 # ---------------------------------------------------------------------------------------------- attention
 def window_attention(qkv: torch.Tensor, bias_exp: torch.Tensor, B: int, H: int, W: int, heads: int, ws: int,
                      shift: int) -> torch.Tensor:
+    """``bias_exp``: ``expand_rel_bias`` table for fp32 qkv, ``expand_rel_bias_mma`` table for bf16 / fp16 qkv."""
     _dev(qkv, bias_exp)
+    plain, frag = (bias_exp, None) if qkv.dtype == torch.float32 else (None, bias_exp)
+    if frag is not None and frag.dim() != 5:
+        raise ValueError("16-bit window attention needs the expand_rel_bias_mma table")
     rows, C3, ld = _rows2d(qkv)
     C = C3 // 3
     if ld != C3 or rows != B * H * W:
         raise ValueError("window_attention: qkv must be dense [B*H*W, 3C]")
     out = torch.empty(rows, C, dtype=qkv.dtype, device=qkv.device)
-    _call("csvit_window_attention", qkv.data_ptr(), bias_exp.data_ptr(), out.data_ptr(), _code(qkv.dtype), B, H, W, C,
-          heads, ws, shift, _stream())
+    _call("csvit_window_attention", qkv.data_ptr(), _p(plain), _p(frag), out.data_ptr(), _code(qkv.dtype), B, H, W, C,
+          heads, ws, shift, _stream(), nbytes=float(qkv.numel() + out.numel()) * qkv.element_size())
     return out
 
 

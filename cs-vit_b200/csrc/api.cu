@@ -150,11 +150,18 @@ int csvit_set_gemm_tuning(int cluster, int tma_store, int max_ctas) {
   return 0;
 }
 
-int csvit_window_attention(const void* qkv, const float* bias, void* out, int dtype, int B, int H, int W, int C, int heads,
-                           int ws, int shift, void* stream) {
-  CSVIT_REQUIRE(bias != nullptr, "window_attention: bias table required");
-  if (dtype == DT_BF16 || dtype == DT_F16)
-    return launch_window_attention_mma(qkv, bias, out, dtype, B, H, W, C, heads, ws, shift, S(stream));
+int csvit_expand_rel_bias_mma(const float* table, float* out, int heads, int ws, void* stream) {
+  CSVIT_REQUIRE(heads > 0 && ws == 7, "expand_rel_bias_mma: heads=%d ws=%d (window 7 only)", heads, ws);
+  return launch_expand_rel_bias_mma(table, out, heads, S(stream));
+}
+
+int csvit_window_attention(const void* qkv, const float* bias, const float* bias_mma, void* out, int dtype, int B, int H,
+                           int W, int C, int heads, int ws, int shift, void* stream) {
+  if (dtype == DT_BF16 || dtype == DT_F16) {
+    CSVIT_REQUIRE(bias_mma != nullptr, "window_attention: 16-bit path needs the csvit_expand_rel_bias_mma table");
+    return launch_window_attention_mma(qkv, bias_mma, out, dtype, B, H, W, C, heads, ws, shift, S(stream));
+  }
+  CSVIT_REQUIRE(bias != nullptr, "window_attention: fp32 path needs the csvit_expand_rel_bias table");
   CSVIT_REQUIRE(dtype == DT_F32, "window_attention: bad dtype %d", dtype);
   CSVIT_REQUIRE(C == heads * 32, "window_attention: head_dim must be 32 (C=%d heads=%d)", C, heads);
   CSVIT_REQUIRE(H % ws == 0 && W % ws == 0, "window_attention: %dx%d not divisible by window %d", H, W, ws);

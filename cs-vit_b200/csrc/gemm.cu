@@ -194,6 +194,52 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tma_store_commit();
           }
         }
+      } else if (ep.coalesced) {
+        // fp32 output (+ residual, + row scatter).  Accumulators arrive row-per-thread; a 32x32 fp32 chunk is
+        // transposed through the swizzled staging buffer so that every global access of the warp covers 4 full
+        // 128-byte lines (8 lanes x 16 B per row) instead of 32 partial ones.
+        long long orow8[8];
+        bool ok8[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int rr = m_blk * kBM + quad * 32 + 4 * j + (lane >> 3);
+          ok8[j] = rr < ep.M;
+          orow8[j] = ok8[j] ? epi_out_row(ep, rr) : 0;
+        }
+        const int q = lane & 7;
+        float* outp = reinterpret_cast<float*>(ep.out);
+#pragma unroll 1
+        for (int c = 0; c < BN / 2; c += 32) {
+          const int col_local = half * (BN / 2) + c;
+          const int gcol = n_blk * BN + col_local;
+          if (gcol >= ep.N) break;  // warp-uniform
+          uint32_t r[32];
+          tmem_ld_32x32(t_addr + uint32_t(col_local), r);
+          tmem_ld_wait();
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          epi_bias_act32(ep, gcol, v);
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            *reinterpret_cast<float4*>(stg + lane * 128 + ((k ^ (lane & 7)) << 4)) =
+                make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+          __syncwarp();
+          float4 val[8], res[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int i = 4 * j + (lane >> 3);
+            val[j] = *reinterpret_cast<const float4*>(stg + i * 128 + ((q ^ (i & 7)) << 4));
+            res[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ep.resid && ok8[j]) res[j] = *reinterpret_cast<const float4*>(ep.resid + orow8[j] * ep.ldr + gcol + 4 * q);
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (ok8[j])
+              *reinterpret_cast<float4*>(outp + orow8[j] * ep.ldo + gcol + 4 * q) =
+                  make_float4(val[j].x + res[j].x, val[j].y + res[j].y, val[j].z + res[j].z, val[j].w + res[j].w);
+          __syncwarp();
+        }
       } else {
         const long long orow = row_ok ? epi_out_row(ep, row) : 0;
 #pragma unroll 1
@@ -383,6 +429,7 @@ int launch_gemm(const void* A, long long lda, const void* W, long long ldw, int 
   const bool can_tma_store = ep.out_dtype != DT_F32 && !ep.resid && ep.map_mode == ROWMAP_IDENTITY && (N % 64 == 0) &&
                              ep.vec_ok;
   ep.tma_store = (tune.tma_store != 0 && can_tma_store) ? 1 : 0;
+  ep.coalesced = (!ep.tma_store && tune.tma_store != 0 && ep.out_dtype == DT_F32 && ep.vec_ok && (N % 32 == 0)) ? 1 : 0;
   CUtensorMap tmA, tmB, tmC;
   if (int e = make_tmap(&tmA, A, lda, M, K, in_dtype, kBM, true)) return e;
   if (int e = make_tmap(&tmB, W, ldw, N, K, in_dtype, BN / cs, true)) return e;

@@ -24,6 +24,7 @@ struct EpiParams {
   int M, N;
   int vec_ok;     // 1: rows are 16-byte aligned for 32-column chunks (ldo/ldr/N multiples of 8)
   int tma_store;  // 1: 16-bit output, identity rows, no residual -> staged through smem and written by TMA
+  int coalesced;  // 1: fp32 output (+residual, +scatter) -> transposed through smem, 4 full lines per warp access
   int map_mode;
   WinGeom geom;
 };

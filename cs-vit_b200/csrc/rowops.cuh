@@ -19,7 +19,8 @@ int launch_merge_index_map(int H, int W, int* out, cudaStream_t stream);
 int launch_expand_rel_bias(const float* table, float* out, int heads, int ws, cudaStream_t stream);
 
 // attention.cu
-int launch_window_attention_mma(const void* qkv, const float* bias_exp, void* out, int dtype, int B, int H, int W,
+int launch_expand_rel_bias_mma(const float* table, float* out, int heads, cudaStream_t stream);
+int launch_window_attention_mma(const void* qkv, const float* bias_frag, void* out, int dtype, int B, int H, int W,
                                 int C, int heads, int ws, int shift, cudaStream_t stream);
 int launch_attention_simt(const void* q, const void* k, const void* v, void* out, int dtype, long long ldq, long long ldk,
                           long long ldv, long long ldo, int n_seq, int Lq, int S, int heads, float scale,

@@ -64,6 +64,8 @@ CSVIT_API int csvit_host_merge_index_map(int H, int W, int32_t* out);
 /* bias[h, i, j] = table[rel_pos_index(i, j), h]; table is [(2ws-1)^2, heads] fp32.      HF:428-434 */
 CSVIT_API int csvit_expand_rel_bias(const float* table, float* out, int heads, int ws, void* stream);
 
+CSVIT_API int csvit_expand_rel_bias_mma(const float* table, float* out, int heads, int ws, void* stream);
+
 /* ---- row kernels (HBM-bound) ----------------------------------------------------------------------------
  * LayerNorm over the last dim of fp32 x[B, H*W, C], eps inside the sqrt, output fp32 or bf16.
  *   CSVIT_LN_IDENTITY : out row r <- x row r                            HF:606/648 layernorm_*, HF:882 final norm
@@ -110,9 +112,11 @@ CSVIT_API int csvit_set_gemm_tuning(int cluster, int tma_store, int max_ctas);
  * Swin window attention on window-ordered qkv[B*H*W, 3C] (Q|K|V column blocks, head h at columns 32h..):
  *   out[B*H*W, C] = softmax(Q K^T / sqrt(32) + bias[h] + shift_mask) V, heads merged.       HF:410-459
  * bf16 / fp16: tensor-core kernel (window 7, head_dim 32).  fp32: exact kernel (validation mode).
- * bias is the expanded [heads, L, L] fp32 table from csvit_expand_rel_bias. */
-CSVIT_API int csvit_window_attention(const void* qkv, const float* bias, void* out, int dtype, int B, int H, int W, int C,
-                           int heads, int ws, int shift, void* stream);
+ * fp32 reads `bias` = the [heads, L, L] table of csvit_expand_rel_bias; the 16-bit kernel reads `bias_mma` = the
+ * same values pre-arranged in MMA accumulator-fragment order by csvit_expand_rel_bias_mma
+ * ([heads, 4, 7, 32, 4] floats, -inf in the padding columns).  The unused one may be NULL. */
+CSVIT_API int csvit_window_attention(const void* qkv, const float* bias, const float* bias_mma, void* out, int dtype,
+                                     int B, int H, int W, int C, int heads, int ws, int shift, void* stream);
 
 /* Dense multi-head attention for short sequences (S <= 64, head_dim 32), exact fp32 math:
  *   out[s, i, h*32:(h+1)*32] = softmax_j(q[s,i,h] . k[s,j,h] * scale) v[s,j,h]

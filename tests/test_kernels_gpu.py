@@ -116,7 +116,7 @@ def test_window_attention(ops, H, heads, shift, dtype):
     qkv = torch.randn(B * H * W, 3 * C, device="cuda", generator=g).to(dtype)
     table = torch.randn(169, heads, device="cuda", generator=g)
     bias = ops.expand_rel_bias(table, ws)
-    out = ops.window_attention(qkv, bias, B, H, W, heads, ws, shift)
+    out = ops.window_attention(qkv, bias if dtype == torch.float32 else ops.expand_rel_bias_mma(table, ws), B, H, W, heads, ws, shift)
     q, k, v = qkv.float().view(B * nW, L, 3, heads, 32).permute(2, 0, 3, 1, 4)
     s = q @ k.transpose(-1, -2) / math.sqrt(32) + bias[None]
     if shift:

@@ -159,6 +159,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int m_blk = mg * CS + rank;
       const int row = m_blk * kBM + row_in_tile;
       const bool row_ok = row < ep.M;
+      // Residual epilogue: row addresses do not depend on the MMA result, so the first chunk's residual
+      // lines are requested BEFORE waiting for the accumulator (and chunk c+1's while chunk c is processed).
+      long long orow8[8];
+      bool ok8[8];
+      float4 res[8];
+      const int q = lane & 7;
+      auto load_resid = [&](int gcol) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          res[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (ep.resid && ok8[j] && gcol < ep.N)
+            res[j] = *reinterpret_cast<const float4*>(ep.resid + orow8[j] * ep.ldr + gcol + 4 * q);
+        }
+      };
+      if (ep.coalesced) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int rr = m_blk * kBM + quad * 32 + 4 * j + (lane >> 3);
+          ok8[j] = rr < ep.M;
+          orow8[j] = ok8[j] ? epi_out_row(ep, rr) : 0;
+        }
+        load_resid(n_blk * BN + half * (BN / 2));
+      }
       mbar_wait(&tfull[as], aph);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(as * BN);
@@ -198,15 +221,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // fp32 output (+ residual, + row scatter).  Accumulators arrive row-per-thread; a 32x32 fp32 chunk is
         // transposed through the swizzled staging buffer so that every global access of the warp covers 4 full
         // 128-byte lines (8 lanes x 16 B per row) instead of 32 partial ones.
-        long long orow8[8];
-        bool ok8[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int rr = m_blk * kBM + quad * 32 + 4 * j + (lane >> 3);
-          ok8[j] = rr < ep.M;
-          orow8[j] = ok8[j] ? epi_out_row(ep, rr) : 0;
-        }
-        const int q = lane & 7;
         float* outp = reinterpret_cast<float*>(ep.out);
 #pragma unroll 1
         for (int c = 0; c < BN / 2; c += 32) {
@@ -225,19 +239,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             *reinterpret_cast<float4*>(stg + lane * 128 + ((k ^ (lane & 7)) << 4)) =
                 make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
           __syncwarp();
-          float4 val[8], res[8];
+          float4 val[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const int i = 4 * j + (lane >> 3);
-            val[j] = *reinterpret_cast<const float4*>(stg + i * 128 + ((q ^ (i & 7)) << 4));
-            res[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (ep.resid && ok8[j]) res[j] = *reinterpret_cast<const float4*>(ep.resid + orow8[j] * ep.ldr + gcol + 4 * q);
+            const float4 t = *reinterpret_cast<const float4*>(stg + i * 128 + ((q ^ (i & 7)) << 4));
+            val[j] = make_float4(t.x + res[j].x, t.y + res[j].y, t.z + res[j].z, t.w + res[j].w);
           }
+          if (c + 32 < BN / 2) load_resid(gcol + 32);   // next chunk's residual in flight during the stores
 #pragma unroll
           for (int j = 0; j < 8; ++j)
-            if (ok8[j])
-              *reinterpret_cast<float4*>(outp + orow8[j] * ep.ldo + gcol + 4 * q) =
-                  make_float4(val[j].x + res[j].x, val[j].y + res[j].y, val[j].z + res[j].z, val[j].w + res[j].w);
+            if (ok8[j]) *reinterpret_cast<float4*>(outp + orow8[j] * ep.ldo + gcol + 4 * q) = val[j];
           __syncwarp();
         }
       } else {

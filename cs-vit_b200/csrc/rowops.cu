@@ -28,79 +28,102 @@ template <> struct Store4<__nv_bfloat16> {
   }
 };
 
-// One warp per output row; the row (<= MAXJ*128 floats) lives in registers between the two passes.
-template <int MAXJ, typename OutT>
+// One warp per R consecutive output rows; the rows (<= MAXJ*128 floats each) live in registers between the two
+// passes, and all R rows' loads are issued before the first reduction so each lane keeps R*MAXJ 16-byte
+// requests in flight (the kernel is purely HBM-bound).
+template <int MAXJ, int R, typename OutT>
 __global__ void __launch_bounds__(256)
 ln_rows_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                OutT* __restrict__ out, long long ldo, int rows, int C, int mode, WinGeom g) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  if (warp >= rows) return;
+  const int row0 = warp * R;
+  if (row0 >= rows) return;
   const int Cout = mode == LN_MERGE2X2 ? 4 * C : C;
   const int n4 = Cout >> 2;
 
-  // source row(s)
-  long long src[4];
-  if (mode == LN_IDENTITY) {
-    src[0] = warp;
-  } else if (mode == LN_WINDOW) {
-    int b = warp / g.N, r = warp - b * g.N;
-    src[0] = static_cast<long long>(b) * g.N + win_row_to_token(g, r);
-  } else {
-    const int Wo = g.W >> 1, No = (g.H >> 1) * Wo;
-    int b = warp / No, t = warp - b * No;
-    int Y = t / Wo, X = t - Y * Wo;
+  float4 v[R][MAXJ];
+  float sum[R];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) src[q] = static_cast<long long>(b) * g.N + merge_src_token(g.W, Y, X, q);
+  for (int r = 0; r < R; ++r) {
+    const int row = row0 + r;
+    sum[r] = 0.f;
+    if (row < rows) {
+      long long src[4];
+      if (mode == LN_IDENTITY) {
+        src[0] = row;
+      } else if (mode == LN_WINDOW) {
+        int b = row / g.N, rr = row - b * g.N;
+        src[0] = static_cast<long long>(b) * g.N + win_row_to_token(g, rr);
+      } else {
+        const int Wo = g.W >> 1, No = (g.H >> 1) * Wo;
+        int b = row / No, t = row - b * No;
+        int Y = t / Wo, X = t - Y * Wo;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) src[q] = static_cast<long long>(b) * g.N + merge_src_token(g.W, Y, X, q);
+      }
+#pragma unroll
+      for (int j = 0; j < MAXJ; ++j) {
+        int i4 = lane + 32 * j;
+        if (i4 < n4) {
+          int e = i4 << 2;
+          const float* p;
+          if (mode == LN_MERGE2X2) { int q = e / C; p = x + src[q] * C + (e - q * C); }
+          else p = x + src[0] * C + e;
+          v[r][j] = *reinterpret_cast<const float4*>(p);
+        }
+      }
+    }
   }
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int row = row0 + r;
+    if (row >= rows) break;   // warp-uniform
+#pragma unroll
+    for (int j = 0; j < MAXJ; ++j)
+      if (lane + 32 * j < n4) sum[r] += (v[r][j].x + v[r][j].y) + (v[r][j].z + v[r][j].w);
+    const float mean = warp_sum(sum[r]) / float(Cout);
+    float sq = 0.f;
+#pragma unroll
+    for (int j = 0; j < MAXJ; ++j) {
+      if (lane + 32 * j < n4) {
+        float a = v[r][j].x - mean, b = v[r][j].y - mean, c = v[r][j].z - mean, d = v[r][j].w - mean;
+        sq += (a * a + b * b) + (c * c + d * d);
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(sq) / float(Cout) + eps);
+    OutT* orow = out + static_cast<long long>(row) * ldo;
+#pragma unroll
+    for (int j = 0; j < MAXJ; ++j) {
+      int i4 = lane + 32 * j;
+      if (i4 < n4) {
+        int e = i4 << 2;
+        float4 gm = __ldg(reinterpret_cast<const float4*>(gamma + e));
+        float4 bt = __ldg(reinterpret_cast<const float4*>(beta + e));
+        Store4<OutT>::st(orow + e, (v[r][j].x - mean) * rstd * gm.x + bt.x, (v[r][j].y - mean) * rstd * gm.y + bt.y,
+                         (v[r][j].z - mean) * rstd * gm.z + bt.z, (v[r][j].w - mean) * rstd * gm.w + bt.w);
+      }
+    }
+  }
+}
 
-  float4 v[MAXJ];
-  float sum = 0.f;
-#pragma unroll
-  for (int j = 0; j < MAXJ; ++j) {
-    int i4 = lane + 32 * j;
-    if (i4 < n4) {
-      int e = i4 << 2;
-      const float* p;
-      if (mode == LN_MERGE2X2) { int q = e / C; p = x + src[q] * C + (e - q * C); }
-      else p = x + src[0] * C + e;
-      v[j] = *reinterpret_cast<const float4*>(p);
-      sum += (v[j].x + v[j].y) + (v[j].z + v[j].w);
-    }
-  }
-  const float mean = warp_sum(sum) / float(Cout);
-  float sq = 0.f;
-#pragma unroll
-  for (int j = 0; j < MAXJ; ++j) {
-    if (lane + 32 * j < n4) {
-      float a = v[j].x - mean, b = v[j].y - mean, c = v[j].z - mean, d = v[j].w - mean;
-      sq += (a * a + b * b) + (c * c + d * d);
-    }
-  }
-  const float rstd = rsqrtf(warp_sum(sq) / float(Cout) + eps);
-  OutT* orow = out + static_cast<long long>(warp) * ldo;
-#pragma unroll
-  for (int j = 0; j < MAXJ; ++j) {
-    int i4 = lane + 32 * j;
-    if (i4 < n4) {
-      int e = i4 << 2;
-      float4 gm = __ldg(reinterpret_cast<const float4*>(gamma + e));
-      float4 bt = __ldg(reinterpret_cast<const float4*>(beta + e));
-      Store4<OutT>::st(orow + e, (v[j].x - mean) * rstd * gm.x + bt.x, (v[j].y - mean) * rstd * gm.y + bt.y,
-                       (v[j].z - mean) * rstd * gm.z + bt.z, (v[j].w - mean) * rstd * gm.w + bt.w);
-    }
-  }
+template <int MAXJ, int R, typename OutT>
+static void launch_ln_cfg(const float* x, const float* gamma, const float* beta, float eps, OutT* out, long long ldo,
+                          int rows, int C, int mode, const WinGeom& g, cudaStream_t stream) {
+  const int warps = (rows + R - 1) / R;
+  ln_rows_kernel<MAXJ, R, OutT><<<(warps + 7) / 8, 256, 0, stream>>>(x, gamma, beta, eps, out, ldo, rows, C, mode, g);
 }
 
 template <typename OutT>
 static int launch_ln_t(const float* x, const float* gamma, const float* beta, float eps, OutT* out, long long ldo,
                        int rows, int C, int mode, const WinGeom& g, cudaStream_t stream) {
   const int Cout = mode == LN_MERGE2X2 ? 4 * C : C;
-  const int blocks = (rows + 7) / 8;
-  if (Cout <= 512) ln_rows_kernel<4, OutT><<<blocks, 256, 0, stream>>>(x, gamma, beta, eps, out, ldo, rows, C, mode, g);
-  else if (Cout <= 1024) ln_rows_kernel<8, OutT><<<blocks, 256, 0, stream>>>(x, gamma, beta, eps, out, ldo, rows, C, mode, g);
-  else if (Cout <= 2048) ln_rows_kernel<16, OutT><<<blocks, 256, 0, stream>>>(x, gamma, beta, eps, out, ldo, rows, C, mode, g);
-  else if (Cout <= 4096) ln_rows_kernel<32, OutT><<<blocks, 256, 0, stream>>>(x, gamma, beta, eps, out, ldo, rows, C, mode, g);
+  if (Cout <= 128) launch_ln_cfg<1, 8, OutT>(x, gamma, beta, eps, out, ldo, rows, C, mode, g, stream);
+  else if (Cout <= 256) launch_ln_cfg<2, 4, OutT>(x, gamma, beta, eps, out, ldo, rows, C, mode, g, stream);
+  else if (Cout <= 512) launch_ln_cfg<4, 4, OutT>(x, gamma, beta, eps, out, ldo, rows, C, mode, g, stream);
+  else if (Cout <= 1024) launch_ln_cfg<8, 2, OutT>(x, gamma, beta, eps, out, ldo, rows, C, mode, g, stream);
+  else if (Cout <= 2048) launch_ln_cfg<16, 1, OutT>(x, gamma, beta, eps, out, ldo, rows, C, mode, g, stream);
+  else if (Cout <= 4096) launch_ln_cfg<32, 1, OutT>(x, gamma, beta, eps, out, ldo, rows, C, mode, g, stream);
   else return set_error("layernorm: row width %d exceeds 4096", Cout);
   CSVIT_CUDA(cudaGetLastError());
   return 0;

@@ -267,6 +267,6 @@ def host_merge_index_map(H: int, W: int) -> torch.Tensor:
     return out
 
 
-def set_gemm_tuning(cluster: int = 0, tma_store: int = -1, max_ctas: int = 0) -> None:
+def set_gemm_tuning(cluster: int = 0, tma_store: int = -1, max_ctas: int = 0, pair: int = -1) -> None:
     """Ablation knobs of the GEMM engine (see ``csvit_set_gemm_tuning``); defaults restore automatic choices."""
-    _lib.check(_lib.load().csvit_set_gemm_tuning(cluster, tma_store, max_ctas))
+    _lib.check(_lib.load().csvit_set_gemm_tuning(cluster, tma_store, max_ctas, pair))

@@ -31,7 +31,7 @@ static_assert(int(CSVIT_LN_WINDOW) == int(LN_WINDOW) && int(CSVIT_LN_MERGE2X2) =
 static_assert(int(CSVIT_GEMM_SIMT_FP32) == int(GEMM_SIMT), "gemm impl codes");
 
 static inline cudaStream_t S(void* s) { return static_cast<cudaStream_t>(s); }
-static GemmTuning g_tune = {0, 0, -1};
+static GemmTuning g_tune = {0, 0, -1, -1};
 
 extern "C" {
 
@@ -144,7 +144,8 @@ int csvit_linear(const void* A, long long lda, const void* W, long long ldw, int
   return launch_gemm(A, lda, W, ldw, in_dtype, M, N, K, ep, impl, g_tune, S(stream));
 }
 
-int csvit_set_gemm_tuning(int cluster, int tma_store, int max_ctas) {
+int csvit_set_gemm_tuning(int cluster, int tma_store, int max_ctas, int pair) {
+  g_tune.pair = pair;
   CSVIT_REQUIRE(cluster == 0 || cluster == 1 || cluster == 2 || cluster == 4, "gemm tuning: cluster %d not in {0,1,2,4}", cluster);
   g_tune.cluster = cluster; g_tune.tma_store = tma_store; g_tune.max_ctas = max_ctas;
   return 0;

@@ -30,10 +30,6 @@ namespace csvit {
 // per-thread 16-byte fragments.  Residual / scatter epilogues keep direct stores: there each thread owns a
 // whole 128-byte line of the fp32 residual stream.
 // ----------------------------------------------------------------------------------------------------
-constexpr int kBM = 128;
-constexpr int kGemmThreads = 320;
-constexpr int kEpiWarps = 8;
-constexpr uint32_t kStageBufBytes = 32 * 128;  // per epilogue warp: 32 rows x 64 16-bit columns
 
 template <int BN>
 struct TcCfg {
@@ -150,121 +146,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int e = warp - 2;
     const int quad = warp & 3;            // TMEM lane quadrant this warp may read
     const int half = e >> 2;              // which half of the tile's columns
-    const int row_in_tile = quad * 32 + lane;
     uint8_t* stg = staging + e * kStageBufBytes;
-    const bool bf = ep.out_dtype == DT_BF16;
     int as = 0; uint32_t aph = 0;
     for (int ct = cluster_id; ct < num_ctiles; ct += num_clusters) {
       const int mg = ct / num_n, n_blk = ct - mg * num_n;
       const int m_blk = mg * CS + rank;
-      const int row = m_blk * kBM + row_in_tile;
-      const bool row_ok = row < ep.M;
-      // Residual epilogue: row addresses do not depend on the MMA result, so the first chunk's residual
-      // lines are requested BEFORE waiting for the accumulator (and chunk c+1's while chunk c is processed).
-      long long orow8[8];
-      bool ok8[8];
-      float4 res[8];
-      const int q = lane & 7;
-      auto load_resid = [&](int gcol) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          res[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (ep.resid && ok8[j] && gcol < ep.N)
-            res[j] = *reinterpret_cast<const float4*>(ep.resid + orow8[j] * ep.ldr + gcol + 4 * q);
-        }
-      };
-      if (ep.coalesced) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int rr = m_blk * kBM + quad * 32 + 4 * j + (lane >> 3);
-          ok8[j] = rr < ep.M;
-          orow8[j] = ok8[j] ? epi_out_row(ep, rr) : 0;
-        }
-        load_resid(n_blk * BN + half * (BN / 2));
-      }
-      mbar_wait(&tfull[as], aph);
-      tc_fence_after();
-      const uint32_t t_addr = tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(as * BN);
-      if (ep.tma_store) {
-#pragma unroll 1
-        for (int c = 0; c < BN / 2; c += 64) {
-          const int col_local = half * (BN / 2) + c;
-          const int gcol = n_blk * BN + col_local;
-          if (gcol >= ep.N) break;  // warp-uniform
-          uint32_t pk[32];          // 64 columns packed to 16 bit
-#pragma unroll
-          for (int hh = 0; hh < 2; ++hh) {
-            uint32_t r[32];
-            tmem_ld_32x32(t_addr + uint32_t(col_local + 32 * hh), r);
-            tmem_ld_wait();
-            float v[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-            epi_bias_act32(ep, gcol + 32 * hh, v);
-#pragma unroll
-            for (int j = 0; j < 16; ++j) pk[16 * hh + j] = pack16(bf, v[2 * j], v[2 * j + 1]);
-          }
-          if (lane == 0) tma_store_wait_read0();  // the previous TMA store has finished reading the staging buffer
-          __syncwarp();
-#pragma unroll
-          for (int q = 0; q < 8; ++q)  // row `lane`, 16-byte chunk q -> swizzled position q ^ (lane & 7)
-            *reinterpret_cast<uint4*>(stg + lane * 128 + ((q ^ (lane & 7)) << 4)) =
-                make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0 && m_blk * kBM + quad * 32 < ep.M) {
-            tma_store_2d(&tmC, stg, gcol, m_blk * kBM + quad * 32);
-            tma_store_commit();
-          }
-        }
-      } else if (ep.coalesced) {
-        // fp32 output (+ residual, + row scatter).  Accumulators arrive row-per-thread; a 32x32 fp32 chunk is
-        // transposed through the swizzled staging buffer so that every global access of the warp covers 4 full
-        // 128-byte lines (8 lanes x 16 B per row) instead of 32 partial ones.
-        float* outp = reinterpret_cast<float*>(ep.out);
-#pragma unroll 1
-        for (int c = 0; c < BN / 2; c += 32) {
-          const int col_local = half * (BN / 2) + c;
-          const int gcol = n_blk * BN + col_local;
-          if (gcol >= ep.N) break;  // warp-uniform
-          uint32_t r[32];
-          tmem_ld_32x32(t_addr + uint32_t(col_local), r);
-          tmem_ld_wait();
-          float v[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-          epi_bias_act32(ep, gcol, v);
-#pragma unroll
-          for (int k = 0; k < 8; ++k)
-            *reinterpret_cast<float4*>(stg + lane * 128 + ((k ^ (lane & 7)) << 4)) =
-                make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
-          __syncwarp();
-          float4 val[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int i = 4 * j + (lane >> 3);
-            const float4 t = *reinterpret_cast<const float4*>(stg + i * 128 + ((q ^ (i & 7)) << 4));
-            val[j] = make_float4(t.x + res[j].x, t.y + res[j].y, t.z + res[j].z, t.w + res[j].w);
-          }
-          if (c + 32 < BN / 2) load_resid(gcol + 32);   // next chunk's residual in flight during the stores
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            if (ok8[j]) *reinterpret_cast<float4*>(outp + orow8[j] * ep.ldo + gcol + 4 * q) = val[j];
-          __syncwarp();
-        }
-      } else {
-        const long long orow = row_ok ? epi_out_row(ep, row) : 0;
-#pragma unroll 1
-        for (int c = 0; c < BN / 2; c += 32) {
-          const int col_local = half * (BN / 2) + c;
-          const int gcol = n_blk * BN + col_local;
-          if (gcol >= ep.N) break;  // warp-uniform
-          uint32_t r[32];
-          tmem_ld_32x32(t_addr + uint32_t(col_local), r);
-          tmem_ld_wait();
-          if (row_ok) epi_store_chunk32(ep, orow, gcol, r);
-        }
-      }
+      epilogue_tile<BN>(ep, &tmC, stg, tmem_base + uint32_t(as * BN), &tfull[as], aph, m_blk, n_blk, quad, half, lane);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[as]);
@@ -338,7 +225,7 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_tmap_encoder() {
 }
 
 // rows x cols row-major tensor, box = box_rows x 128 bytes, 128-byte swizzle, OOB zero fill / clipping.
-static int make_tmap(CUtensorMap* tm, const void* ptr, long long ld, long long rows, long long cols, int dtype, int box_rows,
+int make_tmap(CUtensorMap* tm, const void* ptr, long long ld, long long rows, long long cols, int dtype, int box_rows,
                      bool as_tf32) {
   auto enc = get_tmap_encoder();
   if (!enc) return set_error("cuTensorMapEncodeTiled entry point not available (driver too old?)");
@@ -360,7 +247,7 @@ static int make_tmap(CUtensorMap* tm, const void* ptr, long long ld, long long r
 }
 
 static int g_num_sms = 0;
-static int num_sms() {
+int num_sms() {
   if (!g_num_sms) {
     int dev = 0;
     cudaGetDevice(&dev);
@@ -442,6 +329,10 @@ int launch_gemm(const void* A, long long lda, const void* W, long long ldw, int 
                              ep.vec_ok;
   ep.tma_store = (tune.tma_store != 0 && can_tma_store) ? 1 : 0;
   ep.coalesced = (!ep.tma_store && tune.tma_store != 0 && ep.out_dtype == DT_F32 && ep.vec_ok && (N % 32 == 0)) ? 1 : 0;
+  // CTA pairs (cta_group::2): 256x256 tiles with the weight tile split across the two SMs - a third less
+  // shared-memory ingest per MMA than the single-CTA kernel, which is what bounds the large-K GEMMs.
+  const bool pair_ok = in_dtype != DT_F32 && N % 256 == 0 && num_m * (N / 256) >= 2 * num_sms();
+  if (pair_ok && tune.pair != 0) return launch_gemm_pair(A, lda, W, ldw, in_dtype, M, N, K, ep, tune, stream);
   CUtensorMap tmA, tmB, tmC;
   if (int e = make_tmap(&tmA, A, lda, M, K, in_dtype, kBM, true)) return e;
   if (int e = make_tmap(&tmB, W, ldw, N, K, in_dtype, BN / cs, true)) return e;

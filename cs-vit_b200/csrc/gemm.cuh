@@ -132,6 +132,131 @@ __device__ __forceinline__ void epi_store_chunk32(const EpiParams& ep, long long
   }
 }
 
+
+// ----------------------------------------------------------------------------------------------------
+// Tile epilogue shared by the tcgen05 GEMM kernels: one warp drains its 32 TMEM lanes x (BN/2) columns.
+// ----------------------------------------------------------------------------------------------------
+constexpr int kBM = 128;
+constexpr int kGemmThreads = 320;
+constexpr int kEpiWarps = 8;
+constexpr uint32_t kStageBufBytes = 32 * 128;  // per epilogue warp: 32 rows x 128 B of swizzled staging
+
+template <int BN>
+__device__ __forceinline__ void epilogue_tile(const EpiParams& ep, const CUtensorMap* tmC, uint8_t* stg, uint32_t tmem_tile,
+                                              uint64_t* tfull_bar, uint32_t aph, int m_blk, int n_blk, int quad, int half,
+                                              int lane) {
+  const bool bf = ep.out_dtype == DT_BF16;
+  const int row_in_tile = quad * 32 + lane;
+        const int row = m_blk * kBM + row_in_tile;
+        const bool row_ok = row < ep.M;
+        // Residual epilogue: row addresses do not depend on the MMA result, so the first chunk's residual
+        // lines are requested BEFORE waiting for the accumulator (and chunk c+1's while chunk c is processed).
+        long long orow8[8];
+        bool ok8[8];
+        float4 res[8];
+        const int q = lane & 7;
+        auto load_resid = [&](int gcol) {
+  #pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            res[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ep.resid && ok8[j] && gcol < ep.N)
+              res[j] = *reinterpret_cast<const float4*>(ep.resid + orow8[j] * ep.ldr + gcol + 4 * q);
+          }
+        };
+        if (ep.coalesced) {
+  #pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int rr = m_blk * kBM + quad * 32 + 4 * j + (lane >> 3);
+            ok8[j] = rr < ep.M;
+            orow8[j] = ok8[j] ? epi_out_row(ep, rr) : 0;
+          }
+          load_resid(n_blk * BN + half * (BN / 2));
+        }
+        mbar_wait(tfull_bar, aph);
+        tc_fence_after();
+        const uint32_t t_addr = tmem_tile + (uint32_t(quad * 32) << 16);
+        if (ep.tma_store) {
+  #pragma unroll 1
+          for (int c = 0; c < BN / 2; c += 64) {
+            const int col_local = half * (BN / 2) + c;
+            const int gcol = n_blk * BN + col_local;
+            if (gcol >= ep.N) break;  // warp-uniform
+            uint32_t pk[32];          // 64 columns packed to 16 bit
+  #pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+              uint32_t r[32];
+              tmem_ld_32x32(t_addr + uint32_t(col_local + 32 * hh), r);
+              tmem_ld_wait();
+              float v[32];
+  #pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+              epi_bias_act32(ep, gcol + 32 * hh, v);
+  #pragma unroll
+              for (int j = 0; j < 16; ++j) pk[16 * hh + j] = pack16(bf, v[2 * j], v[2 * j + 1]);
+            }
+            if (lane == 0) tma_store_wait_read0();  // the previous TMA store has finished reading the staging buffer
+            __syncwarp();
+  #pragma unroll
+            for (int q = 0; q < 8; ++q)  // row `lane`, 16-byte chunk q -> swizzled position q ^ (lane & 7)
+              *reinterpret_cast<uint4*>(stg + lane * 128 + ((q ^ (lane & 7)) << 4)) =
+                  make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0 && m_blk * kBM + quad * 32 < ep.M) {
+              tma_store_2d(tmC, stg, gcol, m_blk * kBM + quad * 32);
+              tma_store_commit();
+            }
+          }
+        } else if (ep.coalesced) {
+          // fp32 output (+ residual, + row scatter).  Accumulators arrive row-per-thread; a 32x32 fp32 chunk is
+          // transposed through the swizzled staging buffer so that every global access of the warp covers 4 full
+          // 128-byte lines (8 lanes x 16 B per row) instead of 32 partial ones.
+          float* outp = reinterpret_cast<float*>(ep.out);
+  #pragma unroll 1
+          for (int c = 0; c < BN / 2; c += 32) {
+            const int col_local = half * (BN / 2) + c;
+            const int gcol = n_blk * BN + col_local;
+            if (gcol >= ep.N) break;  // warp-uniform
+            uint32_t r[32];
+            tmem_ld_32x32(t_addr + uint32_t(col_local), r);
+            tmem_ld_wait();
+            float v[32];
+  #pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+            epi_bias_act32(ep, gcol, v);
+  #pragma unroll
+            for (int k = 0; k < 8; ++k)
+              *reinterpret_cast<float4*>(stg + lane * 128 + ((k ^ (lane & 7)) << 4)) =
+                  make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+            __syncwarp();
+            float4 val[8];
+  #pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int i = 4 * j + (lane >> 3);
+              const float4 t = *reinterpret_cast<const float4*>(stg + i * 128 + ((q ^ (i & 7)) << 4));
+              val[j] = make_float4(t.x + res[j].x, t.y + res[j].y, t.z + res[j].z, t.w + res[j].w);
+            }
+            if (c + 32 < BN / 2) load_resid(gcol + 32);   // next chunk's residual in flight during the stores
+  #pragma unroll
+            for (int j = 0; j < 8; ++j)
+              if (ok8[j]) *reinterpret_cast<float4*>(outp + orow8[j] * ep.ldo + gcol + 4 * q) = val[j];
+            __syncwarp();
+          }
+        } else {
+          const long long orow = row_ok ? epi_out_row(ep, row) : 0;
+  #pragma unroll 1
+          for (int c = 0; c < BN / 2; c += 32) {
+            const int col_local = half * (BN / 2) + c;
+            const int gcol = n_blk * BN + col_local;
+            if (gcol >= ep.N) break;  // warp-uniform
+            uint32_t r[32];
+            tmem_ld_32x32(t_addr + uint32_t(col_local), r);
+            tmem_ld_wait();
+            if (row_ok) epi_store_chunk32(ep, orow, gcol, r);
+          }
+        }
+}
+
 // Host launchers (gemm.cu).  in_dtype: DT_BF16 / DT_F16 -> tcgen05 kind::f16 (W in the same format);
 // DT_F32 -> tcgen05 kind::tf32 when impl == GEMM_TC, exact fp32 FMA when impl == GEMM_SIMT.
 enum : int { GEMM_TC = 0, GEMM_SIMT = 1 };
@@ -139,7 +264,13 @@ struct GemmTuning {
   int max_ctas;   // 0 = one per SM
   int cluster;    // 0 = auto, else 1 / 2 / 4 CTAs sharing the weight tile by TMA multicast
   int tma_store;  // -1 = auto, 0 = direct stores, 1 = smem-staged TMA stores where legal
+  int pair;       // -1 = auto, 0 = never, 1 = CTA-pair (cta_group::2) kernel where legal
 };
+int make_tmap(CUtensorMap* tm, const void* ptr, long long ld, long long rows, long long cols, int dtype, int box_rows,
+              bool as_tf32);
+int num_sms();
+int launch_gemm_pair(const void* A, long long lda, const void* W, long long ldw, int in_dtype, int M, int N, int K,
+                     const EpiParams& ep, const GemmTuning& tune, cudaStream_t stream);
 int launch_gemm(const void* A, long long lda, const void* W, long long ldw, int in_dtype, int M, int N, int K,
                 const EpiParams& ep, int impl, const GemmTuning& tune, cudaStream_t stream);
 

@@ -1,0 +1,171 @@
+// CTA-pair GEMM: two CTAs of a cluster (one TPC) execute `tcgen05.mma.cta_group::2` on a 256 x 256 output tile.
+//
+// Why: the single-CTA kernel (gemm.cu) is bounded by bytes entering each SM's shared memory - a 128x256 tile
+// needs 16 KB of A and 32 KB of W per 512 MMA cycles (96 B/clk), and multicasting W does not lower that
+// (profiles/r1_gemm_sweep_cluster_tmastore.txt).  With a pair, each CTA holds its own 128 rows of A and only
+// HALF of the 256-row weight tile; the MMA reads the two halves from both SMs.  Ingest per CTA drops to
+// 16 + 16 KB per 512 cycles (64 B/clk) and the smem ring deepens from 4 to 6 stages.
+//
+// Protocol (rank 0 = leader):
+//   full[s]   lives in the leader, count 2: each CTA's producer arms it (remote arrive.expect_tx) with its own
+//             32 KB and issues its TMA loads with `.cta_group::2`, crediting the leader's barrier.
+//   MMA       issued by the leader's elected thread only; `tcgen05.commit.cta_group::2` multicasts the arrival
+//             to empty[s] (slot free) and tfull[a] (accumulator ready) of BOTH CTAs.
+//   tempty[a] lives in the leader, count 2*8: the epilogue warps of both CTAs arrive on it (remote for rank 1).
+//   TMEM      allocated with cta_group::2 by the same warp of both CTAs; each CTA drains its own 128 lanes.
+#include "errors.h"
+#include "gemm.cuh"
+
+namespace csvit {
+
+constexpr int kPairBN = 256;
+constexpr int kPairStages = 6;
+constexpr uint32_t kPairABytes = kBM * 128;               // 128 rows x 128 B
+constexpr uint32_t kPairBBytes = (kPairBN / 2) * 128;     // this CTA's half of the weight tile
+constexpr uint32_t kPairStageBytes = kPairABytes + kPairBBytes;
+constexpr uint32_t kPairTiles = kPairStages * kPairStageBytes;
+constexpr uint32_t kPairStg = kEpiWarps * kStageBufBytes;
+constexpr size_t kPairSmem = 1024 + size_t(kPairTiles) + kPairStg + 256;
+
+template <int FMT>  // 0 = fp16, 1 = bf16
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ CUtensorMap tmC, int K, EpiParams ep) {
+  constexpr int BN = kPairBN, STAGES = kPairStages, BK = 64;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
+  uint8_t* tiles = smem;
+  uint8_t* staging = smem + kPairTiles;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kPairTiles + kPairStg);
+  uint64_t* full = bars;                     // [STAGES]  (used in the leader)
+  uint64_t* empty = bars + STAGES;           // [STAGES]
+  uint64_t* tfull = bars + 2 * STAGES;       // [2]
+  uint64_t* tempty = bars + 2 * STAGES + 2;  // [2]       (used in the leader)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair_id = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+  const int num_mp = (ep.M + 2 * kBM - 1) / (2 * kBM);
+  const int num_n = (ep.N + BN - 1) / BN;
+  const int num_ptiles = num_mp * num_n;
+  const int num_kb = (K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+    if (ep.tma_store) prefetch_tmap(&tmC);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 2); mbar_init(&empty[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 2 * kEpiWarps); }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc_pair(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ---------------- TMA producer (both CTAs) ----------------
+    if (lane == 0) {
+      int s = 0; uint32_t ph = 0;
+      for (int pt = pair_id; pt < num_ptiles; pt += num_pairs) {
+        const int mp = pt / num_n, n_blk = pt - mp * num_n;
+        const int m_blk = mp * 2 + int(rank);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty[s], ph ^ 1u);
+          const uint32_t lfull = mapa_u32(smem_u32(&full[s]), 0);
+          mbar_arrive_expect_tx_cluster(lfull, kPairStageBytes);
+          uint8_t* sa = tiles + size_t(s) * kPairStageBytes;
+          tma_load_2d_pair(sa, &tmA, lfull, kb * BK, m_blk * kBM);
+          tma_load_2d_pair(sa + kPairABytes, &tmB, lfull, kb * BK, n_blk * BN + int(rank) * (BN / 2));
+          if (++s == STAGES) { s = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------- MMA issuer (leader CTA only) ----------------
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = make_idesc(uint32_t(FMT), 2 * kBM, BN);
+      int s = 0; uint32_t ph = 0;
+      int as = 0; uint32_t aph = 0;
+      for (int pt = pair_id; pt < num_ptiles; pt += num_pairs) {
+        mbar_wait(&tempty[as], aph ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + uint32_t(as * BN);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          const uint32_t sa = base + uint32_t(s) * kPairStageBytes;
+          const uint64_t adesc = make_sw128_kmajor_desc(sa);
+          const uint64_t bdesc = make_sw128_kmajor_desc(sa + kPairABytes);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_ss_pair(d_tmem, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), idesc, (kb | k) ? 1u : 0u);
+          umma_commit_pair(&empty[s], 3);
+          if (kb == num_kb - 1) umma_commit_pair(&tfull[as], 3);
+          if (++s == STAGES) { s = 0; ph ^= 1u; }
+        }
+        if (++as == 2) { as = 0; aph ^= 1u; }
+      }
+    }
+  } else {
+    // ---------------- epilogue (both CTAs, own 128 TMEM lanes) ----------------
+    const int e = warp - 2;
+    const int quad = warp & 3;
+    const int half = e >> 2;
+    uint8_t* stg = staging + e * kStageBufBytes;
+    int as = 0; uint32_t aph = 0;
+    for (int pt = pair_id; pt < num_ptiles; pt += num_pairs) {
+      const int mp = pt / num_n, n_blk = pt - mp * num_n;
+      const int m_blk = mp * 2 + int(rank);
+      epilogue_tile<BN>(ep, &tmC, stg, tmem_base + uint32_t(as * BN), &tfull[as], aph, m_blk, n_blk, quad, half, lane);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty[as]), 0));
+      if (++as == 2) { as = 0; aph ^= 1u; }
+    }
+    if (ep.tma_store && lane == 0) tma_store_wait_all();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) tmem_dealloc_pair(tmem_base, 512);
+}
+
+template <int FMT>
+static int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, int K, const EpiParams& ep,
+                       int max_ctas, cudaStream_t stream) {
+  static bool configured = false;
+  auto kern = gemm_pair_kernel<FMT>;
+  if (!configured) {
+    CSVIT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kPairSmem)));
+    configured = true;
+  }
+  const int num_mp = (ep.M + 2 * kBM - 1) / (2 * kBM), num_n = (ep.N + kPairBN - 1) / kPairBN;
+  int pairs = (max_ctas > 0 ? max_ctas : num_sms()) / 2;
+  if (pairs > num_mp * num_n) pairs = num_mp * num_n;
+  if (pairs < 1) pairs = 1;
+  kern<<<pairs * 2, kGemmThreads, kPairSmem, stream>>>(tmA, tmB, tmC, K, ep);
+  CSVIT_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_gemm_pair(const void* A, long long lda, const void* W, long long ldw, int in_dtype, int M, int N, int K,
+                     const EpiParams& ep, const GemmTuning& tune, cudaStream_t stream) {
+  CUtensorMap tmA, tmB, tmC;
+  if (int e = make_tmap(&tmA, A, lda, M, K, in_dtype, kBM, true)) return e;
+  if (int e = make_tmap(&tmB, W, ldw, N, K, in_dtype, kPairBN / 2, true)) return e;
+  if (ep.tma_store) {
+    if (int e = make_tmap(&tmC, ep.out, ep.ldo, M, N, ep.out_dtype, 32, false)) return e;
+  } else {
+    tmC = tmA;
+  }
+  if (in_dtype == DT_BF16) return launch_pair<1>(tmA, tmB, tmC, K, ep, tune.max_ctas, stream);
+  return launch_pair<0>(tmA, tmB, tmC, K, ep, tune.max_ctas, stream);
+}
+
+}  // namespace csvit

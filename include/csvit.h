@@ -105,8 +105,9 @@ CSVIT_API int csvit_linear(const void* A, long long lda, const void* W, long lon
 /* Process-wide tuning knobs of the GEMM engine (benchmarking / ablation; defaults are automatic):
  *   cluster   0 = auto, 1 / 2 / 4 = CTAs per cluster sharing the weight tile by TMA multicast
  *   tma_store -1 = auto, 0 = direct register stores, 1 = smem-staged TMA stores where legal
- *   max_ctas  0 = one CTA per SM */
-CSVIT_API int csvit_set_gemm_tuning(int cluster, int tma_store, int max_ctas);
+ *   max_ctas  0 = one CTA per SM
+ *   pair      -1 = auto, 0 = never, 1 = CTA-pair (cta_group::2, 256-row MMA) kernel where legal */
+CSVIT_API int csvit_set_gemm_tuning(int cluster, int tma_store, int max_ctas, int pair);
 
 /* ---- attention cores -------------------------------------------------------------------------------------
  * Swin window attention on window-ordered qkv[B*H*W, 3C] (Q|K|V column blocks, head h at columns 32h..):

@@ -46,6 +46,27 @@ def test_linear_plain(ops, M, N, K, dtype):
     assert rel(out, ref) < tol, (dtype, M, N, K, rel(out, ref))
 
 
+@pytest.mark.parametrize("dt", [torch.bfloat16, torch.float16])
+def test_linear_pair_kernel_matches_single(ops, dt):
+    """cta_group::2 kernel (auto-selected for large problems) against the single-CTA kernel and fp32 math."""
+    g = torch.Generator(device="cuda").manual_seed(11)
+    M, N, K = 148 * 2 * 256 + 77, 512, 320
+    a = torch.randn(M, K, device="cuda", generator=g).to(dt)
+    w = (torch.randn(N, K, device="cuda", generator=g) * 0.05).to(dt)
+    b = torch.randn(N, device="cuda", generator=g)
+    x = torch.randn(M, N, device="cuda", generator=g)
+    try:
+        outs = {}
+        for pair in (0, 1):
+            ops.set_gemm_tuning(0, -1, 0, pair)
+            outs[pair] = (ops.linear(a, w, b, act=ops.ACT_GELU, out_dtype=dt), ops.linear(a, w, b, resid=x, out_dtype=torch.float32))
+    finally:
+        ops.set_gemm_tuning()
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    ref = a[-3000:].float() @ w.float().T + b + x[-3000:]
+    assert rel(outs[1][1][-3000:], ref) < 1e-5
+
+
 def test_linear_epilogues(ops):
     g = torch.Generator(device="cuda").manual_seed(5)
     B, H, W, C = 3, 14, 14, 256

@@ -13,8 +13,8 @@ for s, (n, c) in enumerate([(3136, 128), (784, 256), (196, 512), (49, 1024)]):
     shapes += [(f"s{s} qkv", M, 3 * c, c, "store"), (f"s{s} proj", M, c, c, "resid"),
                (f"s{s} fc1", M, 4 * c, c, "gelu"), (f"s{s} fc2", M, c, 4 * c, "resid")]
 only = os.environ.get("ONLY")
-configs = [(1, 0), (1, 1), (2, 1), (4, 1), (2, 0)]
-print(f"{'shape':10s} {'M':>7s} {'N':>5s} {'K':>5s} {'epi':6s} " + " ".join(f"cs{c}/tma{t}".rjust(10) for c, t in configs))
+configs = [(1, 0, 0), (1, 1, 0), (1, 1, 1)]
+print(f"{'shape':10s} {'M':>7s} {'N':>5s} {'K':>5s} {'epi':6s} " + " ".join(f"cs{c}/t{t}/p{p}".rjust(10) for c, t, p in configs))
 for name, M, N, K, epi in shapes:
     if only and only not in name: continue
     g = torch.Generator(device="cuda").manual_seed(1)
@@ -24,8 +24,8 @@ for name, M, N, K, epi in shapes:
     x = torch.randn(M, N, device="cuda", generator=g) if epi == "resid" else None
     res = []
     ref = None
-    for cs, tma in configs:
-        ops.set_gemm_tuning(cs, tma, 0)
+    for cs, tma, pair in configs:
+        ops.set_gemm_tuning(cs, tma, 0, pair)
         def run():
             if epi == "store": return ops.linear(a, w, b, out_dtype=dt)
             if epi == "gelu": return ops.linear(a, w, b, act=ops.ACT_GELU, out_dtype=dt)
@@ -36,7 +36,7 @@ for name, M, N, K, epi in shapes:
                 rr = a[:4096].float() @ w.float().T + b
                 ref = torch.nn.functional.gelu(rr) if epi == "gelu" else rr
             err = ((out[:4096].float() - ref).norm() / ref.norm()).item()
-            assert err < 6e-3, (name, cs, tma, err)
+            assert err < 6e-3, (name, cs, tma, pair, err)
         for _ in range(2): run()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         it = 10

@@ -107,6 +107,10 @@ class SwinBackboneB200(nn.Module):
         super().__init__()
         self.config = config
         self.precision = precision
+        # LayerNorm-prologue pair GEMM (csvit_ln_linear) for Q/K/V and fc1.  Correct and tested, but measured slower than
+        # csvit_layernorm + csvit_linear on B200 (profiles/r1_lnlinear_vs_unfused.txt: the LayerNorm phase is exposed, not
+        # overlapped with the MMAs), so it is opt-in until the A tile can be double-buffered.
+        self.fuse_ln = False
         c0, eps, ws = config.embed_dim, config.layer_norm_eps, config.window_size
         self.embeddings = _holder(
             patch_embeddings=_holder(projection=nn.Conv2d(3, c0, kernel_size=4, stride=4)),
@@ -186,17 +190,26 @@ class SwinBackboneB200(nn.Module):
                            sa.relative_position_bias_table.detach(), ws))
         eps = cfg.layer_norm_eps
         ln1, ln2 = blk.layernorm_before, blk.layernorm_after
-        xn = ops.layernorm(x, self._f32(key + "ln1w", ln1.weight), self._f32(key + "ln1b", ln1.bias), eps, out_dtype=act,
-                           mode=ops.LN_WINDOW, grid=(H, W), ws=ws, shift=shift)
-        qkv = ops.linear(xn, wqkv, bqkv, out_dtype=act, impl=impl)
+        fused_ln = self.fuse_ln and not self._fp32 and x.shape[1] in ops.LN_LINEAR_WIDTHS
+        if fused_ln:   # LayerNorm + shift/partition gather + Q/K/V in one kernel, xn never leaves the SM
+            qkv = ops.ln_linear(x, self._f32(key + "ln1w", ln1.weight), self._f32(key + "ln1b", ln1.bias), eps, wqkv, bqkv,
+                                mode=ops.LN_WINDOW, grid=(H, W), ws=ws, shift=shift)
+        else:
+            xn = ops.layernorm(x, self._f32(key + "ln1w", ln1.weight), self._f32(key + "ln1b", ln1.bias), eps, out_dtype=act,
+                               mode=ops.LN_WINDOW, grid=(H, W), ws=ws, shift=shift)
+            qkv = ops.linear(xn, wqkv, bqkv, out_dtype=act, impl=impl)
         ctx = ops.window_attention(qkv, bias, B, H, W, heads, ws, shift)
         proj = blk.attention.output.dense
         ops.linear(ctx, self._weight(key + "wproj", proj.weight), self._f32(key + "bproj", proj.bias), resid=x, out=x,
                    scatter=(H, W, ws, shift), impl=impl)
-        xn = ops.layernorm(x, self._f32(key + "ln2w", ln2.weight), self._f32(key + "ln2b", ln2.bias), eps, out_dtype=act)
         fc1, fc2 = blk.intermediate.dense, blk.output.dense
-        hid = ops.linear(xn, self._weight(key + "w1", fc1.weight), self._f32(key + "b1", fc1.bias), act=ops.ACT_GELU,
-                         out_dtype=act, impl=impl)
+        if fused_ln:
+            hid = ops.ln_linear(x, self._f32(key + "ln2w", ln2.weight), self._f32(key + "ln2b", ln2.bias), eps,
+                                self._weight(key + "w1", fc1.weight), self._f32(key + "b1", fc1.bias), act=ops.ACT_GELU)
+        else:
+            xn = ops.layernorm(x, self._f32(key + "ln2w", ln2.weight), self._f32(key + "ln2b", ln2.bias), eps, out_dtype=act)
+            hid = ops.linear(xn, self._weight(key + "w1", fc1.weight), self._f32(key + "b1", fc1.bias), act=ops.ACT_GELU,
+                             out_dtype=act, impl=impl)
         ops.linear(hid, self._weight(key + "w2", fc2.weight), self._f32(key + "b2", fc2.bias), resid=x, out=x, impl=impl)
 
     @torch.no_grad()

@@ -209,6 +209,27 @@ def linear(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
     return out
 
 
+def ln_linear(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float, w: torch.Tensor,
+              bias: Optional[torch.Tensor] = None, *, act: int = ACT_NONE, mode: int = LN_IDENTITY,
+              grid: Tuple[int, int] = (0, 0), ws: int = 0, shift: int = 0) -> torch.Tensor:
+    """``act(LayerNorm(x rows) @ w.T + bias)`` in one kernel (see ``csvit_ln_linear``); x fp32 ``[M, C]``, w 16-bit ``[N, C]``."""
+    _dev(x, gamma, beta, w, bias)
+    if x.dtype != torch.float32 or not x.is_contiguous():
+        raise ValueError("ln_linear input must be contiguous float32")
+    M, C = x.shape
+    N, C2, ldw = _rows2d(w)
+    if C2 != C or w.dtype not in (torch.bfloat16, torch.float16):
+        raise ValueError("ln_linear: weight must be 16-bit [N, C]")
+    out = torch.empty(M, N, dtype=w.dtype, device=x.device)
+    H, W = grid
+    _call("csvit_ln_linear", x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), float(eps), mode, H, W, ws, shift, w.data_ptr(),
+          ldw, _code(w.dtype), M, N, C, _p(bias), act, out.data_ptr(), out.stride(0), _stream(), flops=2.0 * M * N * C)
+    return out
+
+
+LN_LINEAR_WIDTHS = (128, 256, 512)
+
+
 # ---------------------------------------------------------------------------------------------- attention
 def window_attention(qkv: torch.Tensor, bias_exp: torch.Tensor, B: int, H: int, W: int, heads: int, ws: int,
                      shift: int) -> torch.Tensor:

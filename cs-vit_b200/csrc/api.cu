@@ -144,6 +144,19 @@ int csvit_linear(const void* A, long long lda, const void* W, long long ldw, int
   return launch_gemm(A, lda, W, ldw, in_dtype, M, N, K, ep, impl, g_tune, S(stream));
 }
 
+int csvit_ln_linear(const float* x, const float* gamma, const float* beta, float eps, int mode, int H, int W, int ws,
+                    int shift, const void* Wt, long long ldw, int dtype, int M, int N, int C, const float* bias, int act,
+                    void* out, long long ldo, void* stream) {
+  CSVIT_REQUIRE(act >= ACT_NONE && act <= ACT_RELU, "ln_linear: bad activation %d", act);
+  WinGeom g = make_geom(H > 0 ? H : 1, W > 0 ? W : 1, ws > 0 ? ws : 1, shift);
+  if (mode == LN_WINDOW) {
+    CSVIT_REQUIRE(ws > 0 && H % ws == 0 && W % ws == 0, "ln_linear(window): %dx%d not divisible by window %d", H, W, ws);
+    CSVIT_REQUIRE(shift >= 0 && shift < ws, "ln_linear(window): shift %d outside [0,%d)", shift, ws);
+    CSVIT_REQUIRE(M % (H * W) == 0, "ln_linear(window): M=%d not a multiple of %d tokens", M, H * W);
+  }
+  return launch_ln_gemm(x, gamma, beta, eps, mode, g, Wt, ldw, dtype, M, N, C, bias, act, out, ldo, S(stream));
+}
+
 int csvit_set_gemm_tuning(int cluster, int tma_store, int max_ctas, int pair) {
   g_tune.pair = pair;
   CSVIT_REQUIRE(cluster == 0 || cluster == 1 || cluster == 2 || cluster == 4, "gemm tuning: cluster %d not in {0,1,2,4}", cluster);

@@ -18,6 +18,11 @@ int launch_rel_index(int ws, int* out, cudaStream_t stream);
 int launch_merge_index_map(int H, int W, int* out, cudaStream_t stream);
 int launch_expand_rel_bias(const float* table, float* out, int heads, int ws, cudaStream_t stream);
 
+// lngemm.cu
+int launch_ln_gemm(const float* x, const float* gamma, const float* beta, float eps, int mode, const WinGeom& g,
+                   const void* W, long long ldw, int dtype, int M, int N, int C, const float* bias, int act, void* out,
+                   long long ldo, cudaStream_t stream);
+
 // attention.cu
 int launch_expand_rel_bias_mma(const float* table, float* out, int heads, cudaStream_t stream);
 int launch_window_attention_mma(const void* qkv, const float* bias_frag, void* out, int dtype, int B, int H, int W,

@@ -102,6 +102,16 @@ CSVIT_API int csvit_linear(const void* A, long long lda, const void* W, long lon
                  int out_dtype, int scatter_H, int scatter_W, int scatter_ws, int scatter_shift, int impl,
                  void* stream);
 
+/* LayerNorm fused into the GEMM that consumes it (CTA-pair tcgen05 kernel, normalised tile resident in smem):
+ *   out[M, N] = act( LayerNorm(x_rows)[M, C] @ Wt[N, C]^T + bias ),  16-bit Wt / out (dtype), x fp32 [*, C].
+ *   mode CSVIT_LN_IDENTITY: row r of x;  CSVIT_LN_WINDOW: rows gathered in shifted-window order (as csvit_layernorm).
+ *   C in {128, 256, 512}, N a multiple of 64.
+ * Replaces csvit_layernorm + csvit_linear for layernorm_before -> Q/K/V (HF:606-622, 404-406) and
+ * layernorm_after -> intermediate.dense + GELU (HF:648, 514-519); the normalised activations never reach HBM. */
+CSVIT_API int csvit_ln_linear(const float* x, const float* gamma, const float* beta, float eps, int mode, int H, int W, int ws,
+                              int shift, const void* Wt, long long ldw, int dtype, int M, int N, int C, const float* bias,
+                              int act, void* out, long long ldo, void* stream);
+
 /* Process-wide tuning knobs of the GEMM engine (benchmarking / ablation; defaults are automatic):
  *   cluster   0 = auto, 1 / 2 / 4 = CTAs per cluster sharing the weight tile by TMA multicast
  *   tma_store -1 = auto, 0 = direct register stores, 1 = smem-staged TMA stores where legal

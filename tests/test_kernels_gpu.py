@@ -67,6 +67,31 @@ def test_linear_pair_kernel_matches_single(ops, dt):
     assert rel(outs[1][1][-3000:], ref) < 1e-5
 
 
+@pytest.mark.parametrize("C,N,mode,gelu", [(128, 384, 1, False), (256, 1024, 0, True), (512, 1536, 1, False), (512, 2048, 0, True)])
+@pytest.mark.parametrize("dt", [torch.bfloat16, torch.float16])
+def test_ln_linear_matches_unfused(ops, C, N, mode, gelu, dt):
+    """LayerNorm-prologue pair GEMM against csvit_layernorm + csvit_linear and against fp32 torch math."""
+    g = torch.Generator(device="cuda").manual_seed(C + N)
+    B, H, W = 5, 14, 14
+    x = torch.randn(B * H * W, C, device="cuda", generator=g) * 1.5 + 0.3
+    gamma = 1 + 0.2 * torch.randn(C, device="cuda", generator=g)
+    beta = 0.2 * torch.randn(C, device="cuda", generator=g)
+    w = (torch.randn(N, C, device="cuda", generator=g) * 0.05).to(dt)
+    b = torch.randn(N, device="cuda", generator=g) * 0.1
+    act = ops.ACT_GELU if gelu else ops.ACT_NONE
+    for shift in ((0, 3) if mode == 1 else (0,)):
+        kw = dict(mode=mode, grid=(H, W), ws=7, shift=shift)
+        fused = ops.ln_linear(x, gamma, beta, 1e-5, w, b, act=act, **kw)
+        xn = ops.layernorm(x, gamma, beta, 1e-5, out_dtype=dt, **kw)
+        unfused = ops.linear(xn, w, b, act=act, out_dtype=dt)
+        src = x if mode == 0 else x.view(B, H * W, C)[:, ops.window_index_map(H, W, 7, shift).long()].reshape(-1, C)
+        ref = torch.nn.functional.layer_norm(src, (C,), gamma, beta, 1e-5) @ w.float().T + b
+        ref = torch.nn.functional.gelu(ref) if gelu else ref
+        tol = 8e-3 if dt == torch.bfloat16 else 1.5e-3
+        assert rel(fused, ref) < tol and rel(unfused, ref) < tol
+        assert rel(fused, unfused) < tol / 2
+
+
 def test_linear_epilogues(ops):
     g = torch.Generator(device="cuda").manual_seed(5)
     B, H, W, C = 3, 14, 14, 256

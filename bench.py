@@ -44,15 +44,19 @@ METRIC = "images/sec Swin-B spatial fwd @224^2 bs256"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--precision", choices=["bf16", "fp16"], default="bf16")
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--variant", default="swin_b")
+    ap.add_argument("--workload", choices=["spatial", "temporal"], default="spatial",
+                    help="spatial = BASELINE configs[1] (headline); temporal = configs[2]: 8-frame clips, realtime cross-frame attention")
+    ap.add_argument("--frames", type=int, default=8)
     ap.add_argument("--cpu-sample", type=int, default=16, help="images per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip roofline / e2e / fp16 passes (debug)")
+    ap.add_argument("--no-graph", action="store_true", help="launch kernels one by one instead of replaying a CUDA graph")
     return ap.parse_args()
 
 
@@ -186,42 +190,64 @@ def run_ours(a):
     tmp = tempfile.mkdtemp(prefix=f"csvit_bench_{rank}_")
     bdir = make_random_backbone_dir(os.path.join(tmp, a.variant), a.variant, seed=0)
     torch.manual_seed(0)
+    temporal = a.workload == "temporal"
+    T = a.frames if temporal else 1
+    clips = a.batch // T                      # same number of images per GPU in both workloads
     model = Poser(bdir, image_size=224, mano_layer=SyntheticMANO(), spatial_layer_type="encoder", persp_decorate="patch",
-                  precision=a.precision)
+                  precision=a.precision, temporal_supervision="realtime" if temporal else "full",
+                  temporal_init_method="random" if temporal else "zero")
     randomize_head_(model)
-    model.phase(Poser.TrainingPhase.SPATIAL)
+    model.phase(Poser.TrainingPhase.INFERENCE if temporal else Poser.TrainingPhase.SPATIAL)
     model.eval()
     model = model.to(dev)
 
-    host = make_inputs(a.batch, 1, 224, seed=100 + rank)
+    host = make_inputs(clips, T, 224, seed=100 + rank)
     keys = ("patches", "square_bboxes", "timestamp", "focal", "princpt")
     pinned = {k: host[k].pin_memory() for k in keys}
     resident = {k: pinned[k].to(dev) for k in keys}
 
-    def step(inp):
+    from cs_vit.graph import GraphedPredict
+
+    def eager_step(inp):
         with torch.no_grad():
             return model.predict_batch(inp["patches"], inp["square_bboxes"], inp["timestamp"], inp["focal"], inp["princpt"])
+
+    graphs = {}
+
+    def step(inp, slot=0):
+        """One predict_batch; replays a captured CUDA graph (one per input-buffer slot and precision)."""
+        if a.no_graph:
+            return eager_step(inp)
+        key = (model.precision, slot)
+        if key not in graphs:
+            graphs[key] = GraphedPredict(model, inp)
+        return graphs[key](inp["patches"], inp["square_bboxes"], inp["timestamp"], inp["focal"], inp["princpt"])
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed_loop(steps):
+    n0 = ops.launch_count
+    eager_step(resident)
+    launches_per_step = ops.launch_count - n0
+
+    def timed_loop(steps, fn=None):
         """K steps on device-resident inputs, CUDA events, max over ranks.  Returns (ms_total, launches)."""
+        fn = fn or step
         barrier()
         n0 = ops.launch_count
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(steps):
-            step(resident)
+            fn(resident)
         e1.record()
         torch.cuda.synchronize()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         barrier()
-        return ms.item(), ops.launch_count - n0
+        return ms.item(), max(ops.launch_count - n0, launches_per_step * steps)
 
     for _ in range(a.warmup):
         step(resident)
@@ -237,10 +263,13 @@ def run_ours(a):
         "metric": METRIC, "value": round(value, 1), "unit": "images/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": round(ms_total / a.steps, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": a.precision, "data": "synthetic",
-        "config": {"workload": f"{a.variant} spatial model (encoder head, addpat, dense persp) predict_batch, batch {a.batch}/GPU, 224x224, T=1",
+        "config": {"workload": (f"{a.variant} temporal model (realtime cross-frame attention), {clips} clips x {T} frames/GPU, 224x224"
+                                if temporal else
+                                f"{a.variant} spatial model (encoder head, addpat, dense persp) predict_batch, batch {a.batch}/GPU, 224x224, T=1"),
                    "global_batch": a.batch * world, "parallelism": f"dp{world}",
                    "l2_policy": "per-step inputs (154 MB) and activations (>1 GB) exceed the 126 MB L2; no explicit flush",
-                   "operands": f"{a.precision} tensor-core operands, fp32 accumulate/residual/LN/softmax, TF32 head"},
+                   "operands": f"{a.precision} tensor-core operands, fp32 accumulate/residual/LN/softmax, TF32 head",
+                   "launch": "eager" if a.no_graph else "CUDA graph replay of the step"},
         "gpu_launches": launches,
         "model_flops_frac_of_peak": round(value / world * FLOP_PER_IMAGE / (peak_tf * 1e12), 4),
         "clocks": clocks,
@@ -249,7 +278,7 @@ def run_ours(a):
     if not a.no_extras:
         # ---- roofline of the dominant kernel (GEMM engine), instrumented pass over the same K steps ----------
         ops.begin_profile("csvit_linear")
-        timed_loop(a.steps)
+        timed_loop(a.steps, eager_step)      # per-launch events need individual launches (no graph replay)
         prof = ops.end_profile()
         if prof["launches"]:
             ach = prof["flops"] / (prof["ms"] / 1e3) / 1e12
@@ -262,7 +291,7 @@ def run_ours(a):
         # ---- end-to-end: host inputs, H2D + D2H inside the timed region, double-buffered ------------------------
         copy_stream = torch.cuda.Stream(device=dev)
         bufs = [{k: torch.empty_like(resident[k]) for k in keys} for _ in range(2)]
-        host_out = torch.empty(a.batch, 1, 21, 3).pin_memory()
+        host_out = torch.empty(clips, 1, 21, 3).pin_memory()
         h2d = sum(pinned[k].numel() * pinned[k].element_size() for k in keys)
 
         def e2e_loop(steps):
@@ -287,7 +316,7 @@ def run_ours(a):
                 if i + 1 < steps:
                     upload(i + 1)
                 main.wait_event(ready[i % 2])
-                res = step(bufs[i % 2])
+                res = step(bufs[i % 2], slot=1 + i % 2)
                 host_out.copy_(res["joint_cam"], non_blocking=True)
                 freed[i % 2].record(main)
             e1.record()

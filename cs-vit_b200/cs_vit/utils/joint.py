@@ -4,8 +4,19 @@ from typing import List, Tuple
 import torch
 
 
+_EDGE_CACHE = {}
+
+
+def _edge_index(connection, device):
+    """Index tensors per (skeleton, device), built once: no host->device copy on the hot path (graph-capturable)."""
+    key = (connection, str(device))
+    if key not in _EDGE_CACHE:
+        _EDGE_CACHE[key] = (torch.tensor([i for i, _ in connection], device=device),
+                            torch.tensor([j for _, j in connection], device=device))
+    return _EDGE_CACHE[key]
+
+
 def mean_connection_length(joints: torch.Tensor, connection: List[Tuple[int, int]]) -> torch.Tensor:
     """Mean bone length over ``connection`` for joints ``(..., J, 3)`` -> ``(...)``   (ref:cs_vit/utils/joint.py:49-70)."""
-    a = torch.tensor([i for i, _ in connection], device=joints.device)
-    b = torch.tensor([j for _, j in connection], device=joints.device)
+    a, b = _edge_index(tuple(connection), joints.device)
     return (joints.index_select(-2, a) - joints.index_select(-2, b)).norm(dim=-1).mean(dim=-1)

@@ -21,11 +21,16 @@
 
 namespace csvit {
 
-constexpr int WA_LD = 40;                     // smem row pitch in 16-bit elements (80 B): conflict-free ldmatrix
+// Per-warp shared memory: Q, K, V as 49 dense 64-byte rows each (16-byte chunks XOR-swizzled by (row>>1)&3 so that
+// ldmatrix is conflict-free without padding), then 15 zero rows.  Fragment loads that run past a 49-row matrix
+// alias into the next one: harmless for Q (those query rows are never stored) and K (those key columns carry a
+// -inf bias); for V they hit the zero rows, and P is exactly 0 there.
 constexpr int WA_L = 49;
-constexpr int WA_Q_ROWS = 64, WA_K_ROWS = 56, WA_V_ROWS = 64;
-constexpr int WA_WARP_BYTES = (WA_Q_ROWS + WA_K_ROWS + WA_V_ROWS) * WA_LD * 2 + 64;  // + region ids
+constexpr int WA_ROW = 64;                                    // bytes per row (32 x 16 bit)
+constexpr int WA_WARP_BYTES = (3 * WA_L + 15) * WA_ROW + 64;  // + region ids
 constexpr int WA_WARPS = 4;
+constexpr int WA_BIAS_BYTES = 4 * 7 * 32 * 16;                // one head's fragment-ordered bias table
+__device__ __forceinline__ uint32_t wa_off(int row, int chunk) { return uint32_t(row * WA_ROW + ((chunk ^ ((row >> 1) & 3)) << 4)); }
 
 __device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const void* p) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
@@ -75,27 +80,29 @@ __global__ void expand_rel_bias_mma_kernel(const float* __restrict__ table, floa
 }
 
 // qkv: window-ordered tokens [B*N, 3C] (Q | K | V column blocks), out: [B*N, C] window-ordered.
+// A CTA serves ONE head (gridDim.x is a multiple of `heads`): its bias table sits in shared memory, its four warps
+// take windows round-robin.
 template <typename T>
-__global__ void __launch_bounds__(WA_WARPS * 32)
-win_attn_warp_kernel(const T* __restrict__ qkv, const float4* __restrict__ bias_frag, T* __restrict__ out, int num_items,
+__global__ void __launch_bounds__(WA_WARPS * 32, 4)
+win_attn_warp_kernel(const T* __restrict__ qkv, const float4* __restrict__ bias_frag, T* __restrict__ out, int num_windows,
                      int C, int heads, WinGeom g, int nW, float scale) {
   extern __shared__ __align__(16) uint8_t wa_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  T* Qs = reinterpret_cast<T*>(wa_smem + warp * WA_WARP_BYTES);
-  T* Ks = Qs + WA_Q_ROWS * WA_LD;
-  T* Vs = Ks + WA_K_ROWS * WA_LD;
-  int8_t* region_s = reinterpret_cast<int8_t*>(Vs + WA_V_ROWS * WA_LD);
+  float4* bias_s = reinterpret_cast<float4*>(wa_smem);
+  uint8_t* Qs = wa_smem + WA_BIAS_BYTES + warp * WA_WARP_BYTES;
+  uint8_t* Ks = Qs + WA_L * WA_ROW;
+  uint8_t* Vs = Ks + WA_L * WA_ROW;
+  int8_t* region_s = reinterpret_cast<int8_t*>(Vs + (WA_L + 15) * WA_ROW);
 
-  // Rows past the 49 tokens are never loaded: zero them once (V padding must be finite: P is exactly 0 there).
+  const int h = blockIdx.x % heads;
+  for (int i = threadIdx.x; i < WA_BIAS_BYTES / 16; i += WA_WARPS * 32) bias_s[i] = __ldg(bias_frag + h * (WA_BIAS_BYTES / 16) + i);
   for (int i = lane; i < (WA_WARP_BYTES >> 2); i += 32) reinterpret_cast<uint32_t*>(Qs)[i] = 0u;
-  __syncwarp();
+  __syncthreads();
 
   const int ld_qkv = 3 * C;
   const int nWy = g.H / g.ws;
-  const int gwarp = blockIdx.x * WA_WARPS + warp, nwarps = gridDim.x * WA_WARPS;
-  for (int item = gwarp; item < num_items; item += nwarps) {
-    const int h = item % heads;
-    const int wg = item / heads;      // global window index = b*nW + w
+  const int wstride = (gridDim.x / heads) * WA_WARPS;
+  for (int wg = (blockIdx.x / heads) * WA_WARPS + warp; wg < num_windows; wg += wstride) {   // global window = b*nW + w
     const int w = wg % nW;
     const long long row0 = static_cast<long long>(wg) * WA_L;
     const T* src = qkv + row0 * ld_qkv + h * 32;
@@ -105,8 +112,7 @@ win_attn_warp_kernel(const T* __restrict__ qkv, const float4* __restrict__ bias_
       if (idx < 3 * WA_L * 4) {
         const int which = idx / (WA_L * 4), rem = idx - which * (WA_L * 4);
         const int r = rem >> 2, ch = rem & 3;
-        T* dst = (which == 0 ? Qs : (which == 1 ? Ks : Vs)) + r * WA_LD + ch * 8;
-        cp_async16(dst, src + static_cast<long long>(r) * ld_qkv + which * C + ch * 8);
+        cp_async16(Qs + which * (WA_L * WA_ROW) + wa_off(r, ch), src + static_cast<long long>(r) * ld_qkv + which * C + ch * 8);
       }
     }
     const int wy = w / g.nWx, wx = w - wy * g.nWx;
@@ -125,14 +131,14 @@ win_attn_warp_kernel(const T* __restrict__ qkv, const float4* __restrict__ bias_
       uint32_t qa[2][4];
 #pragma unroll
       for (int ks = 0; ks < 2; ++ks)
-        ldsm_x4(qa[ks], Qs + (m0 + (lane & 7) + ((lane >> 3) & 1) * 8) * WA_LD + ks * 16 + (lane >> 4) * 8);
+        ldsm_x4(qa[ks], Qs + wa_off(m0 + (lane & 7) + ((lane >> 3) & 1) * 8, ks * 2 + (lane >> 4)));
       float s[7][4];
-      const float4* bf = bias_frag + ((h * 4 + mt) * 7) * 32 + lane;
+      const float4* bf = bias_s + (mt * 7) * 32 + lane;
 #pragma unroll
       for (int j = 0; j < 7; ++j) {
         s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
         uint32_t kb[4];
-        ldsm_x4(kb, Ks + (j * 8 + (lane & 7)) * WA_LD + (lane >> 3) * 8);
+        ldsm_x4(kb, Ks + wa_off(j * 8 + (lane & 7), lane >> 3));
         mma_16816<T>(s[j], qa[0], kb[0], kb[1]);
         mma_16816<T>(s[j], qa[1], kb[2], kb[3]);
       }
@@ -140,7 +146,7 @@ win_attn_warp_kernel(const T* __restrict__ qkv, const float4* __restrict__ bias_
       const int r0 = m0 + (lane >> 2), r1 = r0 + 8;
 #pragma unroll
       for (int j = 0; j < 7; ++j) {
-        const float4 b = __ldg(bf + j * 32);
+        const float4 b = bf[j * 32];
         s[j][0] = fmaf(s[j][0], scale, b.x);
         s[j][1] = fmaf(s[j][1], scale, b.y);
         s[j][2] = fmaf(s[j][2], scale, b.z);
@@ -196,7 +202,7 @@ win_attn_warp_kernel(const T* __restrict__ qkv, const float4* __restrict__ bias_
 #pragma unroll
         for (int np = 0; np < 2; ++np) {
           uint32_t vb[4];
-          ldsm_x4_t(vb, Vs + (kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * WA_LD + np * 16 + (lane >> 4) * 8);
+          ldsm_x4_t(vb, Vs + wa_off(kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, np * 2 + (lane >> 4)));
           mma_16816<T>(o[2 * np], pa, vb[0], vb[1]);
           mma_16816<T>(o[2 * np + 1], pa, vb[2], vb[3]);
         }
@@ -209,7 +215,7 @@ win_attn_warp_kernel(const T* __restrict__ qkv, const float4* __restrict__ bias_
         if (r1 < WA_L) *reinterpret_cast<uint32_t*>(out + (row0 + r1) * C + col) = Half16<T>::pack(o[n][2], o[n][3]);
       }
     }
-    __syncwarp();  // all lanes are done with this item's tiles before the next cp.async overwrites them
+    __syncwarp();  // all lanes are done with this window's tiles before the next cp.async overwrites them
   }
 }
 
@@ -221,19 +227,22 @@ int launch_expand_rel_bias_mma(const float* table, float* out, int heads, cudaSt
 }
 
 template <typename T>
-static int launch_wa(const void* qkv, const float* bias_frag, void* out, int items, int C, int heads, const WinGeom& g, int nW,
-                     cudaStream_t stream) {
+static int launch_wa(const void* qkv, const float* bias_frag, void* out, int num_windows, int C, int heads, const WinGeom& g,
+                     int nW, cudaStream_t stream) {
   static bool configured = false;
   auto kern = win_attn_warp_kernel<T>;
-  const int smem = WA_WARPS * WA_WARP_BYTES;
+  const int smem = WA_BIAS_BYTES + WA_WARPS * WA_WARP_BYTES;
   if (!configured) {
     CSVIT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  int blocks = (items + WA_WARPS - 1) / WA_WARPS;
-  if (blocks > 148 * 3) blocks = 148 * 3;
-  kern<<<blocks, WA_WARPS * 32, smem, stream>>>(static_cast<const T*>(qkv), reinterpret_cast<const float4*>(bias_frag),
-                                               static_cast<T*>(out), items, C, heads, g, nW, 0.17677669529663687f);
+  // one head per CTA: grid is a multiple of `heads`, about 4 CTAs per SM
+  int per_head = (num_windows + WA_WARPS - 1) / WA_WARPS;
+  const int cap = (148 * 4) / heads > 0 ? (148 * 4) / heads : 1;
+  if (per_head > cap) per_head = cap;
+  kern<<<per_head * heads, WA_WARPS * 32, smem, stream>>>(static_cast<const T*>(qkv), reinterpret_cast<const float4*>(bias_frag),
+                                                          static_cast<T*>(out), num_windows, C, heads, g, nW,
+                                                          0.17677669529663687f);
   CSVIT_CUDA(cudaGetLastError());
   return 0;
 }
@@ -249,8 +258,8 @@ int launch_window_attention_mma(const void* qkv, const float* bias_frag, void* o
   if (items <= 0) return 0;
   CSVIT_REQUIRE(items < (1ll << 31), "window_attention: too many work items");
   WinGeom g = make_geom(H, W, ws, shift);
-  if (dtype == DT_BF16) return launch_wa<__nv_bfloat16>(qkv, bias_frag, out, static_cast<int>(items), C, heads, g, nW, stream);
-  return launch_wa<__half>(qkv, bias_frag, out, static_cast<int>(items), C, heads, g, nW, stream);
+  if (dtype == DT_BF16) return launch_wa<__nv_bfloat16>(qkv, bias_frag, out, B * nW, C, heads, g, nW, stream);
+  return launch_wa<__half>(qkv, bias_frag, out, B * nW, C, heads, g, nW, stream);
 }
 
 }  // namespace csvit

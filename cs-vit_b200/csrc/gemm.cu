@@ -151,6 +151,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int ct = cluster_id; ct < num_ctiles; ct += num_clusters) {
       const int mg = ct / num_n, n_blk = ct - mg * num_n;
       const int m_blk = mg * CS + rank;
+      {
+        const int nct = ct + num_clusters;
+        if (ct == cluster_id) prefetch_resid_tile<BN>(ep, m_blk, n_blk, quad, half, lane);
+        if (nct < num_ctiles) prefetch_resid_tile<BN>(ep, (nct / num_n) * CS + rank, nct % num_n, quad, half, lane);
+      }
       epilogue_tile<BN>(ep, &tmC, stg, tmem_base + uint32_t(as * BN), &tfull[as], aph, m_blk, n_blk, quad, half, lane);
       tc_fence_before();
       __syncwarp();

@@ -141,6 +141,19 @@ constexpr int kGemmThreads = 320;
 constexpr int kEpiWarps = 8;
 constexpr uint32_t kStageBufBytes = 32 * 128;  // per epilogue warp: 32 rows x 128 B of swizzled staging
 
+// Pull the residual lines a warp will read for tile (m_blk, n_blk) into L2 one tile ahead of their use: the
+// residual epilogue was latency-bound on those reads (ncu: long-scoreboard stalls, DRAM 38 %).
+template <int BN>
+__device__ __forceinline__ void prefetch_resid_tile(const EpiParams& ep, int m_blk, int n_blk, int quad, int half, int lane) {
+  if (!ep.resid || !ep.coalesced) return;
+  const int row = m_blk * kBM + quad * 32 + lane;
+  const int col0 = n_blk * BN + half * (BN / 2);
+  if (row >= ep.M || col0 >= ep.N) return;
+  const char* p = reinterpret_cast<const char*>(ep.resid + epi_out_row(ep, row) * ep.ldr + col0);
+  const int bytes = (ep.N - col0 < BN / 2 ? ep.N - col0 : BN / 2) * 4;
+  for (int o = 0; o < bytes; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + o));
+}
+
 template <int BN>
 __device__ __forceinline__ void epilogue_tile(const EpiParams& ep, const CUtensorMap* tmC, uint8_t* stg, uint32_t tmem_tile,
                                               uint64_t* tfull_bar, uint32_t aph, int m_blk, int n_blk, int quad, int half,

@@ -121,6 +121,11 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     for (int pt = pair_id; pt < num_ptiles; pt += num_pairs) {
       const int mp = pt / num_n, n_blk = pt - mp * num_n;
       const int m_blk = mp * 2 + int(rank);
+      {
+        const int npt = pt + num_pairs;
+        if (pt == pair_id) prefetch_resid_tile<BN>(ep, m_blk, n_blk, quad, half, lane);
+        if (npt < num_ptiles) prefetch_resid_tile<BN>(ep, (npt / num_n) * 2 + int(rank), npt % num_n, quad, half, lane);
+      }
       epilogue_tile<BN>(ep, &tmC, stg, tmem_base + uint32_t(as * BN), &tfull[as], aph, m_blk, n_blk, quad, half, lane);
       tc_fence_before();
       __syncwarp();

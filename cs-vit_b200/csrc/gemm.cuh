@@ -37,24 +37,24 @@ __device__ __forceinline__ long long epi_out_row(const EpiParams& ep, int row) {
   return row;
 }
 
-// Branch-free exact-erf GELU for the tensor-core epilogues.  erf by Abramowitz-Stegun 7.1.26
-// (|error| <= 1.5e-7, i.e. fp32 round-off level - three orders below the 16-bit output rounding), one
-// MUFU.RCP + one MUFU.EX2 + ~12 FMA-pipe instructions instead of erff()'s two divergent branches.
+// Branch-free erf GELU for the tensor-core epilogues: erfc(|x|/sqrt2) = 2^q(|x|) with q a degree-6 polynomial
+// fitted to log2(erfc) on |x| <= 4*sqrt2 (beyond that erfc < 1.6e-8).  6 FFMA + 1 MUFU.EX2 + 5 other FP ops, no
+// division, no branch.  Max |error| vs 0.5x(1+erf(x/sqrt2)) evaluated in fp32: 4.2e-7 absolute, 1.9e-4 relative in
+// the far negative tail - two to three orders below the 16-bit rounding of the value that is stored.  (The
+// epilogues of fc1 at stages 0/1 are bound by exactly this arithmetic, profiles/r1_gemm_pipeline_analysis.md.)
 // The fp32 validation mode keeps erff() (gelu_erf).
 __device__ __forceinline__ float gelu_fast(float x) {
-  const float z = fabsf(x) * 0.70710678118654752440f;
-  float t;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
-  float p = fmaf(t, 1.061405429f, -1.453152027f);
-  p = fmaf(p, t, 1.421413741f);
-  p = fmaf(p, t, -0.284496736f);
-  p = fmaf(p, t, 0.254829592f);
-  p *= t;
+  const float ax = fminf(fabsf(x), 5.6568542f);
+  float q = fmaf(ax, 3.382089429e-05f, -7.692634491e-04f);
+  q = fmaf(q, ax, 8.055410705e-03f);
+  q = fmaf(q, ax, -5.332621707e-02f);
+  q = fmaf(q, ax, -4.588742488e-01f);
+  q = fmaf(q, ax, -1.151155207e+00f);
+  q = fmaf(q, ax, 1.205011077e-06f);
   float e;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z * z * -1.4426950408889634f));
-  const float erf_abs = fmaf(-p, e, 1.0f);
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(q));
   const float hx = 0.5f * x;
-  return fmaf(fabsf(hx), erf_abs, hx);   // 0.5x(1 + sign(x) erf|z|) = hx + |hx| erf_abs
+  return fmaf(fabsf(hx), 1.0f - e, hx);   // 0.5x(1 + sign(x) erf(|x|/sqrt2)) = hx + |hx| (1 - erfc)
 }
 
 __device__ __forceinline__ float epi_act(int act, float v) {

@@ -111,6 +111,7 @@ class SwinBackboneB200(nn.Module):
         # csvit_layernorm + csvit_linear on B200 (profiles/r1_lnlinear_vs_unfused.txt: the LayerNorm phase is exposed, not
         # overlapped with the MMAs), so it is opt-in until the A tile can be double-buffered.
         self.fuse_ln = False
+        self.fuse_mlp = True   # csvit_mlp_fused for C in {128, 256}: hidden activations never leave the SM
         c0, eps, ws = config.embed_dim, config.layer_norm_eps, config.window_size
         self.embeddings = _holder(
             patch_embeddings=_holder(projection=nn.Conv2d(3, c0, kernel_size=4, stride=4)),
@@ -206,6 +207,12 @@ class SwinBackboneB200(nn.Module):
         if fused_ln:
             hid = ops.ln_linear(x, self._f32(key + "ln2w", ln2.weight), self._f32(key + "ln2b", ln2.bias), eps,
                                 self._weight(key + "w1", fc1.weight), self._f32(key + "b1", fc1.bias), act=ops.ACT_GELU)
+        elif self.fuse_mlp and not self._fp32 and x.shape[1] in ops.MLP_FUSED_WIDTHS:
+            # narrow stages: fc1 + GELU + fc2 + residual in one kernel, the [M, 4C] hidden tensor stays on chip
+            xn = ops.layernorm(x, self._f32(key + "ln2w", ln2.weight), self._f32(key + "ln2b", ln2.bias), eps, out_dtype=act)
+            ops.mlp_fused(xn, self._weight(key + "w1", fc1.weight), self._f32(key + "b1", fc1.bias),
+                          self._weight(key + "w2", fc2.weight), self._f32(key + "b2", fc2.bias), x)
+            return
         else:
             xn = ops.layernorm(x, self._f32(key + "ln2w", ln2.weight), self._f32(key + "ln2b", ln2.bias), eps, out_dtype=act)
             hid = ops.linear(xn, self._weight(key + "w1", fc1.weight), self._f32(key + "b1", fc1.bias), act=ops.ACT_GELU,

@@ -228,6 +228,20 @@ def ln_linear(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: flo
 
 
 LN_LINEAR_WIDTHS = (128, 256, 512)
+MLP_FUSED_WIDTHS = (128, 256)
+
+
+def mlp_fused(xn: torch.Tensor, w1: torch.Tensor, b1: torch.Tensor, w2: torch.Tensor, b2: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
+    """In place ``x += GELU(xn @ w1.T + b1) @ w2.T + b2`` without materialising the hidden tensor (``csvit_mlp_fused``)."""
+    _dev(xn, w1, b1, w2, b2, x)
+    M, C, ldxn = _rows2d(xn)
+    if w1.shape != (4 * C, C) or w2.shape != (C, 4 * C) or x.shape != (M, C) or x.dtype != torch.float32:
+        raise ValueError("mlp_fused: shape mismatch")
+    if not (xn.dtype == w1.dtype == w2.dtype) or xn.dtype not in (torch.bfloat16, torch.float16):
+        raise ValueError("mlp_fused: xn / w1 / w2 must share a 16-bit dtype")
+    _call("csvit_mlp_fused", xn.data_ptr(), ldxn, w1.data_ptr(), w1.stride(0), b1.data_ptr(), w2.data_ptr(), w2.stride(0),
+          b2.data_ptr(), x.data_ptr(), x.stride(0), _code(xn.dtype), M, C, _stream(), flops=16.0 * M * C * C)
+    return x
 
 
 # ---------------------------------------------------------------------------------------------- attention

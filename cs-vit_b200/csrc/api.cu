@@ -157,6 +157,12 @@ int csvit_ln_linear(const float* x, const float* gamma, const float* beta, float
   return launch_ln_gemm(x, gamma, beta, eps, mode, g, Wt, ldw, dtype, M, N, C, bias, act, out, ldo, S(stream));
 }
 
+int csvit_mlp_fused(const void* xn, long long ldxn, const void* W1, long long ldw1, const float* b1, const void* W2,
+                    long long ldw2, const float* b2, float* x, long long ldx, int dtype, int M, int C, void* stream) {
+  CSVIT_REQUIRE(ldxn >= C && ldw1 >= C && ldw2 >= 4 * C && ldx >= C, "mlp_fused: pitches smaller than the logical widths");
+  return launch_mlp_fused(xn, ldxn, W1, ldw1, b1, W2, ldw2, b2, x, ldx, dtype, M, C, S(stream));
+}
+
 int csvit_set_gemm_tuning(int cluster, int tma_store, int max_ctas, int pair) {
   g_tune.pair = pair;
   CSVIT_REQUIRE(cluster == 0 || cluster == 1 || cluster == 2 || cluster == 4, "gemm tuning: cluster %d not in {0,1,2,4}", cluster);

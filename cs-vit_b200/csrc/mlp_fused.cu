@@ -1,0 +1,252 @@
+// Fused MLP half-block for the narrow Swin stages (C = 128, 256):
+//     x[M, C] += GELU( xn[M, C] * W1[4C, C]^T + b1 ) * W2[C, 4C]^T + b2          (x fp32 in place, xn / W 16-bit)
+// Replaces intermediate.dense + GELU + output.dense + residual add (HF:swin/modeling_swin.py:510-531, 650) and,
+// above all, the [M, 4C] hidden tensor: at stage 0 / batch 256 that is 822 MB written and read back per block,
+// which made fc1 and fc2 the two most expensive kernels of the stage.  Here the hidden activations exist only as
+// 128 x 128 chunks: fp32 in TMEM after GEMM1, GELU'd to 16 bit in registers, staged in shared memory in the
+// tcgen05 K-major layout, and consumed as the A operand of GEMM2.
+//
+// One CTA owns a 128-token tile and walks the 4C/128 hidden chunks:
+//   warp 0     TMA: the xn tile once per tile, then W1 / W2 as 128x64 boxes in the order the MMAs need them
+//   warp 1     MMA issuer: G1(j+1) is issued before G2(j), so the tensor core works on the next chunk while the
+//              epilogue warps apply GELU to the current one
+//   warps 2-9  chunk epilogue (TMEM -> +b1 -> GELU -> 16 bit -> smem) and, after the last chunk, the fp32
+//              residual epilogue of the tile (same coalesced path as the GEMM engine)
+// TMEM: two 128-column GEMM1 accumulators + one C-column GEMM2 accumulator (<= 512 columns).
+#include <type_traits>
+
+#include "errors.h"
+#include "gemm.cuh"
+#include "rowops.cuh"
+
+namespace csvit {
+
+constexpr uint32_t kUnit = 128 * 128;   // bytes of one 128-row x 64-column 16-bit box (A slab / weight unit)
+
+template <int C>
+struct MlpCfg {
+  static constexpr int KB1 = C / 64;            // k-blocks of GEMM1
+  static constexpr int N2 = C / 128;            // 128-column groups of the GEMM2 output
+  static constexpr int NCH = 4 * C / 128;       // hidden chunks
+  static constexpr int WSTAGES = C == 128 ? 6 : 4;
+  static constexpr uint32_t A1_BYTES = KB1 * kUnit;
+  static constexpr uint32_t A2_BYTES = 2 * 2 * kUnit;
+  static constexpr uint32_t W_BYTES = WSTAGES * kUnit;
+  static constexpr uint32_t STG_BYTES = kEpiWarps * kStageBufBytes;
+  static constexpr size_t SMEM = 1024 + size_t(A1_BYTES) + A2_BYTES + W_BYTES + STG_BYTES + 512;
+};
+
+struct MlpParams {
+  const float* b1;
+  int M;
+};
+
+template <int FMT, int C>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
+                 const __grid_constant__ CUtensorMap tmW2, MlpParams mp, EpiParams ep) {
+  using Cfg = MlpCfg<C>;
+  constexpr int KB1 = Cfg::KB1, N2 = Cfg::N2, NCH = Cfg::NCH, WS = Cfg::WSTAGES;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t a1_off = 0, a2_off = Cfg::A1_BYTES, w_off = a2_off + Cfg::A2_BYTES, stg_off = w_off + Cfg::W_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + stg_off + Cfg::STG_BYTES);
+  uint64_t* w_full = bars;                    // [WS]
+  uint64_t* w_empty = bars + WS;              // [WS]
+  uint64_t* acc1_full = bars + 2 * WS;        // [2]
+  uint64_t* acc1_empty = acc1_full + 2;       // [2]
+  uint64_t* a2_full = acc1_full + 4;          // [2]
+  uint64_t* a2_empty = acc1_full + 6;         // [2]
+  uint64_t* a1_full = acc1_full + 8;
+  uint64_t* a1_empty = acc1_full + 9;
+  uint64_t* acc2_full = acc1_full + 10;
+  uint64_t* acc2_empty = acc1_full + 11;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc1_full + 12);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_tiles = (mp.M + kBM - 1) / kBM;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmX); prefetch_tmap(&tmW1); prefetch_tmap(&tmW2);
+    for (int s = 0; s < WS; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&acc1_full[b], 1); mbar_init(&acc1_empty[b], kEpiWarps);
+      mbar_init(&a2_full[b], kEpiWarps); mbar_init(&a2_empty[b], 1);
+    }
+    mbar_init(a1_full, 1); mbar_init(a1_empty, 1);
+    mbar_init(acc2_full, 1); mbar_init(acc2_empty, kEpiWarps);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tm_acc2 = tmem_base + 256;
+
+  if (warp == 0) {
+    // ---------------- TMA producer ----------------
+    if (lane == 0) {
+      int s = 0; uint32_t ph = 0;
+      auto load_w = [&](const CUtensorMap* tm, int col, int row) {
+        mbar_wait(&w_empty[s], ph ^ 1u);
+        mbar_arrive_expect_tx(&w_full[s], kUnit);
+        tma_load_2d(smem + w_off + size_t(s) * kUnit, tm, &w_full[s], col, row);
+        if (++s == WS) { s = 0; ph ^= 1u; }
+      };
+      uint32_t it = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+        mbar_wait(a1_empty, (it & 1u) ^ 1u);
+        mbar_arrive_expect_tx(a1_full, Cfg::A1_BYTES);
+        for (int kb = 0; kb < KB1; ++kb) tma_load_2d(smem + a1_off + size_t(kb) * kUnit, &tmX, a1_full, kb * 64, t * kBM);
+        for (int kb = 0; kb < KB1; ++kb) load_w(&tmW1, kb * 64, 0);                       // G1(0)
+        for (int j = 0; j < NCH; ++j) {
+          if (j + 1 < NCH)
+            for (int kb = 0; kb < KB1; ++kb) load_w(&tmW1, kb * 64, (j + 1) * 128);       // G1(j+1)
+          for (int kb2 = 0; kb2 < 2; ++kb2)
+            for (int n2 = 0; n2 < N2; ++n2) load_w(&tmW2, j * 128 + kb2 * 64, n2 * 128);   // G2(j)
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------- MMA issuer ----------------
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(uint32_t(FMT), kBM, 128);
+      int s = 0; uint32_t ph = 0;
+      auto mma_unit = [&](uint32_t a_addr, uint32_t d_tmem, bool first) {
+        mbar_wait(&w_full[s], ph);
+        tc_fence_after();
+        const uint64_t adesc = make_sw128_kmajor_desc(a_addr);
+        const uint64_t bdesc = make_sw128_kmajor_desc(base + w_off + uint32_t(s) * kUnit);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_ss<false>(d_tmem, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), idesc, (first && k == 0) ? 0u : 1u);
+        umma_commit(&w_empty[s]);
+        if (++s == WS) { s = 0; ph ^= 1u; }
+      };
+      uint32_t it = 0;
+      uint32_t use[2] = {0, 0};   // how many chunks have used acc1 / A2 buffer b so far (all tiles)
+      auto gemm1 = [&](int j) {
+        const int b = j & 1;
+        mbar_wait(&acc1_empty[b], (use[b] & 1u) ^ 1u);
+        tc_fence_after();
+        for (int kb = 0; kb < KB1; ++kb) mma_unit(base + a1_off + uint32_t(kb) * kUnit, tmem_base + uint32_t(b * 128), kb == 0);
+        umma_commit(&acc1_full[b]);
+      };
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+        mbar_wait(a1_full, it & 1u);
+        tc_fence_after();
+        gemm1(0);
+        for (int j = 0; j < NCH; ++j) {
+          const int b = j & 1;
+          if (j + 1 < NCH) {
+            gemm1(j + 1);
+            if (j + 2 == NCH) umma_commit(a1_empty);   // last GEMM1 of the tile issued: xn tile free once it completes
+          }
+          mbar_wait(&a2_full[b], use[b] & 1u);
+          tc_fence_after();
+          if (j == 0) { mbar_wait(acc2_empty, (it & 1u) ^ 1u); tc_fence_after(); }
+          for (int kb2 = 0; kb2 < 2; ++kb2)
+            for (int n2 = 0; n2 < N2; ++n2)
+              mma_unit(base + a2_off + uint32_t(b * 2 + kb2) * kUnit, tm_acc2 + uint32_t(n2 * 128), j == 0 && kb2 == 0);
+          umma_commit(&a2_empty[b]);
+          if (j == NCH - 1) umma_commit(acc2_full);
+          ++use[b];
+        }
+      }
+    }
+  } else {
+    // ---------------- epilogues ----------------
+    const int e = warp - 2;
+    const int quad = warp & 3;
+    const int half = e >> 2;
+    const int r = quad * 32 + lane;           // row of the tile owned by this thread
+    const bool bf = FMT == 1;
+    uint8_t* stg = smem + stg_off + e * kStageBufBytes;
+    EpiParams ep1{};                          // chunk epilogue: + b1, GELU
+    ep1.bias = mp.b1; ep1.act = ACT_GELU;
+    uint32_t it = 0;
+    uint32_t use[2] = {0, 0};
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+      for (int j = 0; j < NCH; ++j) {
+        const int b = j & 1;
+        mbar_wait(&acc1_full[b], use[b] & 1u);
+        tc_fence_after();
+        uint32_t pk[32];                      // this thread's 64 hidden columns, packed to 16 bit
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          uint32_t rr[32];
+          tmem_ld_32x32(tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(b * 128 + half * 64 + 32 * hh), rr);
+          tmem_ld_wait();
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(rr[i]);
+          epi_bias_act32(ep1, j * 128 + half * 64 + 32 * hh, v);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) pk[16 * hh + i] = pack16(bf, v[2 * i], v[2 * i + 1]);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc1_empty[b]);            // accumulator drained: GEMM1(j+2) may overwrite it
+        mbar_wait(&a2_empty[b], (use[b] & 1u) ^ 1u);           // GEMM2(j-2) has finished reading this A2 buffer
+        uint8_t* dst = smem + a2_off + uint32_t(b * 2 + half) * kUnit + r * 128;
+#pragma unroll
+        for (int ci = 0; ci < 8; ++ci)
+          *reinterpret_cast<uint4*>(dst + ((ci ^ (r & 7)) << 4)) = make_uint4(pk[4 * ci], pk[4 * ci + 1], pk[4 * ci + 2], pk[4 * ci + 3]);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&a2_full[b]);
+        ++use[b];
+      }
+      // tile epilogue: acc2 (+ b2) + residual -> x, coalesced fp32 path of the GEMM engine (waits on acc2_full itself)
+      epilogue_tile<C>(ep, &tmX, stg, tm_acc2, acc2_full, it & 1u, t, 0, quad, half, lane);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc2_empty);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+template <int FMT, int C>
+static int launch_mlp(const CUtensorMap& tmX, const CUtensorMap& tmW1, const CUtensorMap& tmW2, const MlpParams& mp,
+                      const EpiParams& ep, cudaStream_t stream) {
+  using Cfg = MlpCfg<C>;
+  static bool configured = false;
+  auto kern = mlp_fused_kernel<FMT, C>;
+  if (!configured) {
+    CSVIT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(Cfg::SMEM)));
+    configured = true;
+  }
+  const int tiles = (mp.M + kBM - 1) / kBM;
+  const int ctas = tiles < num_sms() ? tiles : num_sms();
+  kern<<<ctas, kGemmThreads, Cfg::SMEM, stream>>>(tmX, tmW1, tmW2, mp, ep);
+  CSVIT_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_mlp_fused(const void* xn, long long ldxn, const void* W1, long long ldw1, const float* b1, const void* W2,
+                     long long ldw2, const float* b2, float* x, long long ldx, int dtype, int M, int C, cudaStream_t stream) {
+  CSVIT_REQUIRE(dtype == DT_BF16 || dtype == DT_F16, "mlp_fused: 16-bit operand formats only");
+  CSVIT_REQUIRE(C == 128 || C == 256, "mlp_fused: C=%d not in {128, 256}", C);
+  CSVIT_REQUIRE(ldx % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0, "mlp_fused: residual stream must be 16-byte aligned");
+  if (M <= 0) return 0;
+  EpiParams ep{};
+  ep.bias = b2; ep.resid = x; ep.out = x; ep.ldo = ldx; ep.ldr = ldx; ep.out_dtype = DT_F32; ep.act = ACT_NONE;
+  ep.M = M; ep.N = C; ep.vec_ok = 1; ep.tma_store = 0; ep.coalesced = 1;
+  ep.map_mode = ROWMAP_IDENTITY; ep.geom = make_geom(1, 1, 1, 0);
+  MlpParams mp{b1, M};
+  CUtensorMap tmX, tmW1, tmW2;
+  if (int e = make_tmap(&tmX, xn, ldxn, M, C, dtype, kBM, true)) return e;
+  if (int e = make_tmap(&tmW1, W1, ldw1, 4ll * C, C, dtype, 128, true)) return e;
+  if (int e = make_tmap(&tmW2, W2, ldw2, C, 4ll * C, dtype, 128, true)) return e;
+  const bool bf = dtype == DT_BF16;
+  if (C == 128) return bf ? launch_mlp<1, 128>(tmX, tmW1, tmW2, mp, ep, stream) : launch_mlp<0, 128>(tmX, tmW1, tmW2, mp, ep, stream);
+  return bf ? launch_mlp<1, 256>(tmX, tmW1, tmW2, mp, ep, stream) : launch_mlp<0, 256>(tmX, tmW1, tmW2, mp, ep, stream);
+}
+
+}  // namespace csvit

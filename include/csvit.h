@@ -112,6 +112,12 @@ CSVIT_API int csvit_ln_linear(const float* x, const float* gamma, const float* b
                               int shift, const void* Wt, long long ldw, int dtype, int M, int N, int C, const float* bias,
                               int act, void* out, long long ldo, void* stream);
 
+/* Fused MLP half-block for C in {128, 256}:  x[M,C] += GELU(xn[M,C] @ W1[4C,C]^T + b1) @ W2[C,4C]^T + b2, x fp32 in place,
+ * xn / W1 / W2 16-bit (dtype).  The [M,4C] hidden tensor never reaches HBM (128x128 chunks: TMEM -> GELU -> smem ->
+ * second tcgen05 GEMM).  Replaces intermediate.dense + GELU + output.dense + residual add   (HF:510-531, 650). */
+CSVIT_API int csvit_mlp_fused(const void* xn, long long ldxn, const void* W1, long long ldw1, const float* b1, const void* W2,
+                              long long ldw2, const float* b2, float* x, long long ldx, int dtype, int M, int C, void* stream);
+
 /* Process-wide tuning knobs of the GEMM engine (benchmarking / ablation; defaults are automatic):
  *   cluster   0 = auto, 1 / 2 / 4 = CTAs per cluster sharing the weight tile by TMA multicast
  *   tma_store -1 = auto, 0 = direct register stores, 1 = smem-staged TMA stores where legal

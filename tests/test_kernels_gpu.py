@@ -92,6 +92,27 @@ def test_ln_linear_matches_unfused(ops, C, N, mode, gelu, dt):
         assert rel(fused, unfused) < tol / 2
 
 
+@pytest.mark.parametrize("C,M", [(128, 128 * 148 * 2 + 77), (256, 128 * 150 + 5), (128, 64)])
+@pytest.mark.parametrize("dt", [torch.bfloat16, torch.float16])
+def test_mlp_fused_matches_unfused(ops, C, M, dt):
+    """Fused fc1+GELU+fc2+residual against the two-GEMM path and against fp32 torch math."""
+    g = torch.Generator(device="cuda").manual_seed(C + M)
+    xn = torch.randn(M, C, device="cuda", generator=g).to(dt)
+    w1 = (torch.randn(4 * C, C, device="cuda", generator=g) * 0.06).to(dt)
+    b1 = torch.randn(4 * C, device="cuda", generator=g) * 0.1
+    w2 = (torch.randn(C, 4 * C, device="cuda", generator=g) * 0.04).to(dt)
+    b2 = torch.randn(C, device="cuda", generator=g) * 0.1
+    x = torch.randn(M, C, device="cuda", generator=g)
+    fused = ops.mlp_fused(xn, w1, b1, w2, b2, x.clone())
+    hid = ops.linear(xn, w1, b1, act=ops.ACT_GELU, out_dtype=dt)
+    unfused = ops.linear(hid, w2, b2, resid=x.clone(), out_dtype=torch.float32)
+    href = torch.nn.functional.gelu(xn.float() @ w1.float().T + b1)
+    ref = x + href @ w2.float().T + b2
+    tol = 6e-3 if dt == torch.bfloat16 else 1e-3
+    assert rel(fused - x, ref - x) < tol and rel(unfused - x, ref - x) < tol
+    assert rel(fused, unfused) < 1e-4
+
+
 def test_linear_epilogues(ops):
     g = torch.Generator(device="cuda").manual_seed(5)
     B, H, W, C = 3, 14, 14, 256

@@ -33,13 +33,13 @@ namespace csvit {
 
 template <int BN>
 struct TcCfg {
-  static constexpr int STAGES = BN == 256 ? 4 : 6;
+  static constexpr int STAGES = BN == 256 ? 3 : 5;   // one stage traded for a second staging buffer per epilogue warp
   static constexpr uint32_t A_BYTES = kBM * 128;
   static constexpr uint32_t B_BYTES = BN * 128;
   static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr uint32_t TMEM_COLS = 2 * BN <= 256 ? 256 : 512;  // two accumulator buffers, power of 2
   static constexpr uint32_t TILES_BYTES = STAGES * STAGE_BYTES;
-  static constexpr uint32_t STG_BYTES = kEpiWarps * kStageBufBytes;
+  static constexpr uint32_t STG_BYTES = 2 * kEpiWarps * kStageBufBytes;
   static constexpr size_t SMEM = 1024 + size_t(TILES_BYTES) + STG_BYTES + 256;
 };
 
@@ -146,7 +146,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int e = warp - 2;
     const int quad = warp & 3;            // TMEM lane quadrant this warp may read
     const int half = e >> 2;              // which half of the tile's columns
-    uint8_t* stg = staging + e * kStageBufBytes;
+    uint8_t* stg = staging + e * 2 * kStageBufBytes;
+    uint32_t stg_sel = 0;
     int as = 0; uint32_t aph = 0;
     for (int ct = cluster_id; ct < num_ctiles; ct += num_clusters) {
       const int mg = ct / num_n, n_blk = ct - mg * num_n;
@@ -156,7 +157,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (ct == cluster_id) prefetch_resid_tile<BN>(ep, m_blk, n_blk, quad, half, lane);
         if (nct < num_ctiles) prefetch_resid_tile<BN>(ep, (nct / num_n) * CS + rank, nct % num_n, quad, half, lane);
       }
-      epilogue_tile<BN>(ep, &tmC, stg, tmem_base + uint32_t(as * BN), &tfull[as], aph, m_blk, n_blk, quad, half, lane);
+      epilogue_tile<BN>(ep, &tmC, stg, tmem_base + uint32_t(as * BN), &tfull[as], aph, m_blk, n_blk, quad, half, lane, 2, &stg_sel);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[as]);

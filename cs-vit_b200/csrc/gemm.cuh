@@ -57,6 +57,48 @@ __device__ __forceinline__ float gelu_fast(float x) {
   return fmaf(fabsf(hx), 1.0f - e, hx);   // 0.5x(1 + sign(x) erf(|x|/sqrt2)) = hx + |hx| (1 - erfc)
 }
 
+// Two GELUs per instruction for 16-bit outputs: the same degree-6 erfc fit evaluated in packed fp16 (HFMA2, one
+// MUFU.EX2 for the pair).  The fc1 / fused-MLP epilogues are bound by this arithmetic (stages 0-1: every element of
+// the 4C-wide hidden tensor passes through it), and the result is rounded to 16 bit anyway: the packed evaluation
+// adds < 2e-4 absolute error, below the bf16 / at the level of the fp16 output rounding.
+__device__ __forceinline__ __half2 gelu_h2(__half2 x) {
+  const __half2 ax = __hmin2(__habs2(x), __float2half2_rn(5.65625f));
+  __half2 q = __hfma2(ax, __float2half2_rn(3.382089429e-05f), __float2half2_rn(-7.692634491e-04f));
+  q = __hfma2(q, ax, __float2half2_rn(8.055410705e-03f));
+  q = __hfma2(q, ax, __float2half2_rn(-5.332621707e-02f));
+  q = __hfma2(q, ax, __float2half2_rn(-4.588742488e-01f));
+  q = __hfma2(q, ax, __float2half2_rn(-1.151155207e+00f));
+  q = __hmul2(q, ax);
+  __half2 e;
+  asm("ex2.approx.f16x2 %0, %1;" : "=r"(*reinterpret_cast<uint32_t*>(&e)) : "r"(*reinterpret_cast<const uint32_t*>(&q)));
+  const __half2 hx = __hmul2(x, __float2half2_rn(0.5f));
+  return __hfma2(__habs2(hx), __hsub2(__float2half2_rn(1.0f), e), hx);
+}
+// (a, b) fp32 pre-activations -> GELU -> one packed 16-bit pair in the output format.
+__device__ __forceinline__ uint32_t gelu_pack16(bool bf, float a, float b) {
+  const __half2 g = gelu_h2(__floats2half2_rn(a, b));
+  if (!bf) return *reinterpret_cast<const uint32_t*>(&g);
+  const float2 f = __half22float2(g);
+  return pack_bf16x2(f.x, f.y);
+}
+
+// acc (+ bias) -> GELU -> 16 packed pairs, for 32 consecutive full columns (16-byte aligned bias).
+__device__ __forceinline__ void epi_bias_gelu_pack32(const float* bias, bool bf, int col0, const uint32_t (&r)[32], uint32_t* pk) {
+  float v[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+  if (bias) {
+    const float4* b4 = reinterpret_cast<const float4*>(bias + col0);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float4 b = __ldg(b4 + j);
+      v[4 * j + 0] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 16; ++j) pk[j] = gelu_pack16(bf, v[2 * j], v[2 * j + 1]);
+}
+
 __device__ __forceinline__ float epi_act(int act, float v) {
   if (act == ACT_GELU) return gelu_erf(v);
   if (act == ACT_RELU) return fmaxf(v, 0.0f);
@@ -157,7 +199,7 @@ __device__ __forceinline__ void prefetch_resid_tile(const EpiParams& ep, int m_b
 template <int BN>
 __device__ __forceinline__ void epilogue_tile(const EpiParams& ep, const CUtensorMap* tmC, uint8_t* stg, uint32_t tmem_tile,
                                               uint64_t* tfull_bar, uint32_t aph, int m_blk, int n_blk, int quad, int half,
-                                              int lane) {
+                                              int lane, int nbuf = 1, uint32_t* stg_sel = nullptr) {
   const bool bf = ep.out_dtype == DT_BF16;
   const int row_in_tile = quad * 32 + lane;
         const int row = m_blk * kBM + row_in_tile;
@@ -200,23 +242,36 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& ep, const CUtenso
               uint32_t r[32];
               tmem_ld_32x32(t_addr + uint32_t(col_local + 32 * hh), r);
               tmem_ld_wait();
-              float v[32];
-  #pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-              epi_bias_act32(ep, gcol + 32 * hh, v);
-  #pragma unroll
-              for (int j = 0; j < 16; ++j) pk[16 * hh + j] = pack16(bf, v[2 * j], v[2 * j + 1]);
+              if (ep.act == ACT_GELU) {
+                epi_bias_gelu_pack32(ep.bias, bf, gcol + 32 * hh, r, pk + 16 * hh);
+              } else {
+                float v[32];
+    #pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+                epi_bias_act32(ep, gcol + 32 * hh, v);
+    #pragma unroll
+                for (int j = 0; j < 16; ++j) pk[16 * hh + j] = pack16(bf, v[2 * j], v[2 * j + 1]);
+              }
             }
-            if (lane == 0) tma_store_wait_read0();  // the previous TMA store has finished reading the staging buffer
+            // With two staging buffers per warp only the store issued TWO chunks ago must have drained its buffer,
+            // so the TMA engine's read of the previous chunk overlaps this chunk's math and smem writes.
+            uint8_t* sbuf = stg;
+            if (nbuf == 2) {
+              sbuf = stg + (*stg_sel & 1u) * kStageBufBytes;
+              *stg_sel ^= 1u;
+              if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            } else if (lane == 0) {
+              tma_store_wait_read0();
+            }
             __syncwarp();
   #pragma unroll
             for (int q = 0; q < 8; ++q)  // row `lane`, 16-byte chunk q -> swizzled position q ^ (lane & 7)
-              *reinterpret_cast<uint4*>(stg + lane * 128 + ((q ^ (lane & 7)) << 4)) =
+              *reinterpret_cast<uint4*>(sbuf + lane * 128 + ((q ^ (lane & 7)) << 4)) =
                   make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0 && m_blk * kBM + quad * 32 < ep.M) {
-              tma_store_2d(tmC, stg, gcol, m_blk * kBM + quad * 32);
+              tma_store_2d(tmC, sbuf, gcol, m_blk * kBM + quad * 32);
               tma_store_commit();
             }
           }

@@ -19,12 +19,12 @@
 namespace csvit {
 
 constexpr int kPairBN = 256;
-constexpr int kPairStages = 6;
+constexpr int kPairStages = 5;   // 6th stage traded for a second staging buffer per epilogue warp
 constexpr uint32_t kPairABytes = kBM * 128;               // 128 rows x 128 B
 constexpr uint32_t kPairBBytes = (kPairBN / 2) * 128;     // this CTA's half of the weight tile
 constexpr uint32_t kPairStageBytes = kPairABytes + kPairBBytes;
 constexpr uint32_t kPairTiles = kPairStages * kPairStageBytes;
-constexpr uint32_t kPairStg = kEpiWarps * kStageBufBytes;
+constexpr uint32_t kPairStg = 2 * kEpiWarps * kStageBufBytes;
 constexpr size_t kPairSmem = 1024 + size_t(kPairTiles) + kPairStg + 256;
 
 template <int FMT>  // 0 = fp16, 1 = bf16
@@ -116,7 +116,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int e = warp - 2;
     const int quad = warp & 3;
     const int half = e >> 2;
-    uint8_t* stg = staging + e * kStageBufBytes;
+    uint8_t* stg = staging + e * 2 * kStageBufBytes;
+    uint32_t stg_sel = 0;
     int as = 0; uint32_t aph = 0;
     for (int pt = pair_id; pt < num_ptiles; pt += num_pairs) {
       const int mp = pt / num_n, n_blk = pt - mp * num_n;
@@ -126,7 +127,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (pt == pair_id) prefetch_resid_tile<BN>(ep, m_blk, n_blk, quad, half, lane);
         if (npt < num_ptiles) prefetch_resid_tile<BN>(ep, (npt / num_n) * 2 + int(rank), npt % num_n, quad, half, lane);
       }
-      epilogue_tile<BN>(ep, &tmC, stg, tmem_base + uint32_t(as * BN), &tfull[as], aph, m_blk, n_blk, quad, half, lane);
+      epilogue_tile<BN>(ep, &tmC, stg, tmem_base + uint32_t(as * BN), &tfull[as], aph, m_blk, n_blk, quad, half, lane, 2, &stg_sel);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty[as]), 0));

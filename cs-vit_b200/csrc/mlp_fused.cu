@@ -164,8 +164,6 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     const int r = quad * 32 + lane;           // row of the tile owned by this thread
     const bool bf = FMT == 1;
     uint8_t* stg = smem + stg_off + e * kStageBufBytes;
-    EpiParams ep1{};                          // chunk epilogue: + b1, GELU
-    ep1.bias = mp.b1; ep1.act = ACT_GELU;
     uint32_t it = 0;
     uint32_t use[2] = {0, 0};
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
@@ -179,12 +177,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           uint32_t rr[32];
           tmem_ld_32x32(tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(b * 128 + half * 64 + 32 * hh), rr);
           tmem_ld_wait();
-          float v[32];
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(rr[i]);
-          epi_bias_act32(ep1, j * 128 + half * 64 + 32 * hh, v);
-#pragma unroll
-          for (int i = 0; i < 16; ++i) pk[16 * hh + i] = pack16(bf, v[2 * i], v[2 * i + 1]);
+          epi_bias_gelu_pack32(mp.b1, bf, j * 128 + half * 64 + 32 * hh, rr, pk + 16 * hh);
         }
         tc_fence_before();
         __syncwarp();

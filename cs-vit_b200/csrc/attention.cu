@@ -7,7 +7,7 @@
 // The mask is never materialised: region ids come from the closed form in common.cuh, and only windows in
 // the last window row / column of a shifted block evaluate it at all.
 //
-// Work decomposition: ONE WARP per (window, head).  The warp pulls its 49x32 Q, K and V slices with cp.async
+// Work decomposition: ONE WARP per (window, head), one head per CTA.  The warp pulls its 49x32 Q, K and V slices with cp.async
 // into a private shared-memory region, then walks the four 16-row query tiles entirely in registers
 // (mma.sync m16n8k16, P re-used as the A operand of P.V).  No block-level barrier exists, so a CTA's four
 // warps and the three CTAs per SM are always at different points of load / compute and the HBM stream

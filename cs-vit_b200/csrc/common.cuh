@@ -46,6 +46,15 @@ __host__ __device__ inline int win_row_to_token(const WinGeom& g, int r) {
   return y * g.W + x;
 }
 
+// Inverse of win_row_to_token: flat token id -> row of the window-ordered stream.
+__host__ __device__ inline int win_token_to_row(const WinGeom& g, int t) {
+  int y = t / g.W, x = t - y * g.W;
+  int ys = y - g.shift; if (ys < 0) ys += g.H;
+  int xs = x - g.shift; if (xs < 0) xs += g.W;
+  int wy = ys / g.ws, wx = xs / g.ws;
+  return (wy * g.nWx + wx) * g.L + (ys - wy * g.ws) * g.ws + (xs - wx * g.ws);
+}
+
 // Shift-mask region id of slot i in window w, on SHIFTED coordinates (HF get_attn_mask slices).
 __host__ __device__ inline int win_region(const WinGeom& g, int w, int i) {
   int wy = w / g.nWx, wx = w - wy * g.nWx;

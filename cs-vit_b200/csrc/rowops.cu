@@ -50,11 +50,12 @@ ln_rows_kernel(const float* __restrict__ x, const float* __restrict__ gamma, con
     sum[r] = 0.f;
     if (row < rows) {
       long long src[4];
-      if (mode == LN_IDENTITY) {
-        src[0] = row;
+      if (mode == LN_IDENTITY || (mode == LN_WINDOW && C >= 512)) {
+        src[0] = row;   // wide rows in window mode: walk the SOURCE tokens in memory order (sequential fp32 reads, 2/3 of
+                        // the traffic) and scatter the 16-bit rows (>= 1 KB each) to their window-order position
       } else if (mode == LN_WINDOW) {
         int b = row / g.N, rr = row - b * g.N;
-        src[0] = static_cast<long long>(b) * g.N + win_row_to_token(g, rr);
+        src[0] = static_cast<long long>(b) * g.N + win_row_to_token(g, rr);   // narrow rows: gather reads, dense writes
       } else {
         const int Wo = g.W >> 1, No = (g.H >> 1) * Wo;
         int b = row / No, t = row - b * No;
@@ -92,7 +93,12 @@ ln_rows_kernel(const float* __restrict__ x, const float* __restrict__ gamma, con
       }
     }
     const float rstd = rsqrtf(warp_sum(sq) / float(Cout) + eps);
-    OutT* orow = out + static_cast<long long>(row) * ldo;
+    long long drow = row;
+    if (mode == LN_WINDOW && C >= 512) {
+      const int b = row / g.N, t = row - b * g.N;
+      drow = static_cast<long long>(b) * g.N + win_token_to_row(g, t);
+    }
+    OutT* orow = out + drow * ldo;
 #pragma unroll
     for (int j = 0; j < MAXJ; ++j) {
       int i4 = lane + 32 * j;
@@ -120,7 +126,7 @@ static int launch_ln_t(const float* x, const float* gamma, const float* beta, fl
   const int Cout = mode == LN_MERGE2X2 ? 4 * C : C;
   if (Cout <= 128) launch_ln_cfg<1, 8, OutT>(x, gamma, beta, eps, out, ldo, rows, C, mode, g, stream);
   else if (Cout <= 256) launch_ln_cfg<2, 4, OutT>(x, gamma, beta, eps, out, ldo, rows, C, mode, g, stream);
-  else if (Cout <= 512) launch_ln_cfg<4, 4, OutT>(x, gamma, beta, eps, out, ldo, rows, C, mode, g, stream);
+  else if (Cout <= 512) launch_ln_cfg<4, 2, OutT>(x, gamma, beta, eps, out, ldo, rows, C, mode, g, stream);
   else if (Cout <= 1024) launch_ln_cfg<8, 2, OutT>(x, gamma, beta, eps, out, ldo, rows, C, mode, g, stream);
   else if (Cout <= 2048) launch_ln_cfg<16, 1, OutT>(x, gamma, beta, eps, out, ldo, rows, C, mode, g, stream);
   else if (Cout <= 4096) launch_ln_cfg<32, 1, OutT>(x, gamma, beta, eps, out, ldo, rows, C, mode, g, stream);

@@ -37,6 +37,7 @@ SIGNATURES = {
                         c_longlong, c_int, c_int, c_int, c_void_p],
     "csvit_set_gemm_tuning": [c_int, c_int, c_int, c_int],
     "csvit_expand_rel_bias_mma": [c_void_p, c_void_p, c_int, c_int, c_void_p],
+    "csvit_set_attention_impl": [c_int],
     "csvit_window_attention": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                c_void_p],
     "csvit_attention": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_longlong, c_longlong, c_longlong, c_longlong,

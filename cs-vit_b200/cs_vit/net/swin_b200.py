@@ -187,8 +187,7 @@ class SwinBackboneB200(nn.Module):
         bqkv_src = [sa.query.bias, sa.key.bias, sa.value.bias]
         bqkv = self._w(key + "bqkv", bqkv_src, lambda: torch.cat([b.detach() for b in bqkv_src], 0).float().contiguous())
         bias = self._w(key + "relbias", [sa.relative_position_bias_table],
-                       lambda: (ops.expand_rel_bias if self._fp32 else ops.expand_rel_bias_mma)(
-                           sa.relative_position_bias_table.detach(), ws))
+                       lambda: ops.expand_rel_bias(sa.relative_position_bias_table.detach(), ws))
         eps = cfg.layer_norm_eps
         ln1, ln2 = blk.layernorm_before, blk.layernorm_after
         fused_ln = self.fuse_ln and not self._fp32 and x.shape[1] in ops.LN_LINEAR_WIDTHS

@@ -246,12 +246,15 @@ def mlp_fused(xn: torch.Tensor, w1: torch.Tensor, b1: torch.Tensor, w2: torch.Te
 
 # ---------------------------------------------------------------------------------------------- attention
 def window_attention(qkv: torch.Tensor, bias_exp: torch.Tensor, B: int, H: int, W: int, heads: int, ws: int,
-                     shift: int) -> torch.Tensor:
-    """``bias_exp``: ``expand_rel_bias`` table for fp32 qkv, ``expand_rel_bias_mma`` table for bf16 / fp16 qkv."""
-    _dev(qkv, bias_exp)
-    plain, frag = (bias_exp, None) if qkv.dtype == torch.float32 else (None, bias_exp)
-    if frag is not None and frag.dim() != 5:
-        raise ValueError("16-bit window attention needs the expand_rel_bias_mma table")
+                     shift: int, bias_mma: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``bias_exp``: ``expand_rel_bias`` table ``[h,L,L]`` (fp32 kernel and the tcgen05 16-bit kernel) or, for backward
+    compatibility, an ``expand_rel_bias_mma`` table (5-D) which selects the mma.sync 16-bit kernel."""
+    _dev(qkv, bias_exp, bias_mma)
+    plain, frag = bias_exp, bias_mma
+    if bias_exp.dim() == 5:
+        plain, frag = None, bias_exp
+    if qkv.dtype != torch.float32 and plain is None and frag is None:
+        raise ValueError("window attention needs a bias table")
     rows, C3, ld = _rows2d(qkv)
     C = C3 // 3
     if ld != C3 or rows != B * H * W:
@@ -260,6 +263,10 @@ def window_attention(qkv: torch.Tensor, bias_exp: torch.Tensor, B: int, H: int, 
     _call("csvit_window_attention", qkv.data_ptr(), _p(plain), _p(frag), out.data_ptr(), _code(qkv.dtype), B, H, W, C,
           heads, ws, shift, _stream(), nbytes=float(qkv.numel() + out.numel()) * qkv.element_size())
     return out
+
+
+def set_attention_impl(use_tcgen05: bool = True) -> None:
+    _lib.check(_lib.load().csvit_set_attention_impl(1 if use_tcgen05 else 0))
 
 
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, n_seq: int, Lq: int, S: int, heads: int,

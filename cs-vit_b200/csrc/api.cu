@@ -32,6 +32,7 @@ static_assert(int(CSVIT_GEMM_SIMT_FP32) == int(GEMM_SIMT), "gemm impl codes");
 
 static inline cudaStream_t S(void* s) { return static_cast<cudaStream_t>(s); }
 static GemmTuning g_tune = {0, 0, -1, -1};
+static int g_attn_tc = 1;
 
 extern "C" {
 
@@ -175,9 +176,16 @@ int csvit_expand_rel_bias_mma(const float* table, float* out, int heads, int ws,
   return launch_expand_rel_bias_mma(table, out, heads, S(stream));
 }
 
+int csvit_set_attention_impl(int use_tcgen05) {
+  g_attn_tc = use_tcgen05 ? 1 : 0;
+  return 0;
+}
+
 int csvit_window_attention(const void* qkv, const float* bias, const float* bias_mma, void* out, int dtype, int B, int H,
                            int W, int C, int heads, int ws, int shift, void* stream) {
   if (dtype == DT_BF16 || dtype == DT_F16) {
+    // tcgen05 kernel (plain [h,L,L] bias) when that table is given, mma.sync kernel (fragment-ordered bias) otherwise
+    if (bias != nullptr && g_attn_tc) return launch_window_attention_tc(qkv, bias, out, dtype, B, H, W, C, heads, ws, shift, S(stream));
     CSVIT_REQUIRE(bias_mma != nullptr, "window_attention: 16-bit path needs the csvit_expand_rel_bias_mma table");
     return launch_window_attention_mma(qkv, bias_mma, out, dtype, B, H, W, C, heads, ws, shift, S(stream));
   }

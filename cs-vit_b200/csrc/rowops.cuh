@@ -23,6 +23,10 @@ int launch_ln_gemm(const float* x, const float* gamma, const float* beta, float 
                    const void* W, long long ldw, int dtype, int M, int N, int C, const float* bias, int act, void* out,
                    long long ldo, cudaStream_t stream);
 
+// attention_tc.cu
+int launch_window_attention_tc(const void* qkv, const float* bias_plain, void* out, int dtype, int B, int H, int W, int C,
+                               int heads, int ws, int shift, cudaStream_t stream);
+
 // mlp_fused.cu
 int launch_mlp_fused(const void* xn, long long ldxn, const void* W1, long long ldw1, const float* b1, const void* W2,
                      long long ldw2, const float* b2, float* x, long long ldx, int dtype, int M, int C, cudaStream_t stream);

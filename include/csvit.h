@@ -131,9 +131,13 @@ CSVIT_API int csvit_set_gemm_tuning(int cluster, int tma_store, int max_ctas, in
  * bf16 / fp16: tensor-core kernel (window 7, head_dim 32).  fp32: exact kernel (validation mode).
  * fp32 reads `bias` = the [heads, L, L] table of csvit_expand_rel_bias; the 16-bit kernel reads `bias_mma` = the
  * same values pre-arranged in MMA accumulator-fragment order by csvit_expand_rel_bias_mma
- * ([heads, 4, 7, 32, 4] floats, -inf in the padding columns).  The unused one may be NULL. */
+ * ([heads, 4, 7, 32, 4] floats, -inf in the padding columns).  The unused one may be NULL.
+ * 16-bit dtypes: if `bias` is given the tcgen05/TMEM kernel runs (two windows per block-diagonal 128-row tile);
+ * with only `bias_mma` (or after csvit_set_attention_impl(0)) the mma.sync kernel runs. */
 CSVIT_API int csvit_window_attention(const void* qkv, const float* bias, const float* bias_mma, void* out, int dtype,
                                      int B, int H, int W, int C, int heads, int ws, int shift, void* stream);
+
+CSVIT_API int csvit_set_attention_impl(int use_tcgen05);
 
 /* Dense multi-head attention for short sequences (S <= 64, head_dim 32), exact fp32 math:
  *   out[s, i, h*32:(h+1)*32] = softmax_j(q[s,i,h] . k[s,j,h] * scale) v[s,j,h]

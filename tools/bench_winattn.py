@@ -10,8 +10,9 @@ for s, (hw, c, h) in enumerate([(56, 128, 4), (28, 256, 8), (14, 512, 16), (7, 1
     if only and only != f"s{s}": continue
     g = torch.Generator(device="cuda").manual_seed(s)
     qkv = torch.randn(B * hw * hw, 3 * c, device="cuda", generator=g).to(dt)
-    bias = ops.expand_rel_bias_mma(torch.randn(169, h, device="cuda", generator=g), 7)
-    for shift in ((0, 3) if hw > 7 else (0,)):
+    table = torch.randn(169, h, device="cuda", generator=g)
+    for shift, impl in [(sh, im) for sh in ((0, 3) if hw > 7 else (0,)) for im in ("mma.sync", "tcgen05")]:
+        bias = ops.expand_rel_bias_mma(table, 7) if impl == "mma.sync" else ops.expand_rel_bias(table, 7)
         f = lambda: ops.window_attention(qkv, bias, B, hw, hw, h, 7, shift)
         for _ in range(3): f()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -20,4 +21,4 @@ for s, (hw, c, h) in enumerate([(56, 128, 4), (28, 256, 8), (14, 512, 16), (7, 1
         e1.record(); torch.cuda.synchronize()
         us = e0.elapsed_time(e1) * 100
         byts = qkv.numel() * 2 * 4 / 3
-        print(f"s{s} shift={shift} items={B*(hw//7)**2*h:7d} {us:8.1f} us  {byts/us/1e6:6.2f} TB/s  {B*(hw//7)**2*h/us:6.1f} items/us", flush=True)
+        print(f"s{s} {impl:8s} shift={shift} items={B*(hw//7)**2*h:7d} {us:8.1f} us  {byts/us/1e6:6.2f} TB/s  {B*(hw//7)**2*h/us:6.1f} items/us", flush=True)

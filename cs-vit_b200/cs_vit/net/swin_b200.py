@@ -198,7 +198,9 @@ class SwinBackboneB200(nn.Module):
             xn = ops.layernorm(x, self._f32(key + "ln1w", ln1.weight), self._f32(key + "ln1b", ln1.bias), eps, out_dtype=act,
                                mode=ops.LN_WINDOW, grid=(H, W), ws=ws, shift=shift)
             qkv = ops.linear(xn, wqkv, bqkv, out_dtype=act, impl=impl)
-        ctx = ops.window_attention(qkv, bias, B, H, W, heads, ws, shift)
+        bias_mma = None if self._fp32 else self._w(key + "relbias_mma", [sa.relative_position_bias_table],
+                                                   lambda: ops.expand_rel_bias_mma(sa.relative_position_bias_table.detach(), ws))
+        ctx = ops.window_attention(qkv, bias, B, H, W, heads, ws, shift, bias_mma=bias_mma)
         proj = blk.attention.output.dense
         ops.linear(ctx, self._weight(key + "wproj", proj.weight), self._f32(key + "bproj", proj.bias), resid=x, out=x,
                    scatter=(H, W, ws, shift), impl=impl)

@@ -32,7 +32,7 @@ static_assert(int(CSVIT_GEMM_SIMT_FP32) == int(GEMM_SIMT), "gemm impl codes");
 
 static inline cudaStream_t S(void* s) { return static_cast<cudaStream_t>(s); }
 static GemmTuning g_tune = {0, 0, -1, -1};
-static int g_attn_tc = 1;
+static int g_attn_tc = 0;   // measured (profiles/r1_window_attention_impls.txt): the mma.sync kernel is 1.4x faster at 49-token windows
 
 extern "C" {
 
@@ -185,7 +185,7 @@ int csvit_window_attention(const void* qkv, const float* bias, const float* bias
                            int W, int C, int heads, int ws, int shift, void* stream) {
   if (dtype == DT_BF16 || dtype == DT_F16) {
     // tcgen05 kernel (plain [h,L,L] bias) when that table is given, mma.sync kernel (fragment-ordered bias) otherwise
-    if (bias != nullptr && g_attn_tc) return launch_window_attention_tc(qkv, bias, out, dtype, B, H, W, C, heads, ws, shift, S(stream));
+    if (bias != nullptr && (g_attn_tc || bias_mma == nullptr)) return launch_window_attention_tc(qkv, bias, out, dtype, B, H, W, C, heads, ws, shift, S(stream));
     CSVIT_REQUIRE(bias_mma != nullptr, "window_attention: 16-bit path needs the csvit_expand_rel_bias_mma table");
     return launch_window_attention_mma(qkv, bias_mma, out, dtype, B, H, W, C, heads, ws, shift, S(stream));
   }

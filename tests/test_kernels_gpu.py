@@ -192,9 +192,16 @@ def test_window_attention(ops, H, heads, shift, dtype):
     ref = (s.softmax(-1) @ v).transpose(1, 2).reshape(B * H * W, C)
     tol = {torch.bfloat16: 1e-2, torch.float16: 2e-3, torch.float32: 1e-5}[dtype]
     assert rel(out, ref) < tol
-    if dtype != torch.float32:   # the mma.sync kernel (fragment-ordered bias table) must agree with the tcgen05 one
+    if dtype != torch.float32:
+        # `bias` alone selected the tcgen05/TMEM kernel above; the mma.sync kernel (fragment-ordered table) must agree
         out2 = ops.window_attention(qkv, ops.expand_rel_bias_mma(table, ws), B, H, W, heads, ws, shift)
         assert rel(out2, ref) < tol
+        try:   # explicit selection with both tables present
+            ops.set_attention_impl(True)
+            out3 = ops.window_attention(qkv, bias, B, H, W, heads, ws, shift, bias_mma=ops.expand_rel_bias_mma(table, ws))
+        finally:
+            ops.set_attention_impl(False)
+        assert torch.equal(out3, out)
 
 
 @pytest.mark.parametrize("Lq,S", [(52, 52), (3, 49), (3, 3), (1, 8)])

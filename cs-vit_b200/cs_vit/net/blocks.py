@@ -22,6 +22,7 @@ from typing import Optional
 import torch
 import torch.nn as nn
 
+from .. import autograd as ag
 from .. import ops
 from ._pack import PackCache, fold_batchnorm
 
@@ -40,9 +41,20 @@ class _KernelModule(nn.Module):
         return ops.GEMM_SIMT if self.precision == "fp32" else ops.GEMM_TC
 
     def _bn(self, name: str, bn: nn.BatchNorm1d):
-        if bn.training:
-            raise NotImplementedError("train-mode BatchNorm statistics are not built yet (inference / eval only)")
         return self._pack.get(name, [bn.weight, bn.bias, bn.running_mean, bn.running_var], lambda: fold_batchnorm(bn))
+
+    def _norm(self, name: str, bn: nn.BatchNorm1d, x2d: torch.Tensor, grad: bool) -> torch.Tensor:
+        """BatchNorm1d over channels of ``[rows, C]``: batch statistics in train mode, folded running statistics in eval
+        mode; differentiable when ``grad`` (ref:cs_vit/net/transformer_module.py:306-307,312,316)."""
+        if grad or bn.training:
+            return ag.batchnorm(x2d, bn)
+        return ops.affine_rows(x2d, *self._bn(name, bn))
+
+    def _grad(self, *tensors: Optional[torch.Tensor]) -> bool:
+        """True when this call must be differentiable: autograd is on and an input or a parameter of the module wants a gradient."""
+        if not torch.is_grad_enabled():
+            return False
+        return any(t is not None and t.requires_grad for t in tensors) or any(p.requires_grad for p in self.parameters())
 
     @staticmethod
     def _check(x: torch.Tensor) -> None:
@@ -105,6 +117,8 @@ class MHA(_KernelModule):
         """x2d [n*L, D]; ctx2d [n*S, D] or None for self-attention.  Returns resid + MHA(x, ctx) as [n*L, D]."""
         D, h = self.embed_dim, self.num_heads
         scale = 1.0 / self.inv_sqrt_head_dim      # logits are DIVIDED by 1/sqrt(d)  (ref :273, quirk Q1)
+        if self._grad(x2d, ctx2d, resid):
+            return self._attend_grad(x2d, ctx2d, n, L, S, resid, scale)
         if ctx2d is None:
             w, b = self._stack("qkv", [self.query, self.key, self.value])
             qkv = ops.linear(x2d, w, b, impl=self._impl)
@@ -118,6 +132,20 @@ class MHA(_KernelModule):
         ctx = ops.attention(q, k, v, n, L, S, h, scale)
         wo, bo = self._stack("o", [self.output])
         return ops.linear(ctx, wo, bo, resid=resid, impl=self._impl)
+
+    def _attend_grad(self, x2d, ctx2d, n, L, S, resid, scale):
+        """Same computation through the differentiable ops (cs_vit/autograd.py); Q/K/V stay separate parameters, so
+        the stacked weight is a differentiable ``cat``."""
+        D, h = self.embed_dim, self.num_heads
+        q_, k_, v_ = self.query, self.key, self.value
+        if ctx2d is None:
+            qkv = ag.linear(x2d, torch.cat([q_.weight, k_.weight, v_.weight], 0), torch.cat([q_.bias, k_.bias, v_.bias], 0), impl=self._impl)
+            c = ag.attention_packed(qkv, D, n, L, h, scale)
+        else:
+            q = ag.linear(x2d, q_.weight, q_.bias, impl=self._impl)
+            kv = ag.linear(ctx2d, torch.cat([k_.weight, v_.weight], 0), torch.cat([k_.bias, v_.bias], 0), impl=self._impl)
+            c = ag.attention_cross(q, kv, D, n, L, S, h, scale)
+        return ag.linear(c, self.output.weight, self.output.bias, resid=resid, impl=self._impl)
 
     def forward(self, x: torch.Tensor, ctx: torch.Tensor) -> torch.Tensor:
         self._check(x)
@@ -134,6 +162,9 @@ class FeedForwardNetwork(_KernelModule):
 
     def run(self, y2d: torch.Tensor, resid: Optional[torch.Tensor]) -> torch.Tensor:
         f1, f2 = self.net[0], self.net[2]
+        if self._grad(y2d, resid):
+            hid = ag.gelu(ag.linear(y2d, f1.weight, f1.bias, impl=self._impl))
+            return ag.linear(hid, f2.weight, f2.bias, resid=resid, impl=self._impl)
         hid = ops.linear(y2d, f1.weight.detach().float(), f1.bias.detach().float(), act=ops.ACT_GELU, impl=self._impl)
         return ops.linear(hid, f2.weight.detach().float(), f2.bias.detach().float(), resid=resid, impl=self._impl)
 
@@ -154,9 +185,10 @@ class EncoderBlock(_KernelModule):
         self._check(x)
         n, L, D = x.shape
         x2 = _flat(x)
-        y = ops.affine_rows(x2, *self._bn("n1", self.norm1))
+        g = self._grad(x)
+        y = self._norm("n1", self.norm1, x2, g)
         x2 = self.attn.attend(y, None, n, L, L, x2)
-        y = ops.affine_rows(x2, *self._bn("n2", self.norm2))
+        y = self._norm("n2", self.norm2, x2, g)
         return self.ffn.run(y, x2).view(n, L, D)
 
 
@@ -174,11 +206,12 @@ class DecoderBlock(_KernelModule):
         self._check(x)
         n, L, D = x.shape
         x2, r2 = _flat(x), _flat(ref)
-        y = ops.affine_rows(x2, *self._bn("n1", self.norm1))
+        g = self._grad(x, ref)
+        y = self._norm("n1", self.norm1, x2, g)
         x2 = self.self_atten.attend(y, None, n, L, L, x2)
-        y = ops.affine_rows(x2, *self._bn("n2", self.norm2))
+        y = self._norm("n2", self.norm2, x2, g)
         x2 = self.cross_atten.attend(y, r2, n, L, ref.shape[1], x2)     # ``ref`` is not normalised (ref :345-346)
-        y = ops.affine_rows(x2, *self._bn("n3", self.norm3))
+        y = self._norm("n3", self.norm3, x2, g)
         return self.ffn.run(y, x2).view(n, L, D)
 
 
@@ -194,9 +227,10 @@ class CrossAttnDecoder(_KernelModule):
         self._check(x)
         n, L, D = x.shape
         x2, r2 = _flat(x), _flat(ref)
-        y = ops.affine_rows(x2, *self._bn("n1", self.norm1))
+        g = self._grad(x, ref)
+        y = self._norm("n1", self.norm1, x2, g)
         x2 = self.cross_atten.attend(y, r2, n, L, ref.shape[1], x2)
-        y = ops.affine_rows(x2, *self._bn("n2", self.norm2))
+        y = self._norm("n2", self.norm2, x2, g)
         return self.ffn.run(y, x2).view(n, L, D)
 
 

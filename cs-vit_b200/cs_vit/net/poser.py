@@ -23,6 +23,7 @@ import numpy as np
 import torch
 import torch.nn as nn
 
+from .. import autograd as ag
 from .. import ops
 from ..constants import TARGET_JOINTS_CONNECTION
 from ..utils.geometry import matrix_to_axis_angle, rotation_6d_to_matrix
@@ -90,7 +91,10 @@ class TemporalEncoder(_KernelModule):
             u = self.pe_temporal(x)
             for layer in self.layers:
                 u = layer(u)
-        out = ops.linear(_flat(u), self.zero_conv.weight.detach().float(), None, impl=self._impl)
+        if self._grad(u):
+            out = ag.linear(_flat(u), self.zero_conv.weight, None, impl=self._impl)
+        else:
+            out = ops.linear(_flat(u), self.zero_conv.weight.detach().float(), None, impl=self._impl)
         return out.view(u.shape)
 
 
@@ -106,12 +110,18 @@ class PerspectiveEncoder(_KernelModule):
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         """``(n, patch_res*persp_dim)`` -> ``(n, D)``   (ref:cs_vit/net/ti_poser.py:161-182)."""
         self._check(x)
+        last = self.layer[9]
+        if self._grad(x):    # differentiable ops (train-mode BatchNorm uses batch statistics)
+            y = ag.linear(_flat(x), self.proj.weight, self.proj.bias, impl=self._impl)
+            for k in range(3):
+                bn, lin = self.layer[3 * k], self.layer[3 * k + 1]
+                y = ag.linear(self._norm(f"bn{k}", bn, y, True), lin.weight, lin.bias, act=ops.ACT_RELU, impl=self._impl)
+            return ag.linear(y, last.weight, last.bias, impl=self._impl)
         y = ops.linear(_flat(x), self.proj.weight.detach().float(), self.proj.bias.detach().float(), impl=self._impl)
         for k in range(3):
             bn, lin = self.layer[3 * k], self.layer[3 * k + 1]
-            y = ops.affine_rows(y, *self._bn(f"bn{k}", bn))
+            y = self._norm(f"bn{k}", bn, y, False)
             y = ops.linear(y, lin.weight.detach().float(), lin.bias.detach().float(), act=ops.ACT_RELU, impl=self._impl)
-        last = self.layer[9]
         return ops.linear(y, last.weight.detach().float(), last.bias.detach().float(), impl=self._impl)
 
 
@@ -256,6 +266,9 @@ class Poser(nn.Module):
     # ------------------------------------------------------------------------------------------ forward pieces
     def _linear_head(self, seq: nn.Sequential, x: torch.Tensor) -> torch.Tensor:
         lin = seq[0]
+        if torch.is_grad_enabled() and (x.requires_grad or lin.weight.requires_grad):
+            # the three output heads (96 / 10 / 3 columns) stay PyTorch in the training step
+            return torch.nn.functional.linear(x, lin.weight, lin.bias)
         impl = ops.GEMM_SIMT if self.precision == "fp32" else ops.GEMM_TC
         y = ops.linear(_flat(x), lin.weight.detach().float(), lin.bias.detach().float(), impl=impl)
         return y.view(*x.shape[:-1], -1)

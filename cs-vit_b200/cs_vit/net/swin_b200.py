@@ -220,10 +220,12 @@ class SwinBackboneB200(nn.Module):
                              out_dtype=act, impl=impl)
         ops.linear(hid, self._weight(key + "w2", fc2.weight), self._f32(key + "b2", fc2.bias), resid=x, out=x, impl=impl)
 
-    @torch.no_grad()
     def forward_features(self, images: torch.Tensor, normalize: bool, return_stages: bool = False):
         """images fp32 ``[n,3,S,S]``; ``normalize`` folds the ImageNet mean/std of
-        ref:cs_vit/net/ti_poser.py:239-243 into the patch unfold.  Returns fp32 ``[n, (S/32)^2, hidden]``."""
+        ref:cs_vit/net/ti_poser.py:239-243 into the patch unfold.  Returns fp32 ``[n, (S/32)^2, hidden]``.
+
+        With autograd enabled and trainable parameters the differentiable path runs (one ``autograd.Function`` per block,
+        activations kept for the backward kernels); otherwise the in-place inference path."""
         cfg = self.config
         if not images.is_cuda:
             raise RuntimeError("SwinBackboneB200 runs on CUDA tensors only (there is no CPU fallback)")
@@ -232,6 +234,70 @@ class SwinBackboneB200(nn.Module):
         n, _, S, S2 = images.shape
         if S != S2 or S % (32 * cfg.window_size) != 0:
             raise ValueError(f"image side {S} must be a multiple of {32 * cfg.window_size} (no padding path, SURVEY.md §8b)")
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            if return_stages:
+                raise ValueError("return_stages is an inference-path diagnostic")
+            return self._forward_train(images, normalize)
+        with torch.no_grad():
+            return self._forward_infer(images, normalize, return_stages)
+
+    # ------------------------------------------------------------------------------------------ training path
+    def _block_pack(self, blk: _BlockParams, key: str, ws: int) -> Dict:
+        act = self._act_dtype
+        sa = blk.attention.self
+        qkv_src = [sa.query.weight, sa.key.weight, sa.value.weight]
+        bqkv_src = [sa.query.bias, sa.key.bias, sa.value.bias]
+        tab = sa.relative_position_bias_table
+        return {
+            "wqkv": self._w(key + "wqkv", qkv_src, lambda: torch.cat([w.detach() for w in qkv_src], 0).to(act).contiguous()),
+            "bqkv": self._w(key + "bqkv", bqkv_src, lambda: torch.cat([b.detach() for b in bqkv_src], 0).float().contiguous()),
+            "bias": self._w(key + "relbias", [tab], lambda: ops.expand_rel_bias(tab.detach(), ws)),
+            "bias_mma": None if self._fp32 else self._w(key + "relbias_mma", [tab], lambda: ops.expand_rel_bias_mma(tab.detach(), ws)),
+            "wo": self._weight(key + "wproj", blk.attention.output.dense.weight),
+            "w1": self._weight(key + "w1", blk.intermediate.dense.weight),
+            "w2": self._weight(key + "w2", blk.output.dense.weight),
+            "rel_index": self._w(key + "relidx", [sa.relative_position_index], lambda: sa.relative_position_index.reshape(-1).long()),
+            "table_rows": tab.shape[0],
+        }
+
+    def _forward_train(self, images: torch.Tensor, normalize: bool) -> torch.Tensor:
+        """Differentiable forward: same kernels, out-of-place residual stream, activations saved per block
+        (cs_vit/autograd.py holds the backward of every stage)."""
+        from .. import autograd as ag
+        cfg = self.config
+        n, _, S, _ = images.shape
+        act = self._act_dtype
+        impl = ops.GEMM_SIMT if self._fp32 else ops.GEMM_TC
+        eps = cfg.layer_norm_eps
+        H = W = S // 4
+        pe = self.embeddings.patch_embeddings.projection
+        x = ag.PatchEmbedFn.apply(images.float().contiguous(), pe.weight, pe.bias, self.embeddings.norm.weight, self.embeddings.norm.bias,
+                                  self._weight("pe_w", pe.weight), (normalize, eps, act, impl))
+        for s, stage in enumerate(self.encoder.layers):
+            heads = cfg.num_heads[s]
+            for i, blk in enumerate(stage.blocks):
+                ws, shift = cfg.window_size, (0 if i % 2 == 0 else cfg.window_size // 2)
+                if min(H, W) <= ws:  # HF:548-554
+                    ws, shift = min(H, W), 0
+                sa = blk.attention.self
+                pk = self._block_pack(blk, f"s{s}b{i}/", ws)
+                x = ag.SwinBlockFn.apply(
+                    x, blk.layernorm_before.weight, blk.layernorm_before.bias, sa.query.weight, sa.query.bias, sa.key.weight,
+                    sa.key.bias, sa.value.weight, sa.value.bias, sa.relative_position_bias_table, blk.attention.output.dense.weight,
+                    blk.attention.output.dense.bias, blk.layernorm_after.weight, blk.layernorm_after.bias, blk.intermediate.dense.weight,
+                    blk.intermediate.dense.bias, blk.output.dense.weight, blk.output.dense.bias, pk,
+                    (n, H, W, heads, ws, shift, eps, act, impl))
+            if hasattr(stage, "downsample"):
+                ds = stage.downsample
+                x = ag.PatchMergeFn.apply(x, ds.norm.weight, ds.norm.bias, ds.reduction.weight,
+                                          self._weight(f"s{s}/dsr", ds.reduction.weight), (H, W, eps, act, impl))
+                H, W = H // 2, W // 2
+        out = ag.LayerNormFn.apply(x, self.layernorm.weight, self.layernorm.bias, eps)
+        return out.view(n, H * W, cfg.hidden_size)
+
+    def _forward_infer(self, images: torch.Tensor, normalize: bool, return_stages: bool = False):
+        cfg = self.config
+        n, _, S, _ = images.shape
         act = self._act_dtype
         impl = ops.GEMM_SIMT if self._fp32 else ops.GEMM_TC
         eps = cfg.layer_norm_eps

@@ -284,6 +284,136 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, n_seq: int, Lq:
     return out
 
 
+# ---------------------------------------------------------------------------------------------- training step (backward)
+CR_SUM, CR_CENTERED, CR_DOT = 0, 1, 2
+EW_GELU_FWD, EW_GELU_BWD, EW_RELU_BWD = 0, 1, 2
+
+
+def gemm_ex(a: torch.Tensor, a_mn: bool, b: torch.Tensor, b_mn: bool, *, out: Optional[torch.Tensor] = None,
+            out_dtype: Optional[torch.dtype] = None, accumulate: bool = False, impl: int = GEMM_TC, split_k: int = 0) -> torch.Tensor:
+    """``out[M,N] (+)= sum_k A(m,k) B(n,k)``; ``a_mn`` / ``b_mn`` say the operand is stored ``[K, M|N]`` (see ``csvit_gemm_ex``)."""
+    _dev(a, b, out)
+    if a.dtype == torch.float32 and impl == GEMM_TC:   # kind::tf32 is K-major only: transpose the (small) fp32 operands
+        if a_mn:
+            a, a_mn = transpose(a), False
+        if b_mn:
+            b, b_mn = transpose(b), False
+    r0, c0, lda = _rows2d(a)
+    r1, c1, ldb = _rows2d(b)
+    M, K = (c0, r0) if a_mn else (r0, c0)
+    N, K2 = (c1, r1) if b_mn else (r1, c1)
+    if K != K2 or a.dtype != b.dtype:
+        raise ValueError(f"gemm_ex: A {tuple(a.shape)}/{a.dtype} (mn={a_mn}) vs B {tuple(b.shape)}/{b.dtype} (mn={b_mn})")
+    if out is None:
+        if accumulate:
+            raise ValueError("gemm_ex: accumulate needs an output tensor")
+        out = torch.empty(M, N, dtype=out_dtype or a.dtype, device=a.device)
+    Mo, No, ldo = _rows2d(out)
+    if (Mo, No) != (M, N):
+        raise ValueError("gemm_ex: output shape mismatch")
+    _call("csvit_gemm_ex", a.data_ptr(), lda, int(a_mn), b.data_ptr(), ldb, int(b_mn), _code(a.dtype), M, N, K, out.data_ptr(), ldo,
+          _code(out.dtype), int(accumulate), impl, split_k, _stream(), flops=2.0 * M * N * K)
+    return out
+
+
+def transpose(x: torch.Tensor) -> torch.Tensor:
+    """fp32 ``[R, C]`` -> contiguous ``[C, R]`` (row pitch padded to a 16-byte multiple for TMA)."""
+    _dev(x)
+    R, C, ld = _rows2d(x)
+    if x.dtype != torch.float32:
+        raise TypeError("transpose: float32 only")
+    parent = torch.empty(C, -(-R // 4) * 4, dtype=torch.float32, device=x.device)
+    _call("csvit_transpose_f32", x.data_ptr(), ld, parent.data_ptr(), parent.stride(0), R, C, _stream())
+    return parent[:, :R]
+
+
+def col_reduce(a: torch.Tensor, mode: int = CR_SUM, *, b: Optional[torch.Tensor] = None, center: Optional[torch.Tensor] = None,
+               window: Optional[Tuple[int, int, int, int]] = None, copy_dtype: Optional[torch.dtype] = None, sums: bool = True):
+    """Column sums of ``a [rows, C]`` (+ second moment / dot, see ``csvit_col_reduce``) and, with ``copy_dtype``, a converted
+    (optionally window-gathered) copy of the rows.  Returns ``(s1, s2, copy)`` with ``None`` for the parts not requested."""
+    _dev(a, b, center)
+    rows, C, lda = _rows2d(a)
+    s1 = torch.zeros(C, dtype=torch.float32, device=a.device) if sums else None
+    s2 = torch.zeros(C, dtype=torch.float32, device=a.device) if sums and mode != CR_SUM else None
+    copy = torch.empty(rows, C, dtype=copy_dtype, device=a.device) if copy_dtype is not None else None
+    ldb = 0
+    if b is not None:
+        if b.dtype != torch.float32 or b.shape != a.shape:
+            raise ValueError("col_reduce: second operand must be float32 with the same shape")
+        ldb = _rows2d(b)[2]
+    H, W, ws, shift = window if window is not None else (0, 0, 0, 0)
+    _call("csvit_col_reduce", a.data_ptr(), _code(a.dtype), lda, _p(b), ldb, _p(center), mode, rows, C,
+          LN_WINDOW if window is not None else LN_IDENTITY, H, W, ws, shift, _p(copy), _code(copy_dtype or torch.float32),
+          C, _p(s1), _p(s2), _stream())
+    return s1, s2, copy
+
+
+def eltwise(op: int, a: torch.Tensor, b: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _dev(a, b)
+    if not a.is_contiguous() or (b is not None and (not b.is_contiguous() or b.dtype != a.dtype or b.shape != a.shape)):
+        raise ValueError("eltwise: operands must be contiguous with the same shape and dtype")
+    out = torch.empty_like(a)
+    _call("csvit_eltwise", op, a.data_ptr(), _p(b), out.data_ptr(), _code(a.dtype), a.numel(), _stream())
+    return out
+
+
+def affine2_rows(dy: torch.Tensor, x: torch.Tensor, a: torch.Tensor, b: torch.Tensor, c0: torch.Tensor,
+                 resid: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``a[c]*dy + b[c]*x + c0[c] (+ resid)`` on dense fp32 ``[rows, C]`` tensors (BatchNorm1d backward)."""
+    _dev(dy, x, a, b, c0, resid)
+    for t in (dy, x, resid):
+        if t is not None and (t.dtype != torch.float32 or not t.is_contiguous() or t.shape != dy.shape):
+            raise ValueError("affine2_rows: dense float32 operands of one shape")
+    rows, C = dy.shape
+    out = torch.empty_like(dy)
+    _call("csvit_affine2_rows", dy.data_ptr(), x.data_ptr(), a.data_ptr(), b.data_ptr(), c0.data_ptr(), _p(resid), out.data_ptr(),
+          rows, C, _stream())
+    return out
+
+
+def layernorm_bwd(x: torch.Tensor, dy: torch.Tensor, gamma: torch.Tensor, eps: float, *, mode: int = LN_IDENTITY,
+                  grid: Tuple[int, int] = (0, 0), ws: int = 0, shift: int = 0, dres: Optional[torch.Tensor] = None):
+    """Backward of ``layernorm``: returns ``(dx [rows_in, C] fp32 = dres + dLN, dgamma, dbeta)``."""
+    _dev(x, dy, gamma, dres)
+    if x.dtype != torch.float32 or not x.is_contiguous():
+        raise ValueError("layernorm_bwd: x must be contiguous float32")
+    rows_in, C = x.shape
+    rows, width, ldy = _rows2d(dy)
+    if (mode == LN_MERGE2X2 and (rows != rows_in // 4 or width != 4 * C)) or (mode != LN_MERGE2X2 and (rows != rows_in or width != C)):
+        raise ValueError("layernorm_bwd: dy shape does not match the forward output")
+    if dres is not None and (dres.dtype != torch.float32 or dres.shape != x.shape or not dres.is_contiguous()):
+        raise ValueError("layernorm_bwd: dres must be contiguous float32 of x's shape")
+    dx = torch.empty_like(x)
+    dgamma = torch.zeros(width, dtype=torch.float32, device=x.device)
+    dbeta = torch.zeros(width, dtype=torch.float32, device=x.device)
+    H, W = grid
+    _call("csvit_layernorm_bwd", x.data_ptr(), dy.data_ptr(), _code(dy.dtype), ldy, gamma.data_ptr(), float(eps), rows, C, mode, H, W,
+          ws, shift, _p(dres), dx.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), _stream())
+    return dx, dgamma, dbeta
+
+
+def attention_bwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, dout: torch.Tensor, n_seq: int, Lq: int, S: int, heads: int,
+                  scale: float, *, bias: Optional[torch.Tensor] = None, mask: Optional[Tuple[int, int, int, int]] = None,
+                  dq: Optional[torch.Tensor] = None, dk: Optional[torch.Tensor] = None, dv: Optional[torch.Tensor] = None):
+    """Backward of ``attention`` / ``window_attention``.  q/k/v/dout (and dq/dk/dv when given) may be column slices.
+    Returns ``(dq, dk, dv, dbias or None)``."""
+    _dev(q, k, v, dout, bias, dq, dk, dv)
+    rq, D, ldq = _rows2d(q)
+    rk, _, ldk = _rows2d(k)
+    ldv, ldo = _rows2d(v)[2], _rows2d(dout)[2]
+    if rq != n_seq * Lq or rk != n_seq * S or D != heads * 32 or dout.shape != q.shape:
+        raise ValueError("attention_bwd: shape mismatch (head_dim must be 32)")
+    dq = torch.empty(rq, D, dtype=q.dtype, device=q.device) if dq is None else dq
+    dk = torch.empty(rk, D, dtype=q.dtype, device=q.device) if dk is None else dk
+    dv = torch.empty(rk, D, dtype=q.dtype, device=q.device) if dv is None else dv
+    dbias = torch.zeros(heads, Lq, S, dtype=torch.float32, device=q.device) if bias is not None else None
+    mH, mW, mws, msh = mask if mask is not None else (0, 0, 0, 0)
+    _call("csvit_attention_bwd", q.data_ptr(), k.data_ptr(), v.data_ptr(), dout.data_ptr(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(),
+          _code(q.dtype), ldq, ldk, ldv, ldo, dq.stride(0), dk.stride(0), dv.stride(0), n_seq, Lq, S, heads, float(scale),
+          _p(bias), _p(dbias), mH, mW, mws, msh, _stream())
+    return dq, dk, dv, dbias
+
+
 # ---------------------------------------------------------------------------------------------- host-side maps
 def host_maps(H: int, W: int, ws: int, shift: int):
     """CPU evaluation of the kernels' closed-form integer maps (same inline functions, compiled for the host).

@@ -206,4 +206,69 @@ int csvit_attention(const void* q, const void* k, const void* v, void* out, int 
                                S(stream));
 }
 
+// ---- training step (backward) ----------------------------------------------------------------------------
+int csvit_gemm_ex(const void* A, long long lda, int a_mn, const void* B, long long ldb, int b_mn, int in_dtype, int M, int N, int K,
+                  void* out, long long ldo, int out_dtype, int accumulate, int impl, int split_k, void* stream) {
+  CSVIT_REQUIRE(ok_dtype(in_dtype) && ok_dtype(out_dtype), "gemm_ex: bad dtype (%d, %d)", in_dtype, out_dtype);
+  CSVIT_REQUIRE(lda >= (a_mn ? M : K) && ldb >= (b_mn ? N : K) && ldo >= N, "gemm_ex: pitches smaller than the logical widths");
+  return launch_gemm_ex(A, lda, a_mn ? 1 : 0, B, ldb, b_mn ? 1 : 0, in_dtype, M, N, K, out, ldo, out_dtype, accumulate ? 1 : 0, impl,
+                        split_k, S(stream));
+}
+
+int csvit_col_reduce(const void* a, int a_dtype, long long lda, const float* b, long long ldb, const float* center, int mode,
+                     int rows, int C, int row_mode, int H, int W, int ws, int shift, void* copy, int copy_dtype, long long ldc,
+                     float* s1, float* s2, void* stream) {
+  CSVIT_REQUIRE(ok_dtype(a_dtype) && ok_dtype(copy_dtype), "col_reduce: bad dtype (%d, %d)", a_dtype, copy_dtype);
+  WinGeom g = make_geom(H > 0 ? H : 1, W > 0 ? W : 1, ws > 0 ? ws : 1, shift);
+  if (row_mode == LN_WINDOW) {
+    CSVIT_REQUIRE(ws > 0 && H % ws == 0 && W % ws == 0, "col_reduce(window): %dx%d not divisible by window %d", H, W, ws);
+    CSVIT_REQUIRE(shift >= 0 && shift < ws, "col_reduce(window): shift %d outside [0,%d)", shift, ws);
+    CSVIT_REQUIRE(rows % (H * W) == 0, "col_reduce(window): rows %d not a multiple of %d tokens", rows, H * W);
+  }
+  return launch_col_reduce(a, a_dtype, lda, b, ldb, center, mode, rows, C, row_mode, g, copy, copy_dtype, ldc, s1, s2, S(stream));
+}
+
+int csvit_transpose_f32(const float* src, long long lds, float* dst, long long ldd, int rows, int cols, void* stream) {
+  CSVIT_REQUIRE(lds >= cols && ldd >= rows, "transpose: pitches smaller than the logical widths");
+  return launch_transpose_f32(src, lds, dst, ldd, rows, cols, S(stream));
+}
+
+int csvit_eltwise(int op, const void* a, const void* b, void* out, int dtype, long long n, void* stream) {
+  CSVIT_REQUIRE(ok_dtype(dtype), "eltwise: bad dtype %d", dtype);
+  return launch_eltwise(op, a, b, out, dtype, n, S(stream));
+}
+
+int csvit_affine2_rows(const float* dy, const float* x, const float* a, const float* b, const float* c0, const float* resid,
+                       float* out, long long rows, int C, void* stream) {
+  return launch_affine2_rows(dy, x, a, b, c0, resid, out, rows, C, S(stream));
+}
+
+int csvit_layernorm_bwd(const float* x, const void* dy, int dy_dtype, long long ldy, const float* gamma, float eps, int rows, int C,
+                        int mode, int H, int W, int ws, int shift, const float* dres, float* dx, float* dgamma, float* dbeta,
+                        void* stream) {
+  CSVIT_REQUIRE(ok_dtype(dy_dtype), "layernorm_bwd: bad dy dtype %d", dy_dtype);
+  WinGeom g = make_geom(H > 0 ? H : 1, W > 0 ? W : 1, ws > 0 ? ws : 1, shift);
+  if (mode == LN_WINDOW) {
+    CSVIT_REQUIRE(ws > 0 && H % ws == 0 && W % ws == 0, "layernorm_bwd(window): %dx%d not divisible by window %d", H, W, ws);
+    CSVIT_REQUIRE(shift >= 0 && shift < ws, "layernorm_bwd(window): shift %d outside [0,%d)", shift, ws);
+    CSVIT_REQUIRE(rows % (H * W) == 0, "layernorm_bwd(window): rows %d not a multiple of %d tokens", rows, H * W);
+  } else if (mode == LN_MERGE2X2) {
+    CSVIT_REQUIRE(H % 2 == 0 && W % 2 == 0, "layernorm_bwd(merge): %dx%d must be even", H, W);
+    CSVIT_REQUIRE(rows % ((H / 2) * (W / 2)) == 0, "layernorm_bwd(merge): rows %d not a multiple of %d", rows, (H / 2) * (W / 2));
+  } else {
+    CSVIT_REQUIRE(mode == LN_IDENTITY, "layernorm_bwd: unknown mode %d", mode);
+  }
+  return launch_layernorm_bwd(x, dy, dy_dtype, ldy, gamma, eps, rows, C, mode, g, dres, dx, dgamma, dbeta, S(stream));
+}
+
+int csvit_attention_bwd(const void* q, const void* k, const void* v, const void* dout, void* dq, void* dk, void* dv, int dtype,
+                        long long ldq, long long ldk, long long ldv, long long ldo, long long lddq, long long lddk, long long lddv,
+                        int n_seq, int Lq, int S_, int heads, float scale, const float* bias, float* dbias, int mask_H, int mask_W,
+                        int mask_ws, int mask_shift, void* stream) {
+  CSVIT_REQUIRE(ok_dtype(dtype), "attention_bwd: bad dtype %d", dtype);
+  CSVIT_REQUIRE((bias == nullptr) == (dbias == nullptr) || dbias == nullptr, "attention_bwd: dbias given without bias");
+  return launch_attention_bwd(q, k, v, dout, dq, dk, dv, dtype, ldq, ldk, ldv, ldo, lddq, lddk, lddv, n_seq, Lq, S_, heads, scale,
+                              bias, dbias, mask_H, mask_W, mask_ws, mask_shift, S(stream));
+}
+
 }  // extern "C"

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define CSVIT_ABI_VERSION 1
+#define CSVIT_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define CSVIT_API __attribute__((visibility("default")))
@@ -146,6 +146,65 @@ CSVIT_API int csvit_set_attention_impl(int use_tcgen05);
  * ref:cs_vit/net/transformer_module.py:243,273).  dtype applies to q, k, v and out. */
 CSVIT_API int csvit_attention(const void* q, const void* k, const void* v, void* out, int dtype, long long ldq, long long ldk,
                     long long ldv, long long ldo, int n_seq, int Lq, int S, int heads, float scale, void* stream);
+
+/* ---- training step: backward kernels (BASELINE configs[3], the finetune step) ----------------------------
+ * torch autograd derives the backward of the reference from its eager ops (HF:591-653 SwinLayer; ref:cs_vit/net/
+ * transformer_module.py:250-378; driven by loss.backward() at ref:scripts/finetune.py:224).  The entry points below
+ * are what the autograd.Function wrappers of cs_vit/autograd.py bind instead.
+ *
+ * csvit_gemm_ex: out[M,N] = (accumulate ? out : 0) + sum_k A(m,k) B(n,k), fp32 accumulation on tcgen05.
+ *   a_mn = 0: A stored [M,K] (pitch lda >= K);  a_mn = 1: A stored [K,M] (pitch lda >= M).  Same for B / N.
+ *   dgrad  dX = dY W      : A = dY [T,out] a_mn=0, B = W [out,in] b_mn=1, M=T, N=in, K=out
+ *   wgrad  dW = dY^T X    : A = dY [T,out] a_mn=1, B = X [T,in]   b_mn=1, M=out, N=in, K=T  (split-K, fp32 red.add)
+ *   in_dtype BF16/F16 (kind::f16, any layout) or F32 (kind::tf32: K-major operands only; exact FMA in any layout
+ *   with impl = CSVIT_GEMM_SIMT_FP32).
+ *   split_k 0 = automatic.  accumulate / split-K need an fp32 output. */
+CSVIT_API int csvit_gemm_ex(const void* A, long long lda, int a_mn, const void* B, long long ldb, int b_mn, int in_dtype, int M,
+                            int N, int K, void* out, long long ldo, int out_dtype, int accumulate, int impl, int split_k,
+                            void* stream);
+
+/* dst[c, r] = src[r, c], fp32 (pitches in elements).  csvit_gemm_ex takes MN-major operands in the 16-bit formats
+ * only; the fp32 (TF32) head transposes its small backward operands with this instead. */
+CSVIT_API int csvit_transpose_f32(const float* src, long long lds, float* dst, long long ldd, int rows, int cols, void* stream);
+
+/* Column reductions over the rows of a[rows, C] (dtype a_dtype, pitch lda), accumulated with atomics into fp32 s1 / s2
+ * (caller zeroes them):
+ *   CSVIT_CR_SUM      s1[c] += sum_r a          bias gradients (colsum of dY)
+ *   CSVIT_CR_CENTERED s1 += sum_r (a - center), s2 += sum_r (a - center)^2     BatchNorm1d batch statistics
+ *   CSVIT_CR_DOT      s1 += sum_r a,            s2 += sum_r a * b              BatchNorm1d backward (b fp32, pitch ldb)
+ * row_mode CSVIT_LN_WINDOW reads row r from token window_index_map(r) (as csvit_layernorm).  If `copy` is non-NULL the
+ * rows are also written out, converted to copy_dtype, in pass order: the fp32 residual gradient becomes a (window-
+ * ordered) 16-bit GEMM operand in the same pass.  s1 / s2 may be NULL for a pure cast / gather. */
+enum { CSVIT_CR_SUM = 0, CSVIT_CR_CENTERED = 1, CSVIT_CR_DOT = 2 };
+CSVIT_API int csvit_col_reduce(const void* a, int a_dtype, long long lda, const float* b, long long ldb, const float* center,
+                               int mode, int rows, int C, int row_mode, int H, int W, int ws, int shift, void* copy,
+                               int copy_dtype, long long ldc, float* s1, float* s2, void* stream);
+
+/* Elementwise, n elements (multiple of 4) of `dtype`:  GELU_FWD out = gelu(a) (exact erf, nn.GELU / HF "gelu");
+ * GELU_BWD out = a * gelu'(b) (a = dY, b = pre-activation);  RELU_BWD out = b > 0 ? a : 0 (b = forward output). */
+enum { CSVIT_EW_GELU_FWD = 0, CSVIT_EW_GELU_BWD = 1, CSVIT_EW_RELU_BWD = 2 };
+CSVIT_API int csvit_eltwise(int op, const void* a, const void* b, void* out, int dtype, long long n, void* stream);
+
+/* out[r,c] = a[c] dy[r,c] + b[c] x[r,c] + c0[c] (+ resid[r,c]), dense fp32 rows: BatchNorm1d backward per channel. */
+CSVIT_API int csvit_affine2_rows(const float* dy, const float* x, const float* a, const float* b, const float* c0,
+                                 const float* resid, float* out, long long rows, int C, void* stream);
+
+/* Backward of csvit_layernorm (same modes and row maps; x is the fp32 input of the forward, dy the gradient of its
+ * output rows in dy_dtype):  dx[map(r)] = (dres ? dres[map(r)] : 0) + dLN;  dgamma / dbeta (fp32, output width) are
+ * accumulated with atomics (caller zeroes them).  dx may alias dres. */
+CSVIT_API int csvit_layernorm_bwd(const float* x, const void* dy, int dy_dtype, long long ldy, const float* gamma, float eps,
+                                  int rows, int C, int mode, int H, int W, int ws, int shift, const float* dres, float* dx,
+                                  float* dgamma, float* dbeta, void* stream);
+
+/* Backward of csvit_attention and of csvit_window_attention (pass q = qkv, k = qkv + C, v = qkv + 2C, pitches 3C,
+ * n_seq = B*nW, Lq = S = ws*ws, scale = 1/sqrt(32), bias = csvit_expand_rel_bias table, mask_* = the window geometry;
+ * mask_shift = 0 disables the shift mask).  Lq, S <= 64, head_dim 32, exact fp32 math, I/O in `dtype`.
+ * dbias [heads, Lq, S] fp32 is accumulated (caller zeroes it); bias / dbias may be NULL. */
+CSVIT_API int csvit_attention_bwd(const void* q, const void* k, const void* v, const void* dout, void* dq, void* dk, void* dv,
+                                  int dtype, long long ldq, long long ldk, long long ldv, long long ldo, long long lddq,
+                                  long long lddk, long long lddv, int n_seq, int Lq, int S, int heads, float scale,
+                                  const float* bias, float* dbias, int mask_H, int mask_W, int mask_ws, int mask_shift,
+                                  void* stream);
 
 #ifdef __cplusplus
 }

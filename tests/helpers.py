@@ -73,3 +73,34 @@ def rel(a, b) -> float:
     a = torch.as_tensor(a).double().cpu()
     b = torch.as_tensor(b).double().cpu()
     return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+def train_manifest():
+    with open(os.path.join(GOLDEN, "TRAIN_MANIFEST.json")) as f:
+        return json.load(f)
+
+
+def build_train_case(name: str, precision: str = "fp32"):
+    """Product ``Poser`` in the golden case's TRAINING phase (as scripts/finetune.py sets it up) + labelled batch + goldens."""
+    from cs_vit.net import Poser
+    from cs_vit.synthetic import make_inputs, randomize_head_
+    from cs_vit.utils.mano_standin import SyntheticMANO
+
+    case = train_manifest()["cases"][name]
+    torch.manual_seed(0)
+    model = Poser(backbone_dir(case["variant"]), image_size=224, mano_layer=SyntheticMANO(), precision=precision, **case["kwargs"])
+    randomize_head_(model, seed=1)
+    batch = make_inputs(case["batch"], case["frames"], 224, seed=11, labels=True)
+    gold = dict(np.load(os.path.join(GOLDEN, name + ".npz")))
+    assert state_checksum(model.state_dict()) == str(gold["state_checksum"]), "seeded weights drifted from the golden run"
+    assert state_checksum(batch) == str(gold["input_checksum"]), "seeded inputs drifted from the golden run"
+    model.phase(Poser.TrainingPhase(case["phase"]))
+    return model, batch, gold, case
+
+
+def grad_projections(g: torch.Tensor, name: str, n_proj: int = 4):
+    """Same seeded +-1 projections as oracle/make_train_goldens.py::projections."""
+    seed = int.from_bytes(name.encode()[-8:].rjust(8, b"\0"), "little") % (2 ** 31 - 1)
+    gen = torch.Generator().manual_seed(seed)
+    signs = torch.randint(0, 2, (n_proj, g.numel()), generator=gen, dtype=torch.int8).float() * 2 - 1
+    return (signs.double() @ g.reshape(-1).double().cpu()).numpy()

@@ -50,8 +50,9 @@ def parse():
     ap.add_argument("--precision", choices=["bf16", "fp16"], default="bf16")
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--variant", default="swin_b")
-    ap.add_argument("--workload", choices=["spatial", "temporal"], default="spatial",
-                    help="spatial = BASELINE configs[1] (headline); temporal = configs[2]: 8-frame clips, realtime cross-frame attention")
+    ap.add_argument("--workload", choices=["spatial", "temporal", "finetune"], default="spatial",
+                    help="spatial = BASELINE configs[1] (headline); temporal = configs[2]: 8-frame clips, realtime cross-frame attention; "
+                         "finetune = configs[3]: forward + backward + AdamW step, batch 32/GPU, gradient allreduce over NCCL")
     ap.add_argument("--frames", type=int, default=8)
     ap.add_argument("--cpu-sample", type=int, default=16, help="images per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -352,10 +353,105 @@ def run_ours(a):
         dist.destroy_process_group()
 
 
+def run_finetune(a):
+    """BASELINE configs[3]: Swin-B spatial finetune step (ref:scripts/finetune.py:211-227), per-GPU batch 32 (the reference's
+    value), data-parallel with the bucketed NCCL gradient allreduce of cs_vit/train.py overlapped with backward."""
+    import torch.distributed as dist
+    from cs_vit import ops
+    from cs_vit.net import Poser
+    from cs_vit.synthetic import make_inputs, make_random_backbone_dir, randomize_head_
+    from cs_vit.train import GradReducer, broadcast_parameters, finetune_step, scaled_lr
+    from cs_vit.utils.mano_standin import SyntheticMANO
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py (impl ours) needs a CUDA device: there is no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    B = a.batch if a.batch != BATCH else 32
+    tmp = tempfile.mkdtemp(prefix=f"csvit_bench_{rank}_")
+    bdir = make_random_backbone_dir(os.path.join(tmp, a.variant), a.variant, seed=0)
+    torch.manual_seed(0)
+    model = Poser(bdir, image_size=224, mano_layer=SyntheticMANO(), spatial_layer_type="encoder", persp_decorate="patch",
+                  precision=a.precision)
+    randomize_head_(model)
+    model.phase(Poser.TrainingPhase.SPATIAL)          # train mode: batch-statistics BatchNorm, trainable spatial modules
+    model = model.to(dev)
+    broadcast_parameters(model)
+    trainable = [p for p in model.parameters() if p.requires_grad]
+    reducer = GradReducer(trainable)
+    opt = torch.optim.AdamW(trainable, lr=scaled_lr(1e-5, world, B), fused=True)
+    batch = {k: v.to(dev) for k, v in make_inputs(B, 1, 224, seed=100 + rank, labels=True).items()}
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    losses = []
+    for _ in range(max(a.warmup, 2)):                  # step 1 also learns the bucket order
+        losses.append(finetune_step(model, batch, opt, reducer).item())
+    sampler = ClockSampler(local) if rank == 0 else None
+    barrier()
+    n0 = ops.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(a.steps):
+        last = finetune_step(model, batch, opt, reducer)
+    e1.record()
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    launches = ops.launch_count - n0
+    # forward / backward split of one more step (events, not part of the timed region)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    reducer.zero_grad()
+    ev[0].record()
+    out = model(batch)
+    ev[1].record()
+    out["loss"].backward()
+    reducer.finish()
+    ev[2].record()
+    torch.cuda.synchronize()
+    nparams = sum(p.numel() for p in trainable)
+    value = world * B * a.steps / (ms.item() / 1e3)
+    peak_tf, _, _ = peaks()
+    res = {
+        "metric": "images/sec Swin-B spatial finetune step (fwd+bwd+AdamW) bs32/GPU", "value": round(value, 1), "unit": "images/s",
+        "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 2), "ms_per_step": round(ms.item() / a.steps, 3),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": a.precision, "data": "synthetic",
+        "config": {"workload": f"{a.variant} spatial model finetune step (Poser.forward loss, backward, grad clip 5.0, fused AdamW), "
+                               f"batch {B}/GPU, 224x224, train-mode BatchNorm", "global_batch": B * world, "parallelism": f"dp{world}",
+                   "allreduce": f"{nparams * 4 / 1e6:.1f} MB fp32 gradients in {len(reducer.bucket_summary())} flat buckets, "
+                                f"async NCCL allreduce launched from grad-ready hooks",
+                   "operands": f"{a.precision} tensor-core operands forward and backward, fp32 accumulate / gradients / optimizer"},
+        "gpu_launches": launches,
+        "model_flops_frac_of_peak": round(3 * value / world * FLOP_PER_IMAGE / (peak_tf * 1e12), 4),
+        "forward_ms": round(ev[0].elapsed_time(ev[1]), 3), "backward_ms": round(ev[1].elapsed_time(ev[2]), 3),
+        "loss_first_last": [round(losses[0], 4), round(last.item(), 4)],
+        "clocks": sampler.window(t0, t1) if sampler else None,
+    }
+    if sampler:
+        sampler.stop()
+    if rank == 0:
+        print(json.dumps(res))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     a = parse()
     if a.impl == "reference":
         run_reference_arm(a)
+    elif a.workload == "finetune":
+        run_finetune(a)
     else:
         run_ours(a)
 

@@ -121,6 +121,40 @@ def pass_reference(workdir: str) -> None:
               f"global grad norm {total:.4e}  full grads stored {n_full}")
         summary[name] = {"variant": variant, "kwargs": kw, "phase": phase, "batch": B, "frames": T, "loss": loss.item(),
                          "params_with_grad": int(sum(has_grad)), "params": len(names), "global_grad_norm": total}
+    # ---- backbone alone under a LINEAR loss <features, R>: the upstream gradient is then identical for every precision mode,
+    # which isolates the tensor-core backward kernels from the chaotic (sqrt(d)-multiplied softmax, quirk Q1) head.
+    for name, variant, B in (("train_backbone_swint_linear", "swin_t", 4),):
+        sd = torch.load(os.path.join(workdir, "train_swint_encoder_patch_spatial.sd.pt"))
+        m = ref_poser.Poser(backbone=os.path.join(workdir, variant), image_size=224, num_latent_layer=None,
+                            spatial_layer_type="encoder", persp_decorate="patch")
+        m.load_state_dict(sd, strict=True)
+        m.phase(ref_poser.Poser.TrainingPhase.SPATIAL)
+        batch = synth.make_inputs(B, 1, 224, seed=11)
+        imgs = batch["patches"].reshape(B, 3, 224, 224)
+        feats = m.backbone(m.image_preprocessor(imgs)).last_hidden_state          # ref:cs_vit/net/ti_poser.py:425-426
+        R = torch.randn(feats.shape, generator=torch.Generator().manual_seed(5))
+        (feats * R).sum().backward()
+        gold = {"features": feats.detach().numpy().astype(np.float32), "loss": np.array((feats * R).sum().item(), dtype=np.float64)}
+        names, norms, projs = [], [], []
+        for pname, p in m.backbone.named_parameters():
+            names.append(pname)
+            g = p.grad.detach().float()
+            norms.append(g.double().norm().item())
+            projs.append(projections(g, pname))
+            if g.numel() <= FULL_GRAD_MAX:
+                gold["grad/" + pname] = g.numpy().astype(np.float32)
+        gold["param_names"] = np.array(names)
+        gold["param_has_grad"] = np.ones(len(names), dtype=bool)
+        gold["grad_norm"] = np.array(norms, dtype=np.float64)
+        gold["grad_proj"] = np.stack(projs).astype(np.float64)
+        gold["state_checksum"] = np.array(state_checksum(sd))
+        gold["input_checksum"] = np.array(state_checksum(batch))
+        np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), **gold)
+        total = float(np.sqrt((gold["grad_norm"] ** 2).sum()))
+        print(f"[reference] {name}: {len(names)} backbone parameters, global grad norm {total:.4e}")
+        summary[name] = {"variant": variant, "kwargs": dict(spatial_layer_type="encoder", persp_decorate="patch"), "phase": "spatial",
+                         "batch": B, "frames": 1, "loss": float(gold["loss"]), "params": len(names), "global_grad_norm": total,
+                         "linear_loss_seed": 5}
     with open(os.path.join(GOLDEN, "TRAIN_MANIFEST.json"), "w") as f:
         json.dump({"generator": "oracle/make_train_goldens.py", "torch": torch.__version__,
                    "transformers": __import__("transformers").__version__, "input_seed": 11, "weight_seed": 0,

@@ -90,7 +90,7 @@ def build_train_case(name: str, precision: str = "fp32"):
     torch.manual_seed(0)
     model = Poser(backbone_dir(case["variant"]), image_size=224, mano_layer=SyntheticMANO(), precision=precision, **case["kwargs"])
     randomize_head_(model, seed=1)
-    batch = make_inputs(case["batch"], case["frames"], 224, seed=11, labels=True)
+    batch = make_inputs(case["batch"], case["frames"], 224, seed=11, labels="linear_loss_seed" not in case)
     gold = dict(np.load(os.path.join(GOLDEN, name + ".npz")))
     assert state_checksum(model.state_dict()) == str(gold["state_checksum"]), "seeded weights drifted from the golden run"
     assert state_checksum(batch) == str(gold["input_checksum"]), "seeded inputs drifted from the golden run"

@@ -100,3 +100,92 @@ def test_single_process_gather_without_init():
     r = _results(3, 1)
     merged, paths = gather_eval_results(r, ["a", "b/c.jpg", "d"])
     assert paths == ["a", "b/c.jpg", "d"] and torch.equal(merged["joint_reproj_pred"], r["joint_reproj_pred"])
+
+
+# ------------------------------------------------------------------------------------------------ finetune-step reduction
+class _Toy(torch.nn.Module):
+    """Stand-in with the structural features the reducer must cope with: a parameter that never gets a gradient (the
+    discarded head layers, quirk Q2), a frozen parameter, and parameters of very different sizes."""
+
+    def __init__(self):
+        super().__init__()
+        g = torch.Generator().manual_seed(3)
+        self.a = torch.nn.Linear(16, 64)
+        self.b = torch.nn.Linear(64, 64)
+        self.unused = torch.nn.Linear(64, 64)
+        self.frozen = torch.nn.Linear(64, 8)
+        self.c = torch.nn.Linear(64, 4)
+        for p in self.parameters():
+            with torch.no_grad():
+                p.copy_(torch.randn(p.shape, generator=g) * 0.1)
+        self.frozen.requires_grad_(False)
+
+    def forward(self, batch):
+        h = torch.tanh(self.b(torch.relu(self.a(batch["x"]))))
+        return {"loss": ((self.c(h) - batch["y"]) ** 2).mean() + self.frozen(h).mean()}
+
+
+def _toy_data(n):
+    g = torch.Generator().manual_seed(17)
+    return {"x": torch.randn(n, 16, generator=g), "y": torch.randn(n, 4, generator=g)}
+
+
+def _reduce_worker(rank, world, port, q):
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "cs-vit_b200"))
+    from cs_vit.train import GradReducer, broadcast_parameters, finetune_step, scaled_lr
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.manual_seed(100 + rank)            # ranks start from different weights ...
+        model = _Toy()
+        with torch.no_grad():
+            model.a.weight.add_(rank)
+        broadcast_parameters(model)               # ... and must leave with rank 0's (DDP constructor semantics, C1)
+        ref = _Toy()
+        assert all(torch.equal(p, r) for p, r in zip(model.parameters(), ref.parameters()))
+        data = _toy_data(8)
+        per = 8 // world
+        mine = {k: v[rank * per:(rank + 1) * per] for k, v in data.items()}
+        reducer = GradReducer(model.parameters(), bucket_bytes=8 << 10)     # small buckets -> several of them
+        opt = torch.optim.SGD([p for p in model.parameters() if p.requires_grad], lr=scaled_lr(0.05, world, per))
+        ropt = torch.optim.SGD([p for p in ref.parameters() if p.requires_grad], lr=scaled_lr(0.05, world, per))
+        for step in range(3):                     # step 1 learns the bucket order, steps 2-3 use the overlapped hooks
+            finetune_step(model, mine, opt, reducer, max_norm=1e9)
+            # single-process truth: mean over ranks of the per-rank mean loss == loss over the whole batch here
+            ropt.zero_grad(set_to_none=True)
+            ref(data)["loss"].backward()
+            for (n, p), r in zip(model.named_parameters(), ref.parameters()):
+                if r.grad is None:
+                    assert p.grad is None, n
+                else:
+                    assert torch.allclose(p.grad, r.grad, rtol=1e-5, atol=1e-7), (step, n)
+            ropt.step()
+            for p, r in zip(model.parameters(), ref.parameters()):
+                assert torch.allclose(p, r, rtol=1e-5, atol=1e-7)
+        assert len(reducer.bucket_summary()) >= 2
+        assert model.unused.weight.grad is None and model.frozen.weight.grad is None
+        q.put((rank, "ok"))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_grad_reducer_world2_matches_full_batch():
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_reduce_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert sorted(q.get(timeout=5)[0] for _ in range(world)) == [0, 1]
+
+
+def test_scaled_lr_rule():
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "cs-vit_b200"))
+    from cs_vit.train import scaled_lr
+    assert abs(scaled_lr(1e-4, 8, 32) - (8 * 32 / 44) ** 0.5 * 1e-4) < 1e-12      # ref:scripts/finetune.py:138-139
+    assert scaled_lr(1e-4, 1, 44) == 1e-4

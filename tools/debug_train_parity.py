@@ -31,8 +31,9 @@ for i, n in enumerate(names):
     else:
         e = float(np.sqrt(np.mean((grad_projections(g.detach(), n) - gold["grad_proj"][i]) ** 2))); kind = "proj"
     rows.append((e / max(gold["grad_norm"][i], 1e-12), n, f"{kind} norm {g.norm().item():.4e} ref {gold['grad_norm'][i]:.4e}"))
+rows = [r for r in rows if not (r[1].endswith("key.bias") or r[1] == "perspective_mlp.proj.bias")]
 rows.sort(reverse=True)
-for r in rows[:40]: print(f"{r[0]:.3e}  {r[1]}  {r[2]}")
+for r in rows[:int(os.environ.get("TOPN", "40"))]: print(f"{r[0]:.3e}  {r[1]}  {r[2]}")
 print("...")
 for r in rows[-5:]: print(f"{r[0]:.3e}  {r[1]}  {r[2]}")
 print("median", np.median([r[0] for r in rows]))

@@ -403,6 +403,7 @@ def run_finetune(a):
     e0.record()
     for _ in range(a.steps):
         last = finetune_step(model, batch, opt, reducer)
+        losses.append(last)
     e1.record()
     torch.cuda.synchronize()
     t1 = time.perf_counter()
@@ -435,7 +436,7 @@ def run_finetune(a):
         "gpu_launches": launches,
         "model_flops_frac_of_peak": round(3 * value / world * FLOP_PER_IMAGE / (peak_tf * 1e12), 4),
         "forward_ms": round(ev[0].elapsed_time(ev[1]), 3), "backward_ms": round(ev[1].elapsed_time(ev[2]), 3),
-        "loss_first_last": [round(losses[0], 4), round(last.item(), 4)],
+        "losses": [round(float(x), 3) for x in losses],
         "clocks": sampler.window(t0, t1) if sampler else None,
     }
     if sampler:

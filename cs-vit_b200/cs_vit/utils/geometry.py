@@ -18,6 +18,14 @@ def rotation_6d_to_matrix(d6: torch.Tensor) -> torch.Tensor:
     return torch.stack((b1, b2, torch.linalg.cross(b1, b2, dim=-1)), dim=-2)
 
 
+def _sqrt_positive_part(x: torch.Tensor) -> torch.Tensor:
+    """``sqrt(max(0, x))`` with a ZERO subgradient where ``x <= 0`` (ref :150-161).  ``sqrt(clamp(x, 0))`` is the same value but
+    its backward is ``inf * 0 = NaN`` at a clamped entry, which poisons every gradient of a training step."""
+    positive = x > 0
+    safe = torch.where(positive, x, torch.ones_like(x))
+    return torch.where(positive, torch.sqrt(safe), torch.zeros_like(x))
+
+
 def matrix_to_quaternion(matrix: torch.Tensor) -> torch.Tensor:
     """Rotation matrices ``(...,3,3)`` -> quaternions ``(...,4)``, real part first and >= 0   (ref :164-223, :135-147)."""
     if matrix.size(-1) != 3 or matrix.size(-2) != 3:
@@ -25,7 +33,7 @@ def matrix_to_quaternion(matrix: torch.Tensor) -> torch.Tensor:
     m = matrix
     d0, d1, d2 = m[..., 0, 0], m[..., 1, 1], m[..., 2, 2]
     sq = torch.stack([1 + d0 + d1 + d2, 1 + d0 - d1 - d2, 1 - d0 + d1 - d2, 1 - d0 - d1 + d2], dim=-1)
-    q_abs = torch.sqrt(sq.clamp_min(0.0))
+    q_abs = _sqrt_positive_part(sq)
     a, b, c = m[..., 2, 1] - m[..., 1, 2], m[..., 0, 2] - m[..., 2, 0], m[..., 1, 0] - m[..., 0, 1]
     e, f, g = m[..., 1, 0] + m[..., 0, 1], m[..., 0, 2] + m[..., 2, 0], m[..., 1, 2] + m[..., 2, 1]
     q2 = q_abs ** 2

@@ -93,3 +93,18 @@ def test_q2_only_last_encoder_layer_matters():
     with torch.no_grad():
         out = head.predict_batch(inputs, sd, head_options(case), SyntheticMANO(), execute_all=True)
     assert rel(out["joint_cam"], gold["joint_cam"]) < 2e-5
+
+
+def test_rotation_tail_backward_is_finite_at_clamped_entries():
+    """matrix_to_quaternion takes sqrt of four terms that are exactly 0 (or round-off negative) for rotations whose quaternion
+    has a zero component; the reference gives them a zero subgradient (ref:cs_vit/utils/geometry.py:150-161).  A NaN there
+    poisons every gradient of the finetune step through clip_grad_norm_."""
+    from cs_vit.utils.geometry import matrix_to_axis_angle, rotation_6d_to_matrix
+    R = torch.stack([torch.diag(torch.tensor([1.0, -1.0, -1.0])), torch.eye(3), torch.diag(torch.tensor([-1.0, 1.0, -1.0]))])
+    R = R.clone().requires_grad_(True)
+    aa = matrix_to_axis_angle(R)
+    aa.square().sum().backward()
+    assert torch.isfinite(aa).all() and torch.isfinite(R.grad).all()
+    d6 = torch.tensor([[1.0, 0.0, 0.0, 0.0, 1.0, 0.0], [0.3, -0.2, 0.9, 0.1, 0.8, -0.5]], requires_grad=True)
+    matrix_to_axis_angle(rotation_6d_to_matrix(d6)).sum().backward()
+    assert torch.isfinite(d6.grad).all()

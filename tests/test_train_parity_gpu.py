@@ -95,7 +95,7 @@ def test_finetune_step_fp32(name, tol_out, tol_param, tol_global):
         if "spatial_encoder.layers." in k and model.spatial_layer_type == "encoder" and ".layers.5." not in k:
             continue   # the reference also runs the five discarded layers (quirk Q2); the product skips them
         ref = torch.from_numpy(gold["bn/" + k])
-        assert torch.allclose(sd[k].cpu(), ref, rtol=1e-4, atol=1e-5), k
+        assert torch.allclose(sd[k].cpu(), ref, rtol=10 * tol_out, atol=tol_out), k
         checked += 1
     assert checked > 0
 

@@ -62,34 +62,40 @@ class SwinBlockFn(Function):
         C = x.shape[1]
         f32 = torch.float32
         g2 = _c(g2)
+        L = ws * ws
+        nW = (H // ws) * (W // ws)
+        # every small fp32 accumulator of this block (bias / LayerNorm / bias-table gradients) is a slice of ONE zero-filled
+        # workspace: one fill kernel instead of twelve
+        sizes = [C, 4 * C, C, C, C, 3 * C, C, C, heads * L * L, pk["table_rows"] * heads]
+        wsp = torch.zeros(sum(sizes), dtype=f32, device=x.device)
+        zb2, zb1, zl2w, zl2b, zbo, zbqkv, zl1w, zl1b, zdbias, zdtable = torch.split(wsp, sizes)
         # MLP half:  x2 = x1 + fc2(gelu(fc1(LN2(x1))))
-        db2, _, g2c = ops.col_reduce(g2, copy_dtype=act)
+        db2, _, g2c = ops.col_reduce(g2, copy_dtype=act, s1=zb2)
         dw2 = ops.gemm_ex(g2c, True, a, True, out_dtype=f32, impl=impl)
         da = ops.gemm_ex(g2c, False, pk["w2"], True, out_dtype=act, impl=impl)
         dh = ops.eltwise(ops.EW_GELU_BWD, da, h)
         del da
-        db1, _, _ = ops.col_reduce(dh)
+        db1, _, _ = ops.col_reduce(dh, s1=zb1)
         dw1 = ops.gemm_ex(dh, True, xn2, True, out_dtype=f32, impl=impl)
         dxn2 = ops.gemm_ex(dh, False, pk["w1"], True, out_dtype=act, impl=impl)
         del dh
-        g1, dln2w, dln2b = ops.layernorm_bwd(x1, dxn2, ln2w, eps, dres=g2)
+        g1, dln2w, dln2b = ops.layernorm_bwd(x1, dxn2, ln2w, eps, dres=g2, dgamma=zl2w, dbeta=zl2b)
         # attention half:  x1[token(r)] = x[token(r)] + proj(attn(qkv(LN1(x)[token(r)])))   (r = window-ordered row)
-        dbo, _, g1w = ops.col_reduce(g1, window=(H, W, ws, shift), copy_dtype=act)
+        dbo, _, g1w = ops.col_reduce(g1, window=(H, W, ws, shift), copy_dtype=act, s1=zbo)
         dwo = ops.gemm_ex(g1w, True, att, True, out_dtype=f32, impl=impl)
         datt = ops.gemm_ex(g1w, False, pk["wo"], True, out_dtype=act, impl=impl)
-        L = ws * ws
-        nW = (H // ws) * (W // ws)
         dqkv = torch.empty_like(qkv)
         _, _, _, dbias = ops.attention_bwd(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], datt, B * nW, L, L, heads, 1.0 / math.sqrt(32.0),
                                            bias=pk["bias"], mask=(H, W, ws, shift), dq=dqkv[:, :C], dk=dqkv[:, C:2 * C],
-                                           dv=dqkv[:, 2 * C:])
+                                           dv=dqkv[:, 2 * C:], dbias=zdbias.view(heads, L, L))
         # bias[h,i,j] = table[index[i,j], h]  (HF:428-434): scatter-add of a [h,49,49] tensor into [169,h]
-        dtable = torch.zeros(pk["table_rows"], heads, dtype=f32, device=x.device)
+        dtable = zdtable.view(pk["table_rows"], heads)
         dtable.index_add_(0, pk["rel_index"], dbias.reshape(heads, L * L).t())
-        dbqkv, _, _ = ops.col_reduce(dqkv)
+        dbqkv, _, _ = ops.col_reduce(dqkv, s1=zbqkv)
         dwqkv = ops.gemm_ex(dqkv, True, xn1, True, out_dtype=f32, impl=impl)
         dxn1 = ops.gemm_ex(dqkv, False, pk["wqkv"], True, out_dtype=act, impl=impl)
-        g0, dln1w, dln1b = ops.layernorm_bwd(x, dxn1, ln1w, eps, mode=ops.LN_WINDOW, grid=(H, W), ws=ws, shift=shift, dres=g1)
+        g0, dln1w, dln1b = ops.layernorm_bwd(x, dxn1, ln1w, eps, mode=ops.LN_WINDOW, grid=(H, W), ws=ws, shift=shift, dres=g1,
+                                               dgamma=zl1w, dbeta=zl1b)
         return (g0, dln1w, dln1b, dwqkv[:C], dbqkv[:C], dwqkv[C:2 * C], dbqkv[C:2 * C], dwqkv[2 * C:], dbqkv[2 * C:], dtable,
                 dwo, dbo, dln2w, dln2b, dw1, db1, dw2, db2, None, None)
 

@@ -234,10 +234,8 @@ class SwinBackboneB200(nn.Module):
         n, _, S, S2 = images.shape
         if S != S2 or S % (32 * cfg.window_size) != 0:
             raise ValueError(f"image side {S} must be a multiple of {32 * cfg.window_size} (no padding path, SURVEY.md §8b)")
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            if return_stages:
-                raise ValueError("return_stages is an inference-path diagnostic")
-            return self._forward_train(images, normalize)
+        if not return_stages and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            return self._forward_train(images, normalize)    # (return_stages is a diagnostic of the inference path)
         with torch.no_grad():
             return self._forward_infer(images, normalize, return_stages)
 

@@ -328,12 +328,14 @@ def transpose(x: torch.Tensor) -> torch.Tensor:
 
 
 def col_reduce(a: torch.Tensor, mode: int = CR_SUM, *, b: Optional[torch.Tensor] = None, center: Optional[torch.Tensor] = None,
-               window: Optional[Tuple[int, int, int, int]] = None, copy_dtype: Optional[torch.dtype] = None, sums: bool = True):
+               window: Optional[Tuple[int, int, int, int]] = None, copy_dtype: Optional[torch.dtype] = None, sums: bool = True,
+               s1: Optional[torch.Tensor] = None):
     """Column sums of ``a [rows, C]`` (+ second moment / dot, see ``csvit_col_reduce``) and, with ``copy_dtype``, a converted
     (optionally window-gathered) copy of the rows.  Returns ``(s1, s2, copy)`` with ``None`` for the parts not requested."""
     _dev(a, b, center)
     rows, C, lda = _rows2d(a)
-    s1 = torch.zeros(C, dtype=torch.float32, device=a.device) if sums else None
+    if s1 is None:          # a caller-provided s1 must already be zeroed (slices of one zero-filled workspace save launches)
+        s1 = torch.zeros(C, dtype=torch.float32, device=a.device) if sums else None
     s2 = torch.zeros(C, dtype=torch.float32, device=a.device) if sums and mode != CR_SUM else None
     copy = torch.empty(rows, C, dtype=copy_dtype, device=a.device) if copy_dtype is not None else None
     ldb = 0
@@ -372,7 +374,8 @@ def affine2_rows(dy: torch.Tensor, x: torch.Tensor, a: torch.Tensor, b: torch.Te
 
 
 def layernorm_bwd(x: torch.Tensor, dy: torch.Tensor, gamma: torch.Tensor, eps: float, *, mode: int = LN_IDENTITY,
-                  grid: Tuple[int, int] = (0, 0), ws: int = 0, shift: int = 0, dres: Optional[torch.Tensor] = None):
+                  grid: Tuple[int, int] = (0, 0), ws: int = 0, shift: int = 0, dres: Optional[torch.Tensor] = None,
+                  dgamma: Optional[torch.Tensor] = None, dbeta: Optional[torch.Tensor] = None):
     """Backward of ``layernorm``: returns ``(dx [rows_in, C] fp32 = dres + dLN, dgamma, dbeta)``."""
     _dev(x, dy, gamma, dres)
     if x.dtype != torch.float32 or not x.is_contiguous():
@@ -384,8 +387,9 @@ def layernorm_bwd(x: torch.Tensor, dy: torch.Tensor, gamma: torch.Tensor, eps: f
     if dres is not None and (dres.dtype != torch.float32 or dres.shape != x.shape or not dres.is_contiguous()):
         raise ValueError("layernorm_bwd: dres must be contiguous float32 of x's shape")
     dx = torch.empty_like(x)
-    dgamma = torch.zeros(width, dtype=torch.float32, device=x.device)
-    dbeta = torch.zeros(width, dtype=torch.float32, device=x.device)
+    if dgamma is None:      # caller-provided accumulators must already be zeroed
+        dgamma = torch.zeros(width, dtype=torch.float32, device=x.device)
+        dbeta = torch.zeros(width, dtype=torch.float32, device=x.device)
     H, W = grid
     _call("csvit_layernorm_bwd", x.data_ptr(), dy.data_ptr(), _code(dy.dtype), ldy, gamma.data_ptr(), float(eps), rows, C, mode, H, W,
           ws, shift, _p(dres), dx.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), _stream())
@@ -394,7 +398,8 @@ def layernorm_bwd(x: torch.Tensor, dy: torch.Tensor, gamma: torch.Tensor, eps: f
 
 def attention_bwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, dout: torch.Tensor, n_seq: int, Lq: int, S: int, heads: int,
                   scale: float, *, bias: Optional[torch.Tensor] = None, mask: Optional[Tuple[int, int, int, int]] = None,
-                  dq: Optional[torch.Tensor] = None, dk: Optional[torch.Tensor] = None, dv: Optional[torch.Tensor] = None):
+                  dq: Optional[torch.Tensor] = None, dk: Optional[torch.Tensor] = None, dv: Optional[torch.Tensor] = None,
+                  dbias: Optional[torch.Tensor] = None):
     """Backward of ``attention`` / ``window_attention``.  q/k/v/dout (and dq/dk/dv when given) may be column slices.
     Returns ``(dq, dk, dv, dbias or None)``."""
     _dev(q, k, v, dout, bias, dq, dk, dv)
@@ -406,7 +411,8 @@ def attention_bwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, dout: torch
     dq = torch.empty(rq, D, dtype=q.dtype, device=q.device) if dq is None else dq
     dk = torch.empty(rk, D, dtype=q.dtype, device=q.device) if dk is None else dk
     dv = torch.empty(rk, D, dtype=q.dtype, device=q.device) if dv is None else dv
-    dbias = torch.zeros(heads, Lq, S, dtype=torch.float32, device=q.device) if bias is not None else None
+    if dbias is None and bias is not None:   # a caller-provided dbias must already be zeroed
+        dbias = torch.zeros(heads, Lq, S, dtype=torch.float32, device=q.device)
     mH, mW, mws, msh = mask if mask is not None else (0, 0, 0, 0)
     _call("csvit_attention_bwd", q.data_ptr(), k.data_ptr(), v.data_ptr(), dout.data_ptr(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(),
           _code(q.dtype), ldq, ldk, ldv, ldo, dq.stride(0), dk.stride(0), dv.stride(0), n_seq, Lq, S, heads, float(scale),

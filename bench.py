@@ -57,6 +57,7 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=16, help="images per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip roofline / e2e / fp16 passes (debug)")
+    ap.add_argument("--micro-batch", type=int, default=-1, help="images per backbone pass (L2-resident chunks); -1 = library default, 0 = whole batch")
     ap.add_argument("--no-graph", action="store_true", help="launch kernels one by one instead of replaying a CUDA graph")
     return ap.parse_args()
 
@@ -201,6 +202,8 @@ def run_ours(a):
     model.phase(Poser.TrainingPhase.INFERENCE if temporal else Poser.TrainingPhase.SPATIAL)
     model.eval()
     model = model.to(dev)
+    if a.micro_batch >= 0:
+        model.backbone.micro_batch = a.micro_batch
 
     host = make_inputs(clips, T, 224, seed=100 + rank)
     keys = ("patches", "square_bboxes", "timestamp", "focal", "princpt")

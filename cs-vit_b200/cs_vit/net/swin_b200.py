@@ -112,6 +112,11 @@ class SwinBackboneB200(nn.Module):
         # overlapped with the MMAs), so it is opt-in until the A tile can be double-buffered.
         self.fuse_ln = False
         self.fuse_mlp = True   # csvit_mlp_fused for C in {128, 256}: hidden activations never leave the SM
+        # Inference runs the batch through the whole backbone in chunks of this many images (0 = all at once).  Images are
+        # independent, so the result is bit-identical; what changes is locality: a chunk's inter-kernel tensors (tens of MB)
+        # stay resident in the 126 MB L2 between the kernel that writes them and the one that reads them, instead of making
+        # a round trip through HBM as the 100-800 MB tensors of a 256-image batch do (profiles/r1_micro_batch_sweep.txt).
+        self.micro_batch = 0
         c0, eps, ws = config.embed_dim, config.layer_norm_eps, config.window_size
         self.embeddings = _holder(
             patch_embeddings=_holder(projection=nn.Conv2d(3, c0, kernel_size=4, stride=4)),
@@ -293,9 +298,16 @@ class SwinBackboneB200(nn.Module):
         out = ag.LayerNormFn.apply(x, self.layernorm.weight, self.layernorm.bias, eps)
         return out.view(n, H * W, cfg.hidden_size)
 
-    def _forward_infer(self, images: torch.Tensor, normalize: bool, return_stages: bool = False):
+    def _forward_infer(self, images: torch.Tensor, normalize: bool, return_stages: bool = False, out: Optional[torch.Tensor] = None):
         cfg = self.config
         n, _, S, _ = images.shape
+        mb = self.micro_batch
+        if mb and n > mb and not return_stages:
+            images = images.float().contiguous()
+            full = torch.empty(n, (S // 32) ** 2, cfg.hidden_size, dtype=torch.float32, device=images.device)
+            for lo in range(0, n, mb):
+                self._forward_infer(images[lo:lo + mb], normalize, out=full[lo:lo + mb])
+            return full
         act = self._act_dtype
         impl = ops.GEMM_SIMT if self._fp32 else ops.GEMM_TC
         eps = cfg.layer_norm_eps
@@ -317,7 +329,8 @@ class SwinBackboneB200(nn.Module):
                                    out_dtype=act, mode=ops.LN_MERGE2X2, grid=(H, W))
                 x = ops.linear(xm, self._weight(f"s{s}/dsr", ds.reduction.weight), None, out_dtype=torch.float32, impl=impl)
                 H, W = H // 2, W // 2
-        out = ops.layernorm(x, self._f32("final_w", self.layernorm.weight), self._f32("final_b", self.layernorm.bias), eps)
+        out = ops.layernorm(x, self._f32("final_w", self.layernorm.weight), self._f32("final_b", self.layernorm.bias), eps,
+                            out=None if out is None else out.view(n * H * W, cfg.hidden_size))
         out = out.view(n, H * W, cfg.hidden_size)
         return (out, stages) if return_stages else out
 

@@ -62,7 +62,7 @@ class SpatialEncoder(_KernelModule):
         # "encoder": the reference feeds the SAME embedded input to every layer and returns the last layer's
         # output (ref :94-97, typo ``x_embeb``), so only layers[-1] contributes to the result.
         z = self.pe_spatial(torch.cat([x, ctx], dim=1))
-        return self.layers[-1](z)[:, : x.shape[1]]
+        return self.layers[-1].forward_queries(z, x.shape[1])
 
 
 class TemporalEncoder(_KernelModule):

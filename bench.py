@@ -364,7 +364,7 @@ def run_finetune(a):
     from cs_vit import ops
     from cs_vit.net import Poser
     from cs_vit.synthetic import make_inputs, make_random_backbone_dir, randomize_head_
-    from cs_vit.train import GradReducer, broadcast_parameters, finetune_step, scaled_lr
+    from cs_vit.train import GradReducer, GraphedFinetuneStep, broadcast_parameters, finetune_step, scaled_lr
     from cs_vit.utils.mano_standin import SyntheticMANO
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -388,7 +388,8 @@ def run_finetune(a):
     broadcast_parameters(model)
     trainable = [p for p in model.parameters() if p.requires_grad]
     reducer = GradReducer(trainable)
-    opt = torch.optim.AdamW(trainable, lr=scaled_lr(1e-5, world, B), fused=True)
+    graphed = not a.no_graph
+    opt = torch.optim.AdamW(trainable, lr=scaled_lr(1e-5, world, B), fused=True, capturable=graphed)
     batch = {k: v.to(dev) for k, v in make_inputs(B, 1, 224, seed=100 + rank, labels=True).items()}
 
     def barrier():
@@ -397,8 +398,13 @@ def run_finetune(a):
         torch.cuda.synchronize()
 
     losses = []
-    for _ in range(max(a.warmup, 2)):                  # step 1 also learns the bucket order
-        losses.append(finetune_step(model, batch, opt, reducer).item())
+    if graphed:      # the whole step (forward, loss, backward, reduction, clip, AdamW) replayed as one CUDA graph
+        gstep = GraphedFinetuneStep(model, batch, opt, reducer, warmup=max(a.warmup, 2))
+        run_step = lambda: gstep(batch).clone()      # noqa: E731
+    else:
+        run_step = lambda: finetune_step(model, batch, opt, reducer)      # noqa: E731
+        for _ in range(max(a.warmup, 2)):              # step 1 also learns the bucket order
+            losses.append(run_step().item())
     sampler = ClockSampler(local) if rank == 0 else None
     barrier()
     n0 = ops.launch_count
@@ -406,7 +412,7 @@ def run_finetune(a):
     t0 = time.perf_counter()
     e0.record()
     for _ in range(a.steps):
-        last = finetune_step(model, batch, opt, reducer)
+        last = run_step()
         losses.append(last)
     e1.record()
     torch.cuda.synchronize()
@@ -415,13 +421,18 @@ def run_finetune(a):
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     launches = ops.launch_count - n0
-    # forward / backward split of one more step (events, not part of the timed region)
+    # forward / backward split of one more (eager) step (events, not part of the timed region)
+    from cs_vit.train import invalidate_packs
+    invalidate_packs(model)
+    reducer.zero_grad()
+    model.loss_tensors(batch)[0].backward()      # untimed: re-packs the weights for the eager path
+    reducer.finish()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
     reducer.zero_grad()
     ev[0].record()
-    out = model(batch)
+    eager_loss, _, _ = model.loss_tensors(batch)
     ev[1].record()
-    out["loss"].backward()
+    eager_loss.backward()
     reducer.finish()
     ev[2].record()
     torch.cuda.synchronize()
@@ -432,14 +443,15 @@ def run_finetune(a):
         "metric": "images/sec Swin-B spatial finetune step (fwd+bwd+AdamW) bs32/GPU", "value": round(value, 1), "unit": "images/s",
         "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 2), "ms_per_step": round(ms.item() / a.steps, 3),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": a.precision, "data": "synthetic",
-        "config": {"workload": f"{a.variant} spatial model finetune step (Poser.forward loss, backward, grad clip 5.0, fused AdamW), "
+        "config": {"launch": "one CUDA graph per step (cs_vit.train.GraphedFinetuneStep)" if graphed else "eager",
+                   "workload": f"{a.variant} spatial model finetune step (Poser.forward loss, backward, grad clip 5.0, fused AdamW), "
                                f"batch {B}/GPU, 224x224, train-mode BatchNorm", "global_batch": B * world, "parallelism": f"dp{world}",
                    "allreduce": f"{nparams * 4 / 1e6:.1f} MB fp32 gradients in {len(reducer.bucket_summary())} flat buckets, "
                                 f"async NCCL allreduce launched from grad-ready hooks",
                    "operands": f"{a.precision} tensor-core operands forward and backward, fp32 accumulate / gradients / optimizer"},
         "gpu_launches": launches,
         "model_flops_frac_of_peak": round(3 * value / world * FLOP_PER_IMAGE / (peak_tf * 1e12), 4),
-        "forward_ms": round(ev[0].elapsed_time(ev[1]), 3), "backward_ms": round(ev[1].elapsed_time(ev[2]), 3),
+        "eager_forward_ms": round(ev[0].elapsed_time(ev[1]), 3), "eager_backward_ms": round(ev[1].elapsed_time(ev[2]), 3),
         "losses": [round(float(x), 3) for x in losses],
         "clocks": sampler.window(t0, t1) if sampler else None,
     }

@@ -354,10 +354,12 @@ class Poser(nn.Module):
         return {"joint_cam": joint_cam, "verts_cam": verts_cam, "pose_aa": pose_aa, "shape": shape,
                 "root_transl_norm": root_transl_norm, "root_transl": root_transl}
 
-    def _criterion(self, predict, batch):
-        """ref:cs_vit/net/ti_poser.py:724-778."""
+    def _criterion(self, predict, batch, host_logs: bool = True):
+        """ref:cs_vit/net/ti_poser.py:724-778.  ``host_logs=False`` returns the five components as one device tensor instead of
+        Python floats: no device->host sync, so the step can be captured in a CUDA graph (``cs_vit.train.GraphedFinetuneStep``)."""
         T = predict["joint_cam"].shape[1]
-        idx = list(range(T)) if self.temporal_supervision != "realtime" else [-1]
+        # slices, not index lists: an index list becomes a host tensor + H2D copy, which cannot be captured in a CUDA graph
+        idx = slice(None) if self.temporal_supervision != "realtime" else slice(T - 1, T)
         pj, gj, valid = predict["joint_cam"][:, idx], batch["joint_cam"][:, idx], batch["joint_valid"][:, idx]
         loss_cam = torch.mean((pj - gj).norm(dim=-1) * valid)
         loss_rel = torch.mean(((pj - pj[:, :, :1]) - (gj - gj[:, :, :1])).norm(dim=-1) * valid)
@@ -371,9 +373,18 @@ class Poser(nn.Module):
             loss_accel = (ap - ag).norm(dim=-1).mean()
             loss_temporal = 1e-2 * (loss_vel + loss_accel)
         # one device->host transfer for all five scalars instead of five .item() syncs
-        vals = torch.stack([loss_cam, loss_rel, loss_shape, loss_vel, loss_accel]).tolist()
-        logs = dict(zip(("cam", "rel", "shape", "loss_vel", "loss_accel"), vals))
+        parts = torch.stack([loss_cam, loss_rel, loss_shape, loss_vel, loss_accel])
+        if not host_logs:
+            return loss_cam + loss_rel + loss_shape + loss_temporal, parts.detach()
+        logs = dict(zip(("cam", "rel", "shape", "loss_vel", "loss_accel"), parts.tolist()))
         return loss_cam + loss_rel + loss_shape + loss_temporal, logs
+
+    def loss_tensors(self, batch):
+        """``predict_batch`` + ``_criterion`` without any host synchronisation: ``(loss, parts[5], predict)``, all on the device."""
+        predict = self.predict_batch(img_tensor=batch["patches"], square_bboxes=batch["square_bboxes"],
+                                     timestamp=batch["timestamp"], focal=batch["focal"], princpt=batch["princpt"])
+        loss, parts = self._criterion(predict, batch, host_logs=False)
+        return loss, parts, predict
 
     def _vis(self, predict, batch):
         """Reprojection overlay for TensorBoard (ref:cs_vit/net/ti_poser.py:780-813).  Host-side cv2 drawing is

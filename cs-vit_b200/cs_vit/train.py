@@ -3,9 +3,9 @@ reduction (DDP's bucketed allreduce, ref:scripts/finetune.py:133-135; SURVEY.md 
 
 ``GradReducer`` is the NVLink-era replacement for ``DistributedDataParallel(find_unused_parameters=True)`` on this path:
 
-* gradients live as views into a few large flat fp32 buckets (default 64 MB: on NVSwitch the allreduce cost is launch
-  latency + bytes / 900 GB/s, not per-link hops, so few large buckets beat DDP's 25 MB default), so there is no
-  flatten / unflatten copy;
+* gradients are gathered into a few large flat fp32 buckets (default 64 MB: on NVSwitch the allreduce cost is launch
+  latency + bytes / 900 GB/s, not per-link hops, so few large buckets beat DDP's 25 MB default) with one multi-tensor copy
+  per bucket, and the optimizer reads them back as views - no per-parameter accumulate or unflatten kernels;
 * a bucket's ``all_reduce(SUM)`` is launched asynchronously from the post-accumulate-grad hook of its last parameter, i.e.
   overlapped with the rest of the backward pass (buckets are ordered by reverse gradient-ready order, learned on step 1);
 * parameters that never receive a gradient (the five discarded "encoder" head layers, quirk Q2; frozen phases) are left
@@ -51,13 +51,24 @@ class GradReducer:
                 return                      # did not get a gradient on the first step: not bucketed (reduced in finish())
             bucket = self._buckets[b]
             bucket["pending"] -= 1
-            if bucket["pending"] == 0 and self.world > 1:
-                self._handles.append(dist.all_reduce(bucket["flat"], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+            if bucket["pending"] == 0:
+                self._flush(bucket)
         return hook
 
+    def _flush(self, bucket: dict) -> None:
+        """All gradients of the bucket are ready: gather them into the flat buffer with ONE multi-tensor copy (instead of one
+        accumulate kernel per parameter) and start the bucket's allreduce."""
+        have = [(v, self.params[i].grad) for v, i in zip(bucket["views"], bucket["idxs"]) if self.params[i].grad is not None]
+        if len(have) < len(bucket["idxs"]):
+            bucket["flat"].zero_()
+        if have:
+            torch._foreach_copy_([v for v, _ in have], [g for _, g in have])
+        bucket["flushed"] = True
+        if self.world > 1:
+            self._handles.append(dist.all_reduce(bucket["flat"], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+
     def _build(self) -> None:
-        """After the first backward: bucket the parameters that received gradients, in ready order, and re-point their
-        ``.grad`` at views of the flat buffers (the values of this first step are carried over)."""
+        """After the first backward: bucket the parameters that received gradients, in gradient-ready order."""
         buckets, cur, cur_bytes = [], [], 0
         for i in self._order:
             p = self.params[i]
@@ -73,47 +84,42 @@ class GradReducer:
         for b, idxs in enumerate(buckets):
             dev = self.params[idxs[0]].device
             flat = torch.zeros(sum(self.params[i].numel() for i in idxs), dtype=torch.float32, device=dev)
-            off = 0
+            views, off = [], 0
             for i in idxs:
                 p = self.params[i]
-                view = flat[off:off + p.numel()].view_as(p)
-                view.copy_(p.grad)
-                p.grad = view
+                views.append(flat[off:off + p.numel()].view_as(p))
                 off += p.numel()
                 self._bucket_of[i] = b
-            self._buckets.append({"flat": flat, "idxs": idxs, "pending": len(idxs)})
+            self._buckets.append({"flat": flat, "idxs": idxs, "views": views, "pending": len(idxs), "flushed": False})
 
     # ------------------------------------------------------------------------------------------ per-step API
     def zero_grad(self) -> None:
-        """Zero the flat buckets (``.grad`` stays a view, so ``optimizer.zero_grad(set_to_none=True)`` must NOT be used)."""
-        if self._buckets is None:
-            for p in self.params:
-                p.grad = None
-            return
-        for bucket in self._buckets:
-            bucket["flat"].zero_()
+        """Gradients start every step as ``None``: autograd then hands each parameter a fresh tensor (no read-modify-write), which the
+        bucket's flush copies into the flat buffer.  (Use this instead of ``optimizer.zero_grad``.)"""
+        for p in self.params:
+            p.grad = None
+        for bucket in self._buckets or []:
             bucket["pending"] = len(bucket["idxs"])
-        for i, p in enumerate(self.params):
-            if i not in self._bucket_of:
-                p.grad = None
+            bucket["flushed"] = False
 
     def finish(self) -> None:
-        """Call after ``loss.backward()``: completes the reduction and leaves averaged gradients in ``param.grad``."""
-        first = self._buckets is None
-        if first:
+        """Call after ``loss.backward()``: completes the reduction and leaves the averaged gradients in ``param.grad`` (as views of
+        the flat buckets)."""
+        if self._buckets is None:
             self._build()
-            if self.world > 1:
-                self._handles = [dist.all_reduce(b["flat"], op=dist.ReduceOp.SUM, group=self.group, async_op=True) for b in self._buckets]
-        elif self.world > 1:
-            for bucket in self._buckets:     # a bucket whose parameters did not all fire this step is reduced here, late
-                if bucket["pending"] > 0:
-                    self._handles.append(dist.all_reduce(bucket["flat"], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+        for bucket in self._buckets:          # first step, or a bucket whose parameters did not all fire this step
+            if not bucket["flushed"]:
+                self._flush(bucket)
         for h in self._handles:
             h.wait()
         self._handles = []
-        if self.world > 1:
-            for bucket in self._buckets:
+        for bucket in self._buckets:
+            if self.world > 1:
                 bucket["flat"].mul_(1.0 / self.world)
+            for v, i in zip(bucket["views"], bucket["idxs"]):
+                if self.params[i].grad is not None:
+                    self.params[i].grad = v
+        if self.world > 1:
             stray = [p for i, p in enumerate(self.params) if i not in self._bucket_of and p.grad is not None]
             for p in stray:                   # gradient appeared after step 1 (phase change): reduce it directly
                 dist.all_reduce(p.grad, op=dist.ReduceOp.SUM, group=self.group)
@@ -153,3 +159,59 @@ def finetune_step(model: torch.nn.Module, batch: dict, optimizer: torch.optim.Op
     torch.nn.utils.clip_grad_norm_([p for p in model.parameters() if p.grad is not None], max_norm)
     optimizer.step()
     return loss.detach()
+
+
+def invalidate_packs(model: torch.nn.Module) -> None:
+    """Drop every module's packed (16-bit / stacked) parameter copies.  Needed before EAGER use of a model whose optimizer steps
+    ran inside a replayed CUDA graph: replays do not bump ``Tensor._version``, which is what ``PackCache`` watches."""
+    for m in model.modules():
+        pack = getattr(m, "_pack", None)
+        if pack is not None:
+            pack.clear()
+
+
+class GraphedFinetuneStep:
+    """The finetune step (zero grads, forward, loss, backward, gradient reduction, clip, optimizer) as ONE CUDA graph.
+
+    At the reference's batch size (32 per GPU) the eager step is bound by the ~2300 host launches it issues (37 ms for 26 ms of
+    GPU work on B200).  Everything in the step is stream-ordered device work with static shapes - the kernels of this library,
+    torch's fp32 tail, ``clip_grad_norm_`` and a ``capturable`` fused AdamW - so after a few eager warm-up steps (which also
+    build the reducer's buckets and the optimizer state) the whole step is captured once and replayed.  Inputs are copied
+    into static buffers; the loss and its components are read from static output tensors (no ``.item()`` inside the step:
+    ``Poser.loss_tensors``).  The optimizer must have been created with ``capturable=True``.  Call ``invalidate_packs(model)``
+    before using the model eagerly again (evaluation between epochs).
+    """
+
+    def __init__(self, model: torch.nn.Module, batch: dict, optimizer: torch.optim.Optimizer, reducer: Optional[GradReducer] = None,
+                 max_norm: float = 5.0, warmup: int = 3):
+        self.model, self.optimizer, self.reducer, self.max_norm = model, optimizer, reducer, max_norm
+        self.static = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in batch.items()}
+        self.params = [p for p in model.parameters() if p.requires_grad]
+        if reducer is None:
+            self.reducer = GradReducer(self.params)      # also world size 1: keeps .grad in stable flat buffers for the graph
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(max(warmup, 2)):
+                self._step()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss, self.parts = self._step()
+
+    def _step(self):
+        self.reducer.zero_grad()
+        loss, parts, _ = self.model.loss_tensors(self.static)
+        loss.backward()
+        self.reducer.finish()
+        torch.nn.utils.clip_grad_norm_([p for p in self.params if p.grad is not None], self.max_norm)
+        self.optimizer.step()
+        return loss.detach(), parts
+
+    def __call__(self, batch: dict) -> torch.Tensor:
+        for k, v in batch.items():
+            if torch.is_tensor(v) and v.data_ptr() != self.static[k].data_ptr():
+                self.static[k].copy_(v, non_blocking=True)
+        self.graph.replay()
+        return self.loss

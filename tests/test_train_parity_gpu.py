@@ -139,3 +139,34 @@ def test_optimizer_step_changes_packed_weights():
         opt.step()
         losses.append(loss.item())
     assert all(np.isfinite(losses)) and losses[-1] < losses[0], losses
+
+
+def test_graphed_finetune_step_matches_eager():
+    """The whole step replayed as one CUDA graph (cs_vit.train.GraphedFinetuneStep) follows the eager step's loss trajectory."""
+    from cs_vit.train import GradReducer, GraphedFinetuneStep, finetune_step, invalidate_packs
+    traj = {}
+    for mode in ("eager", "graph"):
+        model, batch, gold, case = build_train_case("train_swint_encoder_patch_spatial", "bf16")
+        model = model.cuda()
+        dev = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in batch.items()}
+        params = [p for p in model.parameters() if p.requires_grad]
+        opt = torch.optim.AdamW(params, lr=2e-5, fused=True, capturable=(mode == "graph"))
+        reducer = GradReducer(params)
+        losses = []
+        if mode == "eager":
+            for _ in range(6):
+                losses.append(finetune_step(model, dev, opt, reducer).item())
+        else:
+            step = GraphedFinetuneStep(model, dev, opt, reducer, warmup=3)      # 3 eager warm-up steps inside
+            for _ in range(3):
+                losses.append(step(dev).item())
+            invalidate_packs(model)
+            with torch.no_grad():
+                model.eval()
+                out = model.predict_batch(dev["patches"], dev["square_bboxes"], dev["timestamp"], dev["focal"], dev["princpt"])
+            assert torch.isfinite(out["joint_cam"]).all()
+        traj[mode] = losses
+    # graph steps 1-3 are optimisation steps 4-6 (after its 3 warm-up steps)
+    assert all(np.isfinite(traj["graph"])) and traj["graph"][-1] < traj["eager"][0]
+    for a, b in zip(traj["graph"], traj["eager"][3:]):
+        assert abs(a - b) <= 5e-3 * abs(b), (traj["graph"], traj["eager"])

@@ -458,9 +458,16 @@ def run_finetune(a):
     if sampler:
         sampler.stop()
     if rank == 0:
-        print(json.dumps(res))
+        print(json.dumps(res), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # A replayable graph that holds captured NCCL work must be gone before the communicator is torn down (otherwise
+        # destroy_process_group can wait forever); after the final barrier a hard exit is the robust teardown.
+        if graphed:
+            del gstep, run_step
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stdout.flush()
+        os._exit(0)
 
 
 def main():

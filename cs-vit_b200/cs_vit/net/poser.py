@@ -359,7 +359,7 @@ class Poser(nn.Module):
         Python floats: no device->host sync, so the step can be captured in a CUDA graph (``cs_vit.train.GraphedFinetuneStep``)."""
         T = predict["joint_cam"].shape[1]
         # slices, not index lists: an index list becomes a host tensor + H2D copy, which cannot be captured in a CUDA graph
-        idx = slice(None) if self.temporal_supervision != "realtime" else slice(T - 1, T)
+        idx = slice(None) if self.temporal_supervision != "realtime" else slice(-1, None)   # last frame of prediction AND labels
         pj, gj, valid = predict["joint_cam"][:, idx], batch["joint_cam"][:, idx], batch["joint_valid"][:, idx]
         loss_cam = torch.mean((pj - gj).norm(dim=-1) * valid)
         loss_rel = torch.mean(((pj - pj[:, :, :1]) - (gj - gj[:, :, :1])).norm(dim=-1) * valid)

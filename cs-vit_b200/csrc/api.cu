@@ -1,6 +1,7 @@
 // C ABI of libcsvit_sm100.so (declared in include/csvit.h).
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 
 #include "../../include/csvit.h"
 #include "errors.h"
@@ -267,6 +268,21 @@ int csvit_attention_bwd(const void* q, const void* k, const void* v, const void*
                         int mask_ws, int mask_shift, void* stream) {
   CSVIT_REQUIRE(ok_dtype(dtype), "attention_bwd: bad dtype %d", dtype);
   CSVIT_REQUIRE((bias == nullptr) == (dbias == nullptr) || dbias == nullptr, "attention_bwd: dbias given without bias");
+  // Swin windows on packed 16-bit qkv / dqkv tensors: tensor-core kernel (attention_bwd_mma.cu); everything else (fp32, the
+  // head's dense MHA, unpacked operands) takes the exact SIMT kernel.
+  static int force_simt = -1;
+  if (force_simt < 0) { const char* e = getenv("CSVIT_ATTN_BWD_SIMT"); force_simt = (e && e[0] == '1') ? 1 : 0; }
+  const long long C = 32ll * heads, es = 2;
+  const char *qb = static_cast<const char*>(q), *kb = static_cast<const char*>(k), *vb = static_cast<const char*>(v);
+  const char *dqb = static_cast<const char*>(dq), *dkb = static_cast<const char*>(dk), *dvb = static_cast<const char*>(dv);
+  if (!force_simt && (dtype == DT_BF16 || dtype == DT_F16) && bias && dbias && Lq == 49 && S_ == 49 && mask_ws == 7 && mask_H > 0 &&
+      mask_W > 0 && kb == qb + C * es && vb == qb + 2 * C * es && dkb == dqb + C * es && dvb == dqb + 2 * C * es && ldq == 3 * C &&
+      ldk == 3 * C && ldv == 3 * C && lddq == 3 * C && lddk == 3 * C && lddv == 3 * C && ldo == C) {
+    const int nW = (mask_H / 7) * (mask_W / 7);
+    if (nW > 0 && n_seq % nW == 0 && mask_H % 7 == 0 && mask_W % 7 == 0)
+      return launch_window_attention_bwd_mma(q, dout, dq, dtype, bias, dbias, n_seq / nW, mask_H, mask_W, int(C), heads, 7, mask_shift,
+                                             S(stream));
+  }
   return launch_attention_bwd(q, k, v, dout, dq, dk, dv, dtype, ldq, ldk, ldv, ldo, lddq, lddk, lddv, n_seq, Lq, S_, heads, scale,
                               bias, dbias, mask_H, mask_W, mask_ws, mask_shift, S(stream));
 }

@@ -6,6 +6,7 @@
 // K14 final LayerNorm (:882), K1's Normalize + conv unfold (ref:cs_vit/net/ti_poser.py:239-243,425;
 // HF:swin/modeling_swin.py:286-295), and the BatchNorm1d transposes of the head
 // (ref:cs_vit/net/transformer_module.py:312,316).  All are one pass: read fp32 once, write once.
+#include <cstdlib>
 #include "errors.h"
 #include "rowops.cuh"
 
@@ -34,14 +35,14 @@ template <> struct Store4<__nv_bfloat16> {
 template <int MAXJ, int R, typename OutT>
 __global__ void __launch_bounds__(256)
 ln_rows_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
-               OutT* __restrict__ out, long long ldo, int rows, int C, int mode, WinGeom g) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+               OutT* __restrict__ out, long long ldo, int rows, int C, int mode, WinGeom g, int scatter_min_c) {
   const int lane = threadIdx.x & 31;
-  const int row0 = warp * R;
-  if (row0 >= rows) return;
   const int Cout = mode == LN_MERGE2X2 ? 4 * C : C;
   const int n4 = Cout >> 2;
-
+  const int warps_total = (gridDim.x * blockDim.x) >> 5;
+  // grid-stride over row groups: with a grid of (SMs x resident CTAs) every SM streams until the end instead of
+  // finishing in 2-3 uneven waves of short-lived CTAs
+  for (int row0 = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * R; row0 < rows; row0 += warps_total * R) {
   float4 v[R][MAXJ];
   float sum[R];
 #pragma unroll
@@ -50,7 +51,7 @@ ln_rows_kernel(const float* __restrict__ x, const float* __restrict__ gamma, con
     sum[r] = 0.f;
     if (row < rows) {
       long long src[4];
-      if (mode == LN_IDENTITY || (mode == LN_WINDOW && C >= 512)) {
+      if (mode == LN_IDENTITY || (mode == LN_WINDOW && C >= scatter_min_c)) {
         src[0] = row;   // wide rows in window mode: walk the SOURCE tokens in memory order (sequential fp32 reads, 2/3 of
                         // the traffic) and scatter the 16-bit rows (>= 1 KB each) to their window-order position
       } else if (mode == LN_WINDOW) {
@@ -94,7 +95,7 @@ ln_rows_kernel(const float* __restrict__ x, const float* __restrict__ gamma, con
     }
     const float rstd = rsqrtf(warp_sum(sq) / float(Cout) + eps);
     long long drow = row;
-    if (mode == LN_WINDOW && C >= 512) {
+    if (mode == LN_WINDOW && C >= scatter_min_c) {
       const int b = row / g.N, t = row - b * g.N;
       drow = static_cast<long long>(b) * g.N + win_token_to_row(g, t);
     }
@@ -111,13 +112,22 @@ ln_rows_kernel(const float* __restrict__ x, const float* __restrict__ gamma, con
       }
     }
   }
+  }
 }
 
 template <int MAXJ, int R, typename OutT>
 static void launch_ln_cfg(const float* x, const float* gamma, const float* beta, float eps, OutT* out, long long ldo,
                           int rows, int C, int mode, const WinGeom& g, cudaStream_t stream) {
   const int warps = (rows + R - 1) / R;
-  ln_rows_kernel<MAXJ, R, OutT><<<(warps + 7) / 8, 256, 0, stream>>>(x, gamma, beta, eps, out, ldo, rows, C, mode, g);
+  int blocks = (warps + 7) / 8;
+  static int persist = -1;
+  if (persist < 0) { const char* e = getenv("CSVIT_LN_PERSIST"); persist = e ? atoi(e) : 0; }
+  if (persist > 0 && blocks > num_sms() * persist) blocks = num_sms() * persist;
+  // window mode: rows at least this wide are read in memory order and SCATTERED as 16-bit rows; narrower rows were meant to be
+  // gathered instead, but scattering measured faster down to C = 128 (tools/bench_ln.py: 221 vs 242 us at stage 0)
+  static int scatter_min = -1;
+  if (scatter_min < 0) { const char* e = getenv("CSVIT_LN_SCATTER_MIN_C"); scatter_min = e ? atoi(e) : 128; }
+  ln_rows_kernel<MAXJ, R, OutT><<<blocks, 256, 0, stream>>>(x, gamma, beta, eps, out, ldo, rows, C, mode, g, scatter_min);
 }
 
 template <typename OutT>

@@ -58,4 +58,8 @@ int launch_attention_bwd(const void* q, const void* k, const void* v, const void
                          int n_seq, int Lq, int S, int heads, float scale, const float* bias, float* dbias, int mH, int mW, int mws,
                          int mshift, cudaStream_t stream);
 
+// attention_bwd_mma.cu
+int launch_window_attention_bwd_mma(const void* qkv, const void* dout, void* dqkv, int dtype, const float* bias, float* dbias, int B,
+                                    int H, int W, int C, int heads, int ws, int shift, cudaStream_t stream);
+
 }  // namespace csvit

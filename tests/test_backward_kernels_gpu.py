@@ -206,7 +206,7 @@ def test_attention_bwd_dense(ops, L, S, heads, n):
 
 
 @pytest.mark.parametrize("H,shift,heads", [(14, 3, 12), (28, 0, 6), (7, 0, 24), (28, 3, 8)])
-@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16, torch.float16])
 def test_window_attention_bwd(ops, H, shift, heads, dt):
     B, ws, L = 2, 7, 49
     C = heads * 32
@@ -224,6 +224,7 @@ def test_window_attention_bwd(ops, H, shift, heads, dt):
     dqkv = torch.empty_like(qkv)
     _, _, _, dbias = ops.attention_bwd(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], do, B * nW, L, L, heads, 1 / math.sqrt(32.0),
                                       bias=bias, mask=(H, H, ws, shift), dq=dqkv[:, :C], dk=dqkv[:, C:2 * C], dv=dqkv[:, 2 * C:])
-    tol = 2e-5 if dt == torch.float32 else 6e-3
+    # 16-bit: tensor-core kernel (attention_bwd_mma.cu): P and dS are rounded to the operand format for the second MMA
+    tol = {torch.float32: 2e-5, torch.bfloat16: 8e-3, torch.float16: 2e-3}[dt]
     assert rel(dqkv, eqkv) < tol, rel(dqkv, eqkv)
-    assert rel(dbias, ebias) < (1e-4 if dt == torch.float32 else 6e-3), rel(dbias, ebias)
+    assert rel(dbias, ebias) < (1e-4 if dt == torch.float32 else tol), rel(dbias, ebias)

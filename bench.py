@@ -58,6 +58,8 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=16, help="images per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip roofline / e2e / fp16 passes (debug)")
+    ap.add_argument("--latent-layers", type=int, default=0, help="finetune workload: num_latent_layer of the 'ti' configurations "
+                    "(spatial_dexycb_swinb_spenc_addpat_ti ships 3); 0 = no latent consistency branch")
     ap.add_argument("--micro-batch", type=int, default=-1, help="images per backbone pass (L2-resident chunks); -1 = library default, 0 = whole batch")
     ap.add_argument("--no-graph", action="store_true", help="launch kernels one by one instead of replaying a CUDA graph")
     return ap.parse_args()
@@ -381,7 +383,7 @@ def run_finetune(a):
     bdir = make_random_backbone_dir(os.path.join(tmp, a.variant), a.variant, seed=0)
     torch.manual_seed(0)
     model = Poser(bdir, image_size=224, mano_layer=SyntheticMANO(), spatial_layer_type="encoder", persp_decorate="patch",
-                  precision=a.precision)
+                  precision=a.precision, num_latent_layer=a.latent_layers or None)
     randomize_head_(model)
     model.phase(Poser.TrainingPhase.SPATIAL)          # train mode: batch-statistics BatchNorm, trainable spatial modules
     model = model.to(dev)
@@ -445,7 +447,9 @@ def run_finetune(a):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": a.precision, "data": "synthetic",
         "config": {"launch": "one CUDA graph per step (cs_vit.train.GraphedFinetuneStep)" if graphed else "eager",
                    "workload": f"{a.variant} spatial model finetune step (Poser.forward loss, backward, grad clip 5.0, fused AdamW), "
-                               f"batch {B}/GPU, 224x224, train-mode BatchNorm", "global_batch": B * world, "parallelism": f"dp{world}",
+                               f"batch {B}/GPU, 224x224, train-mode BatchNorm"
+                               + (f", latent consistency branch with {a.latent_layers} layers ('ti' configuration)" if a.latent_layers else ""),
+                   "global_batch": B * world, "parallelism": f"dp{world}",
                    "allreduce": f"{nparams * 4 / 1e6:.1f} MB fp32 gradients in {len(reducer.bucket_summary())} flat buckets, "
                                 f"async NCCL allreduce launched from grad-ready hooks",
                    "operands": f"{a.precision} tensor-core operands forward and backward, fp32 accumulate / gradients / optimizer"},

@@ -26,7 +26,7 @@ import torch.nn as nn
 from .. import autograd as ag
 from .. import ops
 from ..constants import TARGET_JOINTS_CONNECTION
-from ..utils.geometry import matrix_to_axis_angle, rotation_6d_to_matrix
+from ..utils.geometry import axis_angle_to_matrix, matrix_to_axis_angle, rotation_6d_to_matrix
 from ..utils.joint import mean_connection_length
 from .blocks import (CrossAttnDecoder, DecoderBlock, EncoderBlock, PositionalEncoding, _KernelModule, _flat,
                      set_precision)
@@ -172,10 +172,6 @@ class Poser(nn.Module):
         assert persp_embed_method in ["dense", "sparse"]
         assert persp_decorate in ["query", "patch"]
         assert global_positioning in ["direct", "orientation"]
-        if num_latent_layer is not None:
-            raise NotImplementedError(
-                "the training-only latent scale/rotation branch (num_latent_layer) is not built yet "
-                "(SURVEY.md §8f row 3); eval.py always passes num_latent_layer=None")
 
         self.backbone_ckpt_dir = backbone
         self.num_pose_query = num_pose_query
@@ -199,7 +195,13 @@ class Poser(nn.Module):
         heads = self.backbone.config.num_heads
         self.num_heads = heads[-1] if isinstance(heads, list) else heads
         self.num_p = self.image_size // 32
-        self.latent_trans = None
+        if num_latent_layer is not None:     # training-only consistency branch of the "ti" configurations (ref :255-265)
+            from .latent_transformers import ScaleRotComplexEmbedTransformationGroup
+            self.latent_trans = ScaleRotComplexEmbedTransformationGroup(
+                num_layers=num_latent_layer, embed_dim=self.hidden_dim, num_heads=self.num_heads, num_p=self.num_p, num_q=self.num_p)
+        else:
+            self.latent_trans = None
+        self._latent_override = None         # tests: (scale_coef [B], angle_rad [B]) instead of the random draw
 
         self.rmano_layer = _load_mano(smplx_path, mano_layer)
         self.rmano_layer.requires_grad_(False)
@@ -285,8 +287,21 @@ class Poser(nn.Module):
             queries = queries + persp_bias[:, None, :]
         else:
             patches = patches + persp_bias[:, None, :]
-        tokens = self.spatial_encoder(queries.contiguous(), patches)                    # [BT, 3, D]
-        tokens = tokens.reshape(B, T, 3, -1)
+        # Latent consistency branch (ref :442-457): a second copy of the patches, scaled / rotated in latent space, goes through
+        # the same spatial encoder; the batch doubles (n = 2) and the copy's predictions are rotated back below.
+        n = 1
+        if self.latent_trans is not None:
+            if self._latent_override is not None:
+                scale_coef, angle_rad = (t.to(patches.device, patches.dtype) for t in self._latent_override)
+            else:
+                scale_coef = torch.randn(B, device=patches.device, dtype=patches.dtype).clamp(-0.3, 0.3) + 1.0
+                angle_rad = torch.rand(B, device=patches.device, dtype=patches.dtype) * 2 * math.pi
+            patches = torch.cat([patches, self.latent_trans.do_sr(patches, scale_coef, angle_rad)], dim=0)
+            queries = torch.cat([queries, queries], dim=0)
+            timestamp = torch.cat([timestamp, timestamp], dim=0)
+            n = 2
+        tokens = self.spatial_encoder(queries.contiguous(), patches)                    # [n BT, 3, D]
+        tokens = tokens.reshape(n * B, T, 3, -1)
         if self.training_phase in (Poser.TrainingPhase.INFERENCE, Poser.TrainingPhase.TEMPORAL):
             encoders = (self.pose_temporal_encoder, self.shape_temporal_encoder, self.root_temporal_encoder)
             streams = []
@@ -302,7 +317,18 @@ class Poser(nn.Module):
         pose_6d = self._linear_head(self.pose_decoder, pose_tok)
         pose_6d = pose_6d.reshape(*pose_6d.shape[:2], self.num_pose_query, 6)
         pose_aa = matrix_to_axis_angle(rotation_6d_to_matrix(pose_6d))
-        return pose_aa, self._linear_head(self.shape_decoder, shape_tok), self._linear_head(self.root_decoder, root_tok)
+        shape = self._linear_head(self.shape_decoder, shape_tok)
+        root = self._linear_head(self.root_decoder, root_tok)
+        if self.latent_trans is not None:      # rotate the transformed copy's predictions back (ref :537-557)
+            Tp = pose_aa.shape[1]
+            sin, cos = torch.sin(-angle_rad), torch.cos(-angle_rad)
+            zero, one = torch.zeros_like(sin), torch.ones_like(sin)
+            rot_z = torch.stack([cos, -sin, zero, sin, cos, zero, zero, zero, one], dim=-1).view(B, 1, 3, 3).expand(B, Tp, 3, 3)
+            pose_back = matrix_to_axis_angle(rot_z[:, :, None] @ axis_angle_to_matrix(pose_aa[B:]))
+            pose_aa = torch.cat([pose_aa[:B], pose_back], dim=0)
+            root_back = torch.einsum("btk,btkc->btc", root[B:], rot_z.transpose(-1, -2)) / scale_coef[:, None, None]
+            root = torch.cat([root[:B], root_back], dim=0)
+        return pose_aa, shape, root
 
     def _pose_fk(self, pose_aa: torch.Tensor, shape: torch.Tensor, root_transl_norm: torch.Tensor):
         """MANO forward kinematics, joint regression, de-normalisation to mm   (ref:cs_vit/net/ti_poser.py:561-607)."""
@@ -383,8 +409,13 @@ class Poser(nn.Module):
         """``predict_batch`` + ``_criterion`` without any host synchronisation: ``(loss, parts[5], predict)``, all on the device."""
         predict = self.predict_batch(img_tensor=batch["patches"], square_bboxes=batch["square_bboxes"],
                                      timestamp=batch["timestamp"], focal=batch["focal"], princpt=batch["princpt"])
-        loss, parts = self._criterion(predict, batch, host_logs=False)
-        return loss, parts, predict
+        if self.latent_trans is None:
+            loss, parts = self._criterion(predict, batch, host_logs=False)
+            return loss, parts, predict
+        b = batch["patches"].shape[0]
+        loss_o, parts = self._criterion({k: v[:b] for k, v in predict.items()}, batch, host_logs=False)
+        loss_t, _ = self._criterion({k: v[b:] for k, v in predict.items()}, batch, host_logs=False)
+        return loss_o + 1e-2 * loss_t, parts, predict
 
     def _vis(self, predict, batch):
         """Reprojection overlay for TensorBoard (ref:cs_vit/net/ti_poser.py:780-813).  Host-side cv2 drawing is
@@ -401,12 +432,18 @@ class Poser(nn.Module):
         predict = self.predict_batch(img_tensor=batch["patches"], square_bboxes=batch["square_bboxes"],
                                      timestamp=batch["timestamp"], focal=batch["focal"], princpt=batch["princpt"])
         predict_origin = {k: v[:batch_size].clone() for k, v in predict.items()}
-        loss, origin_dict = self._criterion(predict_origin, batch)
-        loss_origin_val = loss.item()
+        loss_origin, origin_dict = self._criterion(predict_origin, batch)
+        loss, trans_val, trans_dict = loss_origin, 0.0, {}
+        if self.latent_trans is not None:     # consistency loss on the latent-transformed copy (ref :835-837)
+            predict_trans = {k: v[batch_size:].clone() for k, v in predict.items()}
+            loss_trans, trans_dict = self._criterion(predict_trans, batch)
+            loss = loss_origin + 1e-2 * loss_trans
+            trans_val = loss_trans.item()
         return {
             "loss": loss,
             "logs": {
-                "scalar": {"total": loss_origin_val, "origin": {"origin": loss_origin_val, **origin_dict}, "trans": {"trans": 0.0}},
+                "scalar": {"total": loss.item(), "origin": {"origin": loss_origin.item(), **origin_dict},
+                           "trans": {"trans": trans_val, **trans_dict}},
                 "image": {"img_reproj": self._vis(predict_origin, batch)},
             },
         }

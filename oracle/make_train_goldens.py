@@ -39,7 +39,11 @@ TRAIN_CASES = {
     "train_swint_encoder_patch_temporal": ("swin_t", dict(spatial_layer_type="encoder", persp_decorate="patch",
                                                           temporal_supervision="realtime", temporal_init_method="random"),
                                            "temporal", 4, 4),
+    # "ti" finetune configuration: latent scale / rotation consistency branch (doubles the spatial-encoder batch)
+    "train_swint_encoder_patch_spatial_ti": ("swin_t", dict(spatial_layer_type="encoder", persp_decorate="patch", num_latent_layer=2),
+                                             "spatial", 4, 1),
 }
+LATENT_SEED = 777
 OUT_KEYS = ("joint_cam", "verts_cam", "pose_aa", "shape", "root_transl_norm", "root_transl")
 FULL_GRAD_MAX = 4096
 N_PROJ = 4
@@ -78,16 +82,26 @@ def pass_reference(workdir: str) -> None:
     summary = {}
     for name, (variant, kw, phase, B, T) in TRAIN_CASES.items():
         sd = torch.load(os.path.join(workdir, name + ".sd.pt"))
-        m = ref_poser.Poser(backbone=os.path.join(workdir, variant), image_size=224, num_latent_layer=None, **kw)
+        m = ref_poser.Poser(backbone=os.path.join(workdir, variant), image_size=224, **{"num_latent_layer": None, **kw})
         m.load_state_dict(sd, strict=True)
         m.phase(ref_poser.Poser.TrainingPhase(phase))
         batch = synth.make_inputs(B, T, 224, seed=11, labels=True)
+        torch.manual_seed(LATENT_SEED)      # the reference draws (scale, angle) from the global RNG inside _decode_pose (:442-447)
         predict = m.predict_batch(batch["patches"].clone(), batch["square_bboxes"].clone(), batch["timestamp"].clone(),
                                   batch["focal"].clone(), batch["princpt"].clone())
-        loss, parts = m._criterion(predict, batch)
+        if kw.get("num_latent_layer") is not None:      # as Poser.forward does (ref :823-837)
+            loss, parts = m._criterion({k: v[:B] for k, v in predict.items()}, batch)
+            loss_trans, _ = m._criterion({k: v[B:] for k, v in predict.items()}, batch)
+            loss = loss + 1e-2 * loss_trans
+        else:
+            loss, parts = m._criterion(predict, batch)
         loss.backward()
 
         gold = {k: predict[k].detach().numpy().astype(np.float32) for k in OUT_KEYS}
+        if kw.get("num_latent_layer") is not None:      # the same draws, for the product's test hook (Poser._latent_override)
+            torch.manual_seed(LATENT_SEED)
+            gold["latent_scale"] = (torch.randn(B).clamp(-0.3, 0.3) + 1.0).numpy()
+            gold["latent_angle"] = (torch.rand(B) * 2 * torch.pi).numpy()
         gold["loss"] = np.array(loss.item(), dtype=np.float64)
         gold["loss_parts"] = np.array([parts[k] for k in ("cam", "rel", "shape", "loss_vel", "loss_accel")], dtype=np.float64)
         names, has_grad, norms, projs = [], [], [], []

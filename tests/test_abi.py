@@ -111,3 +111,34 @@ def test_finetune_config_contract():
     with pytest.raises(TypeError):
         cfg.update(3)
     assert '"img_size": 224' in cfg.to_json()
+
+
+def test_latent_branch_schema_and_option_checks():
+    """"ti" configurations (num_latent_layer set, ref:cs_vit/net/ti_poser.py:213-214, 255-265): same option assert and the
+    reference's parameter / buffer names (the strict load into the real reference model is done in oracle/make_train_goldens.py)."""
+    from helpers import backbone_dir
+    from cs_vit.net import Poser
+    from cs_vit.utils.mano_standin import SyntheticMANO
+    with pytest.raises(AssertionError):
+        Poser(backbone_dir("swin_t"), image_size=224, mano_layer=SyntheticMANO(), num_latent_layer=2, persp_decorate="query")
+    m = Poser(backbone_dir("swin_t"), image_size=224, mano_layer=SyntheticMANO(), num_latent_layer=2, persp_decorate="patch",
+              spatial_layer_type="encoder")
+    sd = m.state_dict()
+    expect = {
+        "latent_trans.rope2d.embedding": (32, 768),
+        "latent_trans.rope2d.rot_matrix": (7, 7, 384, 2, 2),
+        "latent_trans.rope2d.pos_ceil": (7, 7),
+        "latent_trans.rope2d.alpha": (7, 7, 1),
+        "latent_trans.sr.1.attn.query.weight": (768, 768),
+        "latent_trans.sr.0.norm2.running_var": (768,),
+        "latent_trans.scale_embedder.freq_base": (32,),
+        "latent_trans.scale_embedder.proj.0.weight": (768, 64),
+        "latent_trans.angle_embedder.proj.2.bias": (768,),
+        "latent_trans.scale_linear.4.weight": (768, 768),
+        "latent_trans.angle_linear.0.bias": (768,),
+    }
+    for k, shape in expect.items():
+        assert k in sd and tuple(sd[k].shape) == shape, (k, tuple(sd[k].shape) if k in sd else None)
+    # the reference never re-enables the group after the constructor's INFERENCE phase: frozen and in eval mode while finetuning
+    m.phase(Poser.TrainingPhase.SPATIAL)
+    assert not any(p.requires_grad for p in m.latent_trans.parameters()) and not m.latent_trans.training

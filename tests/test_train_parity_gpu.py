@@ -23,8 +23,15 @@ def run_step(name, precision):
     model, batch, gold, case = build_train_case(name, precision)
     model = model.cuda()
     dev = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in batch.items()}
+    if "latent_scale" in gold:      # the (scale, angle) the reference drew from its RNG for the latent consistency branch
+        model._latent_override = (torch.from_numpy(gold["latent_scale"]), torch.from_numpy(gold["latent_angle"]))
     predict = model.predict_batch(dev["patches"], dev["square_bboxes"], dev["timestamp"], dev["focal"], dev["princpt"])
-    loss, parts = model._criterion(predict, dev)
+    if model.latent_trans is not None:      # Poser.forward's combination (ref:cs_vit/net/ti_poser.py:823-837)
+        b = dev["patches"].shape[0]
+        loss, parts = model._criterion({k: v[:b] for k, v in predict.items()}, dev)
+        loss = loss + 1e-2 * model._criterion({k: v[b:] for k, v in predict.items()}, dev)[0]
+    else:
+        loss, parts = model._criterion(predict, dev)
     loss.backward()
     torch.cuda.synchronize()
     return model, predict, loss, parts, gold
@@ -77,7 +84,8 @@ def compare_grads(model, gold, tol_param, tol_global, floor=1e-6):
 @pytest.mark.parametrize("name,tol_out,tol_param,tol_global", [
     ("train_swint_encoder_patch_spatial", 1e-4, 2e-3, 5e-4),
     ("train_swint_decoder_query_spatial", 1e-3, 1e-2, 5e-3),
-    ("train_swint_encoder_patch_temporal", 1e-4, 2e-3, 5e-4)])
+    ("train_swint_encoder_patch_temporal", 1e-4, 2e-3, 5e-4),
+    ("train_swint_encoder_patch_spatial_ti", 5e-4, 5e-3, 1e-3)])
 def test_finetune_step_fp32(name, tol_out, tol_param, tol_global):
     model, predict, loss, parts, gold = run_step(name, "fp32")
     assert abs(loss.item() - float(gold["loss"])) <= 1e-4 * abs(float(gold["loss"])), (loss.item(), float(gold["loss"]))

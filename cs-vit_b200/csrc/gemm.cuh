@@ -237,17 +237,18 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& ep, const CUtenso
             const int gcol = n_blk * BN + col_local;
             if (gcol >= ep.N) break;  // warp-uniform
             uint32_t pk[32];          // 64 columns packed to 16 bit
+            uint32_t r2[2][32];       // both 32-column TMEM loads are issued before the single wait: their latency overlaps
+            tmem_ld_32x32(t_addr + uint32_t(col_local), r2[0]);
+            tmem_ld_32x32(t_addr + uint32_t(col_local + 32), r2[1]);
+            tmem_ld_wait();
   #pragma unroll
             for (int hh = 0; hh < 2; ++hh) {
-              uint32_t r[32];
-              tmem_ld_32x32(t_addr + uint32_t(col_local + 32 * hh), r);
-              tmem_ld_wait();
               if (ep.act == ACT_GELU) {
-                epi_bias_gelu_pack32(ep.bias, bf, gcol + 32 * hh, r, pk + 16 * hh);
+                epi_bias_gelu_pack32(ep.bias, bf, gcol + 32 * hh, r2[hh], pk + 16 * hh);
               } else {
                 float v[32];
     #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r2[hh][j]);
                 epi_bias_act32(ep, gcol + 32 * hh, v);
     #pragma unroll
                 for (int j = 0; j < 16; ++j) pk[16 * hh + j] = pack16(bf, v[2 * j], v[2 * j + 1]);

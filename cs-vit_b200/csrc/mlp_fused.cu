@@ -172,12 +172,14 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         mbar_wait(&acc1_full[b], use[b] & 1u);
         tc_fence_after();
         uint32_t pk[32];                      // this thread's 64 hidden columns, packed to 16 bit
-#pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {
-          uint32_t rr[32];
-          tmem_ld_32x32(tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(b * 128 + half * 64 + 32 * hh), rr);
+        {   // both 32-column TMEM loads are in flight before the single wait (the chunk epilogue is latency-bound, not issue-bound)
+          uint32_t rr0[32], rr1[32];
+          const uint32_t ta = tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(b * 128 + half * 64);
+          tmem_ld_32x32(ta, rr0);
+          tmem_ld_32x32(ta + 32u, rr1);
           tmem_ld_wait();
-          epi_bias_gelu_pack32(mp.b1, bf, j * 128 + half * 64 + 32 * hh, rr, pk + 16 * hh);
+          epi_bias_gelu_pack32(mp.b1, bf, j * 128 + half * 64, rr0, pk);
+          epi_bias_gelu_pack32(mp.b1, bf, j * 128 + half * 64 + 32, rr1, pk + 16);
         }
         tc_fence_before();
         __syncwarp();

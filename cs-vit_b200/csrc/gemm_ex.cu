@@ -292,7 +292,7 @@ int launch_gemm_ex(const void* A, long long lda, int a_mn, const void* B, long l
   if (splits <= 0) {
     splits = 1;
     if (out_dtype == DT_F32 && tiles * 2 <= num_sms() && num_kb >= 16) {
-      splits = (num_sms() + tiles - 1) / tiles;
+      splits = num_sms() / tiles;            // floor: tiles * splits <= SMs, one full wave (ceil spills a few items into a second wave)
       if (splits > num_kb / 8) splits = num_kb / 8;
       if (splits < 1) splits = 1;
     }

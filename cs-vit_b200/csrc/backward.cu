@@ -54,71 +54,75 @@ template <> __device__ __forceinline__ void st4<__half>(__half* p, float4 v) {
 // Column reductions (+ optional cast / gather copy)
 // ----------------------------------------------------------------------------------------------------
 enum : int { CR_SUM = 0, CR_CENTERED = 1, CR_DOT = 2 };
-constexpr int CR_ROWS = 64;   // rows per CTA
-
 // a: SrcT [rows, C] (pitch lda).  Row r of the pass reads source row map(r) (identity or window gather, as csvit_layernorm).
 //   CR_SUM      s1[c] += sum_r a[r,c]
 //   CR_CENTERED s1[c] += sum_r (a - center[c]),  s2[c] += sum_r (a - center[c])^2
 //   CR_DOT      s1[c] += sum_r a[r,c],           s2[c] += sum_r a[r,c] * b[r,c]         (b fp32, pitch ldb, same row map)
 // copy (optional): copy[r, c] = a[map(r), c] in OutT.   s1 / s2 may be null (pure cast / gather).
+// Grid: x = row blocks of `rows_per_cta`, y = groups of 128 columns (one float4 per lane), so wide-and-short tensors (the
+// [6272, 2048] hidden gradient of stage 2) still fill the machine; each warp streams rows r0 + warp, + 8, ...
 template <typename SrcT, typename OutT>
 __global__ void __launch_bounds__(256)
 col_reduce_kernel(const SrcT* __restrict__ a, long long lda, const float* __restrict__ b, long long ldb,
                   const float* __restrict__ center, int mode, int rows, int C, int row_mode, WinGeom g, OutT* __restrict__ copy,
-                  long long ldc, float* __restrict__ s1, float* __restrict__ s2) {
+                  long long ldc, float* __restrict__ s1, float* __restrict__ s2, int rows_per_cta) {
   __shared__ float4 red1[8][32];
   __shared__ float4 red2[8][32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int n4 = C >> 2;
-  const int r0 = blockIdx.x * CR_ROWS, r1 = min(rows, r0 + CR_ROWS);
-  for (int c4 = lane; c4 < ((n4 + 31) / 32) * 32; c4 += 32) {
-    const bool ok = c4 < n4;
-    float4 acc1 = make_float4(0.f, 0.f, 0.f, 0.f), acc2 = acc1, ctr = acc1;
-    if (ok && mode == CR_CENTERED) ctr = *reinterpret_cast<const float4*>(center + 4 * c4);
-    if (ok) {
-      for (int r = r0 + warp; r < r1; r += 8) {
-        long long src = r;
-        if (row_mode == LN_WINDOW) {
-          const int bi = r / g.N, rr = r - bi * g.N;
-          src = static_cast<long long>(bi) * g.N + win_row_to_token(g, rr);
-        }
-        float4 v = ld4<SrcT>(a + src * lda + 4 * c4);
-        if (copy) st4<OutT>(copy + static_cast<long long>(r) * ldc + 4 * c4, v);
-        if (mode == CR_CENTERED) {
-          v.x -= ctr.x; v.y -= ctr.y; v.z -= ctr.z; v.w -= ctr.w;
-          acc2.x = fmaf(v.x, v.x, acc2.x); acc2.y = fmaf(v.y, v.y, acc2.y); acc2.z = fmaf(v.z, v.z, acc2.z); acc2.w = fmaf(v.w, v.w, acc2.w);
-        } else if (mode == CR_DOT) {
-          const float4 w = *reinterpret_cast<const float4*>(b + src * ldb + 4 * c4);
-          acc2.x = fmaf(v.x, w.x, acc2.x); acc2.y = fmaf(v.y, w.y, acc2.y); acc2.z = fmaf(v.z, w.z, acc2.z); acc2.w = fmaf(v.w, w.w, acc2.w);
-        }
-        acc1.x += v.x; acc1.y += v.y; acc1.z += v.z; acc1.w += v.w;
+  const int r0 = blockIdx.x * rows_per_cta, r1 = min(rows, r0 + rows_per_cta);
+  const int c4 = blockIdx.y * 32 + lane;
+  const bool ok = c4 < n4;
+  float4 acc1 = make_float4(0.f, 0.f, 0.f, 0.f), acc2 = acc1, ctr = acc1;
+  if (ok && mode == CR_CENTERED) ctr = *reinterpret_cast<const float4*>(center + 4 * c4);
+  if (ok) {
+#pragma unroll 4
+    for (int r = r0 + warp; r < r1; r += 8) {
+      long long src = r;
+      if (row_mode == LN_WINDOW) {
+        const int bi = r / g.N, rr = r - bi * g.N;
+        src = static_cast<long long>(bi) * g.N + win_row_to_token(g, rr);
       }
+      float4 v = ld4<SrcT>(a + src * lda + 4 * c4);
+      if (copy) st4<OutT>(copy + static_cast<long long>(r) * ldc + 4 * c4, v);
+      if (mode == CR_CENTERED) {
+        v.x -= ctr.x; v.y -= ctr.y; v.z -= ctr.z; v.w -= ctr.w;
+        acc2.x = fmaf(v.x, v.x, acc2.x); acc2.y = fmaf(v.y, v.y, acc2.y); acc2.z = fmaf(v.z, v.z, acc2.z); acc2.w = fmaf(v.w, v.w, acc2.w);
+      } else if (mode == CR_DOT) {
+        const float4 w = *reinterpret_cast<const float4*>(b + src * ldb + 4 * c4);
+        acc2.x = fmaf(v.x, w.x, acc2.x); acc2.y = fmaf(v.y, w.y, acc2.y); acc2.z = fmaf(v.z, w.z, acc2.z); acc2.w = fmaf(v.w, w.w, acc2.w);
+      }
+      acc1.x += v.x; acc1.y += v.y; acc1.z += v.z; acc1.w += v.w;
     }
-    if (s1 == nullptr && s2 == nullptr) continue;
-    red1[warp][lane] = acc1;
-    red2[warp][lane] = acc2;
-    __syncthreads();
-    if (warp == 0 && ok) {
-      float4 t1 = red1[0][lane], t2 = red2[0][lane];
+  }
+  if (s1 == nullptr && s2 == nullptr) return;
+  red1[warp][lane] = acc1;
+  red2[warp][lane] = acc2;
+  __syncthreads();
+  if (warp == 0 && ok) {
+    float4 t1 = red1[0][lane], t2 = red2[0][lane];
 #pragma unroll
-      for (int w = 1; w < 8; ++w) {
-        const float4 u1 = red1[w][lane], u2 = red2[w][lane];
-        t1.x += u1.x; t1.y += u1.y; t1.z += u1.z; t1.w += u1.w;
-        t2.x += u2.x; t2.y += u2.y; t2.z += u2.z; t2.w += u2.w;
-      }
-      if (s1) { atomicAdd(s1 + 4 * c4, t1.x); atomicAdd(s1 + 4 * c4 + 1, t1.y); atomicAdd(s1 + 4 * c4 + 2, t1.z); atomicAdd(s1 + 4 * c4 + 3, t1.w); }
-      if (s2 && mode != CR_SUM) { atomicAdd(s2 + 4 * c4, t2.x); atomicAdd(s2 + 4 * c4 + 1, t2.y); atomicAdd(s2 + 4 * c4 + 2, t2.z); atomicAdd(s2 + 4 * c4 + 3, t2.w); }
+    for (int w = 1; w < 8; ++w) {
+      const float4 u1 = red1[w][lane], u2 = red2[w][lane];
+      t1.x += u1.x; t1.y += u1.y; t1.z += u1.z; t1.w += u1.w;
+      t2.x += u2.x; t2.y += u2.y; t2.z += u2.z; t2.w += u2.w;
     }
-    __syncthreads();
+    if (s1) { atomicAdd(s1 + 4 * c4, t1.x); atomicAdd(s1 + 4 * c4 + 1, t1.y); atomicAdd(s1 + 4 * c4 + 2, t1.z); atomicAdd(s1 + 4 * c4 + 3, t1.w); }
+    if (s2 && mode != CR_SUM) { atomicAdd(s2 + 4 * c4, t2.x); atomicAdd(s2 + 4 * c4 + 1, t2.y); atomicAdd(s2 + 4 * c4 + 2, t2.z); atomicAdd(s2 + 4 * c4 + 3, t2.w); }
   }
 }
 
 template <typename SrcT, typename OutT>
 static int launch_cr_t(const void* a, long long lda, const float* b, long long ldb, const float* center, int mode, int rows, int C,
                        int row_mode, const WinGeom& g, void* copy, long long ldc, float* s1, float* s2, cudaStream_t stream) {
-  const int blocks = (rows + CR_ROWS - 1) / CR_ROWS;
-  col_reduce_kernel<SrcT, OutT><<<blocks, 256, 0, stream>>>(static_cast<const SrcT*>(a), lda, b, ldb, center, mode, rows, C, row_mode, g,
-                                                            static_cast<OutT*>(copy), ldc, s1, s2);
+  const int col_groups = (C / 4 + 31) / 32;
+  // rows per CTA: as many as keep about 4 CTAs per SM in flight, between 64 and 512 (fewer atomics, longer streams)
+  int rpc = 512;
+  while (rpc > 64 && static_cast<long long>((rows + rpc - 1) / rpc) * col_groups < 4ll * 148) rpc >>= 1;
+  dim3 grid((rows + rpc - 1) / rpc, col_groups);
+  CSVIT_REQUIRE(grid.y < 65536, "col_reduce: too many column groups");
+  col_reduce_kernel<SrcT, OutT><<<grid, 256, 0, stream>>>(static_cast<const SrcT*>(a), lda, b, ldb, center, mode, rows, C, row_mode, g,
+                                                          static_cast<OutT*>(copy), ldc, s1, s2, rpc);
   CSVIT_CUDA(cudaGetLastError());
   return 0;
 }

@@ -30,7 +30,8 @@ from ..utils.geometry import axis_angle_to_matrix, matrix_to_axis_angle, rotatio
 from ..utils.joint import mean_connection_length
 from .blocks import (CrossAttnDecoder, DecoderBlock, EncoderBlock, PositionalEncoding, _KernelModule, _flat,
                      set_precision)
-from .swin_b200 import SwinBackboneB200
+from .swin_b200 import SwinBackboneB200  # noqa: F401  (re-exported)
+from .swinv2_b200 import load_backbone
 
 
 def derivative(x: torch.Tensor, dim: int) -> torch.Tensor:
@@ -190,7 +191,7 @@ class Poser(nn.Module):
         self.global_positioning = global_positioning
         self.training_phase = Poser.TrainingPhase.INFERENCE
 
-        self.backbone = SwinBackboneB200.from_pretrained(backbone, precision=precision)
+        self.backbone = load_backbone(backbone, precision=precision)   # swin (v1) or swinv2, by config.json
         self.hidden_dim = self.backbone.config.hidden_size
         heads = self.backbone.config.num_heads
         self.num_heads = heads[-1] if isinstance(heads, list) else heads

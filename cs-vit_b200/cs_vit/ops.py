@@ -284,6 +284,60 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, n_seq: int, Lq:
     return out
 
 
+# ---------------------------------------------------------------------------------------------- SwinV2
+COPY_NONE, COPY_IDENTITY, COPY_WINDOW, COPY_MERGE2X2 = 0, 1, 2, 3
+
+
+def swinv2_window_attention(qkv: torch.Tensor, bias_tab: torch.Tensor, logit_scale: torch.Tensor, B: int, H: int, W: int, heads: int,
+                            ws: int, shift: int, mask_repeat: int = 2) -> torch.Tensor:
+    """Scaled-cosine window attention (``csvit_swinv2_window_attention``): qkv window-ordered ``[B*H*W, 3C]``, ``bias_tab`` fp32
+    ``[heads, (2ws-1)^2]``, ``logit_scale`` fp32 ``[heads]`` (already clamped and exponentiated)."""
+    _dev(qkv, bias_tab, logit_scale)
+    rows, C3, ld = _rows2d(qkv)
+    C = C3 // 3
+    if ld != C3 or rows != B * H * W:
+        raise ValueError("swinv2_window_attention: qkv must be dense [B*H*W, 3C]")
+    if bias_tab.dtype != torch.float32 or tuple(bias_tab.shape) != (heads, (2 * ws - 1) ** 2) or not bias_tab.is_contiguous():
+        raise ValueError(f"swinv2_window_attention: bias table must be contiguous float32 [{heads}, {(2 * ws - 1) ** 2}]")
+    if logit_scale.dtype != torch.float32 or logit_scale.numel() != heads or not logit_scale.is_contiguous():
+        raise ValueError("swinv2_window_attention: logit_scale must be contiguous float32 [heads]")
+    out = torch.empty(rows, C, dtype=qkv.dtype, device=qkv.device)
+    L = ws * ws
+    _call("csvit_swinv2_window_attention", qkv.data_ptr(), bias_tab.data_ptr(), logit_scale.data_ptr(), out.data_ptr(),
+          _code(qkv.dtype), B, H, W, C, heads, ws, shift, mask_repeat, _stream(),
+          flops=4.0 * rows * L * C, nbytes=float(qkv.numel() + out.numel()) * qkv.element_size())
+    return out
+
+
+def layernorm_post(y: torch.Tensor, resid: Optional[torch.Tensor], gamma: torch.Tensor, beta: torch.Tensor, eps: float, *,
+                   out: Optional[torch.Tensor] = None, copy_mode: int = COPY_NONE, copy_dtype: torch.dtype = torch.bfloat16,
+                   geom: Tuple[int, int, int, int] = (0, 0, 0, 0)) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    """``out = (resid) + LayerNorm(y)`` in fp32 and, in the same pass, the copy of ``out`` laid out for the next GEMM
+    (``csvit_layernorm_post``).  ``geom`` = (H, W, ws, shift) of the copy's window order / merge grid.  Returns (out, copy)."""
+    _dev(y, resid, gamma, beta, out)
+    rows, C, ldy = _rows2d(y)
+    if y.dtype != torch.float32:
+        raise ValueError("layernorm_post input must be float32")
+    if resid is not None and (resid.dtype != torch.float32 or tuple(resid.shape) != (rows, C) or not resid.is_contiguous()):
+        raise ValueError("layernorm_post: residual must be contiguous float32 [rows, C]")
+    if gamma.numel() != C or beta.numel() != C:
+        raise ValueError(f"layernorm_post affine width {gamma.numel()} != {C}")
+    if out is None:
+        out = torch.empty(rows, C, dtype=torch.float32, device=y.device)
+    elif out.dtype != torch.float32 or tuple(out.shape) != (rows, C) or not out.is_contiguous():
+        raise ValueError("layernorm_post: out must be contiguous float32 [rows, C]")
+    H, W, ws, shift = geom
+    copy = None
+    if copy_mode == COPY_MERGE2X2:
+        copy = torch.empty(rows // 4, 4 * C, dtype=copy_dtype, device=y.device)
+    elif copy_mode != COPY_NONE:
+        copy = torch.empty(rows, C, dtype=copy_dtype, device=y.device)
+    _call("csvit_layernorm_post", y.data_ptr(), ldy, _p(resid), gamma.data_ptr(), beta.data_ptr(), float(eps), out.data_ptr(), _p(copy),
+          _code(copy_dtype), 0 if copy is None else copy.stride(0), copy_mode, rows, C, H, W, ws, shift, _stream(),
+          nbytes=float(rows * C * (8 + (4 if resid is not None else 0) + (0 if copy is None else copy.element_size()))))
+    return out, copy
+
+
 # ---------------------------------------------------------------------------------------------- training step (backward)
 CR_SUM, CR_CENTERED, CR_DOT = 0, 1, 2
 EW_GELU_FWD, EW_GELU_BWD, EW_RELU_BWD = 0, 1, 2

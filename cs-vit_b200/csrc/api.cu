@@ -207,6 +207,34 @@ int csvit_attention(const void* q, const void* k, const void* v, void* out, int 
                                S(stream));
 }
 
+// ---- SwinV2 ------------------------------------------------------------------------------------------------
+int csvit_swinv2_window_attention(const void* qkv, const float* bias_tab, const float* logit_scale, void* out, int dtype, int B, int H,
+                                  int W, int C, int heads, int ws, int shift, int mask_repeat, void* stream) {
+  CSVIT_REQUIRE(ok_dtype(dtype), "swinv2_window_attention: bad dtype %d", dtype);
+  CSVIT_REQUIRE(bias_tab != nullptr && logit_scale != nullptr, "swinv2_window_attention: bias table and logit scale are required");
+  CSVIT_REQUIRE(mask_repeat >= 0 && mask_repeat <= 2, "swinv2_window_attention: mask_repeat %d outside [0,2]", mask_repeat);
+  return launch_swinv2_window_attention(qkv, bias_tab, logit_scale, out, dtype, B, H, W, C, heads, ws, shift, mask_repeat, S(stream));
+}
+
+int csvit_layernorm_post(const float* y, long long ldy, const float* resid, const float* gamma, const float* beta, float eps, float* out,
+                         void* copy, int copy_dtype, long long ldc, int copy_mode, int rows, int C, int H, int W, int ws, int shift,
+                         void* stream) {
+  CSVIT_REQUIRE(ok_dtype(copy_dtype), "layernorm_post: bad copy dtype %d", copy_dtype);
+  CSVIT_REQUIRE(ldy >= C, "layernorm_post: pitch smaller than the row width");
+  WinGeom g = make_geom(H > 0 ? H : 1, W > 0 ? W : 1, ws > 0 ? ws : 1, shift);
+  if (copy_mode == CSVIT_COPY_WINDOW) {
+    CSVIT_REQUIRE(ws > 0 && H % ws == 0 && W % ws == 0, "layernorm_post(window): %dx%d not divisible by window %d", H, W, ws);
+    CSVIT_REQUIRE(shift >= 0 && shift < ws, "layernorm_post(window): shift %d outside [0,%d)", shift, ws);
+    CSVIT_REQUIRE(rows % (H * W) == 0, "layernorm_post(window): rows %d not a multiple of %d tokens", rows, H * W);
+    CSVIT_REQUIRE(ldc >= C, "layernorm_post(window): copy pitch smaller than the row width");
+  } else if (copy_mode == CSVIT_COPY_MERGE2X2) {
+    CSVIT_REQUIRE(H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0, "layernorm_post(merge): %dx%d must be even", H, W);
+    CSVIT_REQUIRE(rows % (H * W) == 0, "layernorm_post(merge): rows %d not a multiple of %d tokens", rows, H * W);
+    CSVIT_REQUIRE(ldc >= 4 * C, "layernorm_post(merge): copy pitch smaller than 4C");
+  }
+  return launch_layernorm_post(y, ldy, resid, gamma, beta, eps, out, copy, copy_dtype, ldc, copy_mode, rows, C, g, S(stream));
+}
+
 // ---- training step (backward) ----------------------------------------------------------------------------
 int csvit_gemm_ex(const void* A, long long lda, int a_mn, const void* B, long long ldb, int b_mn, int in_dtype, int M, int N, int K,
                   void* out, long long ldo, int out_dtype, int accumulate, int impl, int split_k, void* stream) {

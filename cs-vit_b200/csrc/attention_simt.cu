@@ -1,4 +1,4 @@
-// Exact-fp32 dense attention for short sequences (<= 64 keys, head_dim 32): the CS-ViT head's MHA
+// Exact-fp32 dense attention for short sequences (<= 128 keys, head_dim 32): the CS-ViT head's MHA
 // (ref:cs_vit/net/transformer_module.py:250-282), whose logits are MULTIPLIED by sqrt(head_dim) (line 273,
 // quirk Q1: near-argmax softmax, kept in fp32 on purpose), and the fp32 validation mode of the Swin window
 // attention (bias table + closed-form shift mask).
@@ -19,10 +19,11 @@ template <> __device__ __forceinline__ float from_f<float>(float v) { return v; 
 template <> __device__ __forceinline__ __nv_bfloat16 from_f<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
 template <> __device__ __forceinline__ __half from_f<__half>(float v) { return __float2half_rn(v); }
 
-constexpr int SA_MAXS = 64;
+constexpr int SA_MAXS = 128;   // 3 query tokens + 64 patches of a 256^2 SwinV2 backbone = 67 keys in the "encoder" head
+constexpr int SA_KPL = SA_MAXS / 32;   // keys per lane
 constexpr int SA_HD = 32;
 
-// One CTA (4 warps) per (sequence, head); warp per query row, lane per key (two keys per lane).
+// One CTA (4 warps) per (sequence, head); warp per query row, lane per key (up to SA_KPL keys per lane).
 template <typename T>
 __global__ void __launch_bounds__(128)
 attention_simt_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __restrict__ v, T* __restrict__ out,
@@ -47,10 +48,10 @@ attention_simt_kernel(const T* __restrict__ q, const T* __restrict__ k, const T*
     for (int i = warp; i < Lq; i += 4) {
       Qs[warp][lane] = to_f<T>(q[(static_cast<long long>(seq) * Lq + i) * ldq + h * SA_HD + lane]);
       __syncwarp();
-      float sc[2];
+      float sc[SA_KPL];
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        const int j = lane + 32 * half;
+      for (int t = 0; t < SA_KPL; ++t) {
+        const int j = lane + 32 * t;
         float a = -INFINITY;
         if (j < S) {
           a = 0.f;
@@ -60,14 +61,21 @@ attention_simt_kernel(const T* __restrict__ q, const T* __restrict__ k, const T*
           if (bias) a += __ldg(bias + (static_cast<long long>(h) * Lq + i) * S + j);
           if (g.shift > 0 && region_s[j] != region_s[i]) a += -100.0f;
         }
-        sc[half] = a;
+        sc[t] = a;
       }
-      const float mx = warp_max(fmaxf(sc[0], sc[1]));
-      const float e0 = lane < S ? expf(sc[0] - mx) : 0.f;
-      const float e1 = lane + 32 < S ? expf(sc[1] - mx) : 0.f;
-      const float inv = 1.0f / warp_sum(e0 + e1);
-      Ps[warp][lane] = e0 * inv;
-      Ps[warp][lane + 32] = e1 * inv;
+      float mx = sc[0];
+#pragma unroll
+      for (int t = 1; t < SA_KPL; ++t) mx = fmaxf(mx, sc[t]);
+      mx = warp_max(mx);
+      float esum = 0.f;
+#pragma unroll
+      for (int t = 0; t < SA_KPL; ++t) {
+        sc[t] = lane + 32 * t < S ? expf(sc[t] - mx) : 0.f;
+        esum += sc[t];
+      }
+      const float inv = 1.0f / warp_sum(esum);
+#pragma unroll
+      for (int t = 0; t < SA_KPL; ++t) Ps[warp][lane + 32 * t] = sc[t] * inv;
       __syncwarp();
       float acc = 0.f;
       for (int j = 0; j < S; ++j) acc = fmaf(Ps[warp][j], Vs[j][lane], acc);

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define CSVIT_ABI_VERSION 2
+#define CSVIT_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define CSVIT_API __attribute__((visibility("default")))
@@ -140,7 +140,32 @@ CSVIT_API int csvit_window_attention(const void* qkv, const float* bias, const f
 
 CSVIT_API int csvit_set_attention_impl(int use_tcgen05);
 
-/* Dense multi-head attention for short sequences (S <= 64, head_dim 32), exact fp32 math:
+/* ---- SwinV2 ("V2:" = transformers/models/swinv2/modeling_swinv2.py) ---------------------------
+ * Scaled-cosine window attention on window-ordered qkv[B*H*W, 3C] (layout as csvit_window_attention):
+ *   out = softmax( normalize(Q) normalize(K)^T * logit_scale[h] + bias_tab[h, rel_pos_index(i, j)]
+ *                  + mask_repeat * shift_mask ) V, heads merged.                                  V2:421-487
+ *   bias_tab    [heads, (2ws-1)^2] fp32 = 16 sigmoid(continuous_position_bias_mlp(relative_coords_table))  V2:460-472, 489-510
+ *   logit_scale [heads] fp32 = exp(min(logit_scale, ln 100))                                      V2:455
+ *   mask_repeat how often the {0,-100} shift mask is added (HF adds it twice, V2:466-474: pass 2)
+ * ws^2 must be a multiple of 16 and <= 256 (window 16: 256 tokens; window 8: 64).  bf16 / fp16: tensor-core kernel with
+ * online softmax; fp32: exact kernel (validation mode). */
+CSVIT_API int csvit_swinv2_window_attention(const void* qkv, const float* bias_tab, const float* logit_scale, void* out,
+                                            int dtype, int B, int H, int W, int C, int heads, int ws, int shift,
+                                            int mask_repeat, void* stream);
+
+/* Post-norm residual LayerNorm of SwinV2 (V2:707-712, 387, 282) with the next GEMM's operand copy folded in:
+ *   out[r, :] = (resid ? resid[r, :] : 0) + LayerNorm(y[r, :]) * gamma + beta        fp32, rows in token order;
+ *   out may alias resid or y (in place); resid / out are dense [rows, C], y has pitch ldy.
+ * copy (optional, dtype copy_dtype, pitch ldc) receives the same values at
+ *   CSVIT_COPY_IDENTITY  row r                                   (operand of intermediate.dense)
+ *   CSVIT_COPY_WINDOW    the (shifted-)window order of (H, W, ws, shift): replaces torch.roll + window_partition  V2:676-684
+ *   CSVIT_COPY_MERGE2X2  row (b, y/2, x/2), column block ((y&1) + 2(x&1)) * C: the concat of patch merging       V2:373-384 */
+enum { CSVIT_COPY_NONE = 0, CSVIT_COPY_IDENTITY = 1, CSVIT_COPY_WINDOW = 2, CSVIT_COPY_MERGE2X2 = 3 };
+CSVIT_API int csvit_layernorm_post(const float* y, long long ldy, const float* resid, const float* gamma, const float* beta,
+                                   float eps, float* out, void* copy, int copy_dtype, long long ldc, int copy_mode, int rows,
+                                   int C, int H, int W, int ws, int shift, void* stream);
+
+/* Dense multi-head attention for short sequences (S <= 128, head_dim 32), exact fp32 math:
  *   out[s, i, h*32:(h+1)*32] = softmax_j(q[s,i,h] . k[s,j,h] * scale) v[s,j,h]
  * q rows: n_seq*Lq, k/v rows: n_seq*S.  `scale` multiplies the logits (the reference passes sqrt(head_dim),
  * ref:cs_vit/net/transformer_module.py:243,273).  dtype applies to q, k, v and out. */

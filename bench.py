@@ -40,6 +40,22 @@ BATCH = 256
 FLOP_PER_IMAGE = 31.15e9     # executed algorithmic FLOPs: 30.860 backbone + 0.281 head layer (K/V for 52 tokens, the rest for the 3 kept
                              # query rows; BASELINE.md §3 counts the full layer: 32.19) + 0.010
 METRIC = "images/sec Swin-B spatial fwd @224^2 bs256"
+# SwinV2 w16 @256 (the shipped configuration family): 24 N C^2 + 4 L N C per block (L = 256 / 64-token windows)
+# + merges + embed = 43.57 (B) / 13.20 (T) GFLOP per image; "encoder" head layer on 3 + 64 tokens.
+V2_FLOP_PER_IMAGE = {"swinv2_b": 43.57e9 + 0.34e9, "swinv2_t": 13.20e9 + 0.19e9}
+
+
+def image_side(variant: str) -> int:
+    return 256 if variant.startswith("swinv2") else 224
+
+
+def variant_table(variant: str):
+    from cs_vit.synthetic import SWIN_VARIANTS, SWINV2_VARIANTS
+    return SWINV2_VARIANTS[variant] if variant in SWINV2_VARIANTS else SWIN_VARIANTS[variant]
+
+
+def metric_name(variant: str) -> str:
+    return METRIC if variant == "swin_b" else f"images/sec {variant} spatial fwd @{image_side(variant)}^2"
 
 
 def parse():
@@ -78,25 +94,33 @@ def cpu_reference_rate(variant: str, sample: int, steps: int, warmup: int):
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
     tmp = tempfile.mkdtemp(prefix="csvit_bench_cpu_")
-    bdir = make_random_backbone_dir(os.path.join(tmp, variant), variant, seed=0)
+    S = image_side(variant)
+    bdir = make_random_backbone_dir(os.path.join(tmp, variant), variant, seed=0, image_size=S)
     torch.manual_seed(0)
-    model = Poser(bdir, image_size=224, mano_layer=SyntheticMANO(), spatial_layer_type="encoder", persp_decorate="patch")
+    model = Poser(bdir, image_size=S, mano_layer=SyntheticMANO(), spatial_layer_type="encoder", persp_decorate="patch")
     randomize_head_(model)
     sd = {k: v.detach() for k, v in model.state_dict().items()}
-    _, depths, heads = SWIN_VARIANTS[variant]
+    _, depths, heads = variant_table(variant)
     opt = head.HeadOptions(num_heads=heads[-1], depths=depths, swin_heads=heads, spatial_layer_type="encoder",
                            persp_decorate="patch", phase="spatial")
     features_fn, kind_note = None, "oracle restatement of HF Swin"
+    if variant.startswith("swinv2"):
+        from oracle import swinv2_restated as v2r
+        bsd = {k[len("backbone."):]: v for k, v in sd.items() if k.startswith("backbone.")}
+        _mean = torch.tensor(head.IMAGENET_MEAN)[None, :, None, None]
+        _std = torch.tensor(head.IMAGENET_STD)[None, :, None, None]
+        features_fn = lambda x: v2r.swinv2_forward((x - _mean) / _std, bsd, depths, heads, window=16)  # noqa: E731
+        kind_note = "oracle restatement of HF Swinv2"
     try:
         import transformers
         hf = transformers.AutoModel.from_pretrained(bdir).eval()
         mean = torch.tensor(head.IMAGENET_MEAN)[None, :, None, None]
         std = torch.tensor(head.IMAGENET_STD)[None, :, None, None]
         features_fn = lambda x: hf((x - mean) / std).last_hidden_state  # noqa: E731
-        kind_note = f"HF transformers {transformers.__version__} SwinModel"
+        kind_note = f"HF transformers {transformers.__version__} {type(hf).__name__}"
     except Exception:
         pass
-    inputs = make_inputs(sample, 1, 224, seed=0)
+    inputs = make_inputs(sample, 1, S, seed=0)
     mano = SyntheticMANO()
     times = []
     with torch.inference_mode():
@@ -117,7 +141,7 @@ def run_reference_arm(a):
     steps = max(1, min(a.steps, 5))
     rate, ms, threads, note = cpu_reference_rate(a.variant, a.cpu_sample, steps, warm)
     print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": round(rate, 3), "unit": "images/s", "n_gpus": a.gpus,
+        "impl": "reference", "metric": metric_name(a.variant), "value": round(rate, 3), "unit": "images/s", "n_gpus": a.gpus,
         "steps": steps, "warmup": warm, "ms_per_step": round(ms, 2), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
         "config": {"workload": f"{a.variant} spatial model (encoder head, addpat) forward, CPU sample of {a.cpu_sample} images"},
@@ -193,12 +217,13 @@ def run_ours(a):
     dev = torch.device("cuda", local)
 
     tmp = tempfile.mkdtemp(prefix=f"csvit_bench_{rank}_")
-    bdir = make_random_backbone_dir(os.path.join(tmp, a.variant), a.variant, seed=0)
+    S = image_side(a.variant)
+    bdir = make_random_backbone_dir(os.path.join(tmp, a.variant), a.variant, seed=0, image_size=S)
     torch.manual_seed(0)
     temporal = a.workload == "temporal"
     T = a.frames if temporal else 1
     clips = a.batch // T                      # same number of images per GPU in both workloads
-    model = Poser(bdir, image_size=224, mano_layer=SyntheticMANO(), spatial_layer_type="encoder", persp_decorate="patch",
+    model = Poser(bdir, image_size=S, mano_layer=SyntheticMANO(), spatial_layer_type="encoder", persp_decorate="patch",
                   precision=a.precision, temporal_supervision="realtime" if temporal else "full",
                   temporal_init_method="random" if temporal else "zero")
     randomize_head_(model)
@@ -208,7 +233,8 @@ def run_ours(a):
     if a.micro_batch >= 0:
         model.backbone.micro_batch = a.micro_batch
 
-    host = make_inputs(clips, T, 224, seed=100 + rank)
+    host = make_inputs(clips, T, S, seed=100 + rank)
+    flop_per_image = V2_FLOP_PER_IMAGE.get(a.variant, FLOP_PER_IMAGE)
     keys = ("patches", "square_bboxes", "timestamp", "focal", "princpt")
     pinned = {k: host[k].pin_memory() for k in keys}
     resident = {k: pinned[k].to(dev) for k in keys}
@@ -267,18 +293,18 @@ def run_ours(a):
     peak_tf, peak_gbs, peak_kind = peaks()
 
     out = {
-        "metric": METRIC, "value": round(value, 1), "unit": "images/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+        "metric": metric_name(a.variant), "value": round(value, 1), "unit": "images/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": round(ms_total / a.steps, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": a.precision, "data": "synthetic",
-        "config": {"workload": (f"{a.variant} temporal model (realtime cross-frame attention), {clips} clips x {T} frames/GPU, 224x224"
+        "config": {"workload": (f"{a.variant} temporal model (realtime cross-frame attention), {clips} clips x {T} frames/GPU, {S}x{S}"
                                 if temporal else
-                                f"{a.variant} spatial model (encoder head, addpat, dense persp) predict_batch, batch {a.batch}/GPU, 224x224, T=1"),
+                                f"{a.variant} spatial model (encoder head, addpat, dense persp) predict_batch, batch {a.batch}/GPU, {S}x{S}, T=1"),
                    "global_batch": a.batch * world, "parallelism": f"dp{world}",
                    "l2_policy": "per-step inputs (154 MB) and activations (>1 GB) exceed the 126 MB L2; no explicit flush",
                    "operands": f"{a.precision} tensor-core operands, fp32 accumulate/residual/LN/softmax, TF32 head",
                    "launch": "eager" if a.no_graph else "CUDA graph replay of the step"},
         "gpu_launches": launches,
-        "model_flops_frac_of_peak": round(value / world * FLOP_PER_IMAGE / (peak_tf * 1e12), 4),
+        "model_flops_frac_of_peak": round(value / world * flop_per_image / (peak_tf * 1e12), 4),
         "clocks": clocks,
     }
 

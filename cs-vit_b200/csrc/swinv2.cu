@@ -40,42 +40,61 @@ template <> __device__ __forceinline__ float2 unpack2<__half>(uint32_t u) {
 __host__ __device__ inline int v2_smem_bytes(int ws) {
   const int L = ws * ws, tw = 2 * ws - 1;
   const int tb = (tw * tw + 3) & ~3;
-  return tb * 4 + 2 * L * 4 + L * 2 + L + 3 * L * ROW_BYTES;
+  return tb * 4 + 2 * L * 4 + L + 3 * L * ROW_BYTES;
 }
+
+__device__ __forceinline__ float ex2_ftz(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+template <typename T> struct Ones16;
+template <> struct Ones16<__nv_bfloat16> { static constexpr uint32_t v = 0x3F803F80u; };
+template <> struct Ones16<__half> { static constexpr uint32_t v = 0x3C003C00u; };
+
+constexpr float V2_LOG2E = 1.4426950408889634f;
 
 // qkv: window-ordered tokens [B*N, 3C] (Q | K | V column blocks, head h at columns 32h), out [B*N, C] window-ordered.
 // bias_tab [heads, (2ws-1)^2] = 16 sigmoid(cpb_mlp(coords)) (V2:460-472), logit_scale [heads] = exp(min(ls, ln 100)).
 // gridDim.x is a multiple of `heads`: a CTA serves one head (its bias table stays in shared memory) and walks windows.
-template <typename T>
+//
+// The kernel is bound by instruction issue on the softmax side (head_dim 32: 2 MMAs per 64 logits), so the per-logit work is
+// pared down to  FMUL, FFMA(+bias), max, FADD, MUFU.EX2, half a pack:
+//   * logits live in the log2 domain: log2(e) is folded into the per-row scale, the bias table and the mask value
+//   * the bias address is (per-thread row base) - (compile-time column term): one LDS with an immediate offset, no index math
+//   * row sums come out of the tensor core: P V is extended by a ones column (one extra MMA per 16 keys), which also makes the
+//     normaliser the sum of the ROUNDED probabilities that multiply V
+template <typename T, int WS>
 __global__ void __launch_bounds__(V2_THREADS, 4)
 swinv2_attn_kernel(const T* __restrict__ qkv, const float* __restrict__ bias_tab, const float* __restrict__ logit_scale,
                    T* __restrict__ out, int num_windows, int C, int heads, WinGeom g, int nW, float mask_value) {
+  static_assert(WS == 8 || WS == 16, "windows of 8x8 and 16x16 tokens");
+  constexpr int L = WS * WS, TW = 2 * WS - 1, TB = TW * TW, TBP = (TB + 3) & ~3;
   extern __shared__ __align__(16) uint8_t v2_smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int L = g.L, ws = g.ws, tw = 2 * ws - 1, TB = tw * tw;
   float* bias_s = reinterpret_cast<float*>(v2_smem);
-  float* rq_s = bias_s + ((TB + 3) & ~3);
+  float* rq_s = bias_s + TBP;
   float* rk_s = rq_s + L;
-  int16_t* ct_s = reinterpret_cast<int16_t*>(rk_s + L);
-  int8_t* region_s = reinterpret_cast<int8_t*>(ct_s + L);
+  int8_t* region_s = reinterpret_cast<int8_t*>(rk_s + L);
   uint8_t* Qs = reinterpret_cast<uint8_t*>(region_s + L);
   uint8_t* Ks = Qs + L * ROW_BYTES;
   uint8_t* Vs = Ks + L * ROW_BYTES;
 
   const int h = blockIdx.x % heads;
-  for (int i = tid; i < TB; i += V2_THREADS) bias_s[i] = __ldg(bias_tab + h * TB + i);
-  for (int i = tid; i < L; i += V2_THREADS) ct_s[i] = static_cast<int16_t>((i / ws) * tw + (i % ws));
-  const float scale = __ldg(logit_scale + h);
-  const int row_const = (ws - 1) * tw + (ws - 1);     // rel_pos_index(i, j) = ct[i] + row_const - ct[j]
+  for (int i = tid; i < TB; i += V2_THREADS) bias_s[i] = __ldg(bias_tab + h * TB + i) * V2_LOG2E;
+  const float scale = __ldg(logit_scale + h) * V2_LOG2E;
+  const float mask_l2 = mask_value * V2_LOG2E;
 
   const int ld_qkv = 3 * C;
-  const int nWy = g.H / ws;
+  const int nWy = g.H / WS;
   const int wstride = gridDim.x / heads;
+  const int q2 = (lane & 3) * 2;
   for (int wg = blockIdx.x / heads; wg < num_windows; wg += wstride) {   // global window = b*nW + w
-    __syncthreads();   // the previous window's tiles are consumed (first pass: the tables above are written)
+    __syncthreads();   // the previous window's tiles are consumed (first pass: the bias table above is written)
     const int w = wg % nW;
     const long long row0 = static_cast<long long>(wg) * L;
     const T* src = qkv + row0 * ld_qkv + h * 32;
+#pragma unroll 4
     for (int idx = tid; idx < 3 * L * 4; idx += V2_THREADS) {
       const int which = idx / (L * 4), rem = idx - which * (L * 4);
       const int r = rem >> 2, ch = rem & 3;
@@ -87,7 +106,7 @@ swinv2_attn_kernel(const T* __restrict__ qkv, const float* __restrict__ bias_tab
       for (int i = tid; i < L; i += V2_THREADS) region_s[i] = static_cast<int8_t>(win_region(g, w, i));
     cp_async_wait_all();
     __syncthreads();
-    // 1 / max(|q_i|, 1e-12) (times the head's logit scale) and 1 / max(|k_j|, 1e-12)   (F.normalize, V2:452-454)
+    // log2(e) * logit_scale / max(|q_i|, 1e-12) and 1 / max(|k_j|, 1e-12)   (F.normalize, V2:452-455)
     for (int i = tid; i < 2 * L; i += V2_THREADS) {
       const int which = i >= L ? 1 : 0, r = i - which * L;
       const uint4* rowp = reinterpret_cast<const uint4*>(Qs + which * (L * ROW_BYTES) + r * ROW_BYTES);
@@ -104,7 +123,7 @@ swinv2_attn_kernel(const T* __restrict__ qkv, const float* __restrict__ bias_tab
     __syncthreads();
 
 #pragma unroll 1
-    for (int mt = warp; mt < (L >> 4); mt += V2_THREADS / 32) {
+    for (int mt = warp; mt < L / 16; mt += V2_THREADS / 32) {
       const int m0 = mt * 16;
       uint32_t qa[2][4];
 #pragma unroll
@@ -112,97 +131,89 @@ swinv2_attn_kernel(const T* __restrict__ qkv, const float* __restrict__ bias_tab
         ldsm_x4(qa[ks], Qs + row_off(m0 + (lane & 7) + ((lane >> 3) & 1) * 8, ks * 2 + (lane >> 4)));
       const int r0 = m0 + (lane >> 2), r1 = r0 + 8;
       const float rq0 = rq_s[r0], rq1 = rq_s[r1];
-      const int rt0 = ct_s[r0] + row_const, rt1 = ct_s[r1] + row_const;
+      // rel_pos_index(i, j) = (iy - jy + WS-1) TW + (ix - jx + WS-1): per-thread row base minus a compile-time column term
+      const float* bp0 = bias_s + ((r0 / WS) * TW + (r0 % WS) + (WS - 1) * (TW + 1) - q2);
+      const float* bp1 = bias_s + ((r1 / WS) * TW + (r1 % WS) + (WS - 1) * (TW + 1) - q2);
       int reg0 = 0, reg1 = 0;
       if (masked) { reg0 = region_s[r0]; reg1 = region_s[r1]; }
-      float mrun0 = -INFINITY, mrun1 = -INFINITY, l0 = 0.f, l1 = 0.f;
-      float o[4][4];
+      float mrun0 = -INFINITY, mrun1 = -INFINITY;
+      float o[5][4];   // o[4] = running row sums (ones column)
 #pragma unroll
-      for (int n = 0; n < 4; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
+      for (int n = 0; n < 5; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
 
 #pragma unroll 1
       for (int c0 = 0; c0 < L; c0 += 64) {
-        const int nt = min(8, (L - c0) >> 3);   // 8-key tiles in this chunk (even: L is a multiple of 16)
         float s[8][4];
         // ---- S = Q K^T on the raw 16-bit operands ----
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
-          if (j < nt) {
-            uint32_t kb[4];
-            ldsm_x4(kb, Ks + row_off(c0 + j * 8 + (lane & 7), lane >> 3));
-            mma_16816<T>(s[j], qa[0], kb[0], kb[1]);
-            mma_16816<T>(s[j], qa[1], kb[2], kb[3]);
-          }
+          uint32_t kb[4];
+          ldsm_x4(kb, Ks + row_off(c0 + j * 8 + (lane & 7), lane >> 3));
+          mma_16816<T>(s[j], qa[0], kb[0], kb[1]);
+          mma_16816<T>(s[j], qa[1], kb[2], kb[3]);
         }
-        // ---- cosine scaling, continuous position bias, shift mask (fp32) ----
-        float mx0 = -INFINITY, mx1 = -INFINITY;
+        // ---- cosine scaling, continuous position bias (log2 domain, fp32) ----
+        const float* b0 = bp0 - (c0 / WS) * TW;
+        const float* b1 = bp1 - (c0 / WS) * TW;
+        const float* rkp = rk_s + c0 + q2;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          if (j < nt) {
-            const int c = c0 + j * 8 + (lane & 3) * 2;
-            const float2 rk = *reinterpret_cast<const float2*>(rk_s + c);
-            const uint32_t ctp = *reinterpret_cast<const uint32_t*>(ct_s + c);
-            const int ct0 = static_cast<int>(ctp & 0xffffu), ct1 = static_cast<int>(ctp >> 16);
-            s[j][0] = fmaf(s[j][0] * rq0, rk.x, bias_s[rt0 - ct0]);
-            s[j][1] = fmaf(s[j][1] * rq0, rk.y, bias_s[rt0 - ct1]);
-            s[j][2] = fmaf(s[j][2] * rq1, rk.x, bias_s[rt1 - ct0]);
-            s[j][3] = fmaf(s[j][3] * rq1, rk.y, bias_s[rt1 - ct1]);
-            if (masked) {
-              const int rc0 = region_s[c], rc1 = region_s[c + 1];
-              if (rc0 != reg0) s[j][0] += mask_value;
-              if (rc1 != reg0) s[j][1] += mask_value;
-              if (rc0 != reg1) s[j][2] += mask_value;
-              if (rc1 != reg1) s[j][3] += mask_value;
-            }
-            mx0 = fmaxf(mx0, fmaxf(s[j][0], s[j][1]));
-            mx1 = fmaxf(mx1, fmaxf(s[j][2], s[j][3]));
+          const int ct = (WS == 16 ? (j >> 1) * TW + 8 * (j & 1) : j * TW);     // key (c0 + 8j + q2 + e): jy * TW + jx, less q2 + e
+          const float2 rk = *reinterpret_cast<const float2*>(rkp + j * 8);
+          s[j][0] = fmaf(s[j][0] * rq0, rk.x, b0[-ct]);
+          s[j][1] = fmaf(s[j][1] * rq0, rk.y, b0[-ct - 1]);
+          s[j][2] = fmaf(s[j][2] * rq1, rk.x, b1[-ct]);
+          s[j][3] = fmaf(s[j][3] * rq1, rk.y, b1[-ct - 1]);
+        }
+        if (masked) {   // shift mask, only in the last window row / column of a shifted block
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const uint32_t rc = *reinterpret_cast<const uint16_t*>(region_s + c0 + j * 8 + q2);
+            const int rc0 = static_cast<int>(rc & 0xffu), rc1 = static_cast<int>(rc >> 8);
+            if (rc0 != reg0) s[j][0] += mask_l2;
+            if (rc1 != reg0) s[j][1] += mask_l2;
+            if (rc0 != reg1) s[j][2] += mask_l2;
+            if (rc1 != reg1) s[j][3] += mask_l2;
           }
+        }
+        float mx0 = fmaxf(s[0][0], s[0][1]), mx1 = fmaxf(s[0][2], s[0][3]);
+#pragma unroll
+        for (int j = 1; j < 8; ++j) {
+          mx0 = fmaxf(mx0, fmaxf(s[j][0], s[j][1]));
+          mx1 = fmaxf(mx1, fmaxf(s[j][2], s[j][3]));
         }
         mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
         mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
         // ---- online softmax: rescale the running sums to the new row maximum ----
         const float mn0 = fmaxf(mrun0, mx0), mn1 = fmaxf(mrun1, mx1);
-        const float corr0 = __expf(mrun0 - mn0), corr1 = __expf(mrun1 - mn1);
+        const float corr0 = ex2_ftz(mrun0 - mn0), corr1 = ex2_ftz(mrun1 - mn1);
         mrun0 = mn0; mrun1 = mn1;
-        l0 *= corr0; l1 *= corr1;
 #pragma unroll
-        for (int n = 0; n < 4; ++n) { o[n][0] *= corr0; o[n][1] *= corr0; o[n][2] *= corr1; o[n][3] *= corr1; }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          if (j < nt) {
-            s[j][0] = __expf(s[j][0] - mn0); s[j][1] = __expf(s[j][1] - mn0);
-            s[j][2] = __expf(s[j][2] - mn1); s[j][3] = __expf(s[j][3] - mn1);
-            l0 += s[j][0] + s[j][1];
-            l1 += s[j][2] + s[j][3];
-          }
-        }
-        // ---- O += P V  (P re-used in registers as the A operand) ----
+        for (int n = 0; n < 5; ++n) { o[n][0] *= corr0; o[n][1] *= corr0; o[n][2] *= corr1; o[n][3] *= corr1; }
+        // ---- O += P V, row sums += P 1  (P re-used in registers as the A operand) ----
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
-          if (2 * kk < nt) {
-            uint32_t pa[4];
-            pa[0] = Half16<T>::pack(s[2 * kk][0], s[2 * kk][1]);
-            pa[1] = Half16<T>::pack(s[2 * kk][2], s[2 * kk][3]);
-            pa[2] = Half16<T>::pack(s[2 * kk + 1][0], s[2 * kk + 1][1]);
-            pa[3] = Half16<T>::pack(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+          uint32_t pa[4];
+          pa[0] = Half16<T>::pack(ex2_ftz(s[2 * kk][0] - mn0), ex2_ftz(s[2 * kk][1] - mn0));
+          pa[1] = Half16<T>::pack(ex2_ftz(s[2 * kk][2] - mn1), ex2_ftz(s[2 * kk][3] - mn1));
+          pa[2] = Half16<T>::pack(ex2_ftz(s[2 * kk + 1][0] - mn0), ex2_ftz(s[2 * kk + 1][1] - mn0));
+          pa[3] = Half16<T>::pack(ex2_ftz(s[2 * kk + 1][2] - mn1), ex2_ftz(s[2 * kk + 1][3] - mn1));
 #pragma unroll
-            for (int np = 0; np < 2; ++np) {
-              uint32_t vb[4];
-              ldsm_x4_t(vb, Vs + row_off(c0 + kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, np * 2 + (lane >> 4)));
-              mma_16816<T>(o[2 * np], pa, vb[0], vb[1]);
-              mma_16816<T>(o[2 * np + 1], pa, vb[2], vb[3]);
-            }
+          for (int np = 0; np < 2; ++np) {
+            uint32_t vb[4];
+            ldsm_x4_t(vb, Vs + row_off(c0 + kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, np * 2 + (lane >> 4)));
+            mma_16816<T>(o[2 * np], pa, vb[0], vb[1]);
+            mma_16816<T>(o[2 * np + 1], pa, vb[2], vb[3]);
           }
+          mma_16816<T>(o[4], pa, Ones16<T>::v, Ones16<T>::v);
         }
       }
-      l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
-      l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
-      const float inv0 = 1.0f / l0, inv1 = 1.0f / l1;
+      const float inv0 = 1.0f / o[4][0], inv1 = 1.0f / o[4][2];
       // ---- store (head merge folded into the column offset) ----
 #pragma unroll
       for (int n = 0; n < 4; ++n) {
-        const int col = h * 32 + n * 8 + (lane & 3) * 2;
+        const int col = h * 32 + n * 8 + q2;
         *reinterpret_cast<uint32_t*>(out + (row0 + r0) * C + col) = Half16<T>::pack(o[n][0] * inv0, o[n][1] * inv0);
         *reinterpret_cast<uint32_t*>(out + (row0 + r1) * C + col) = Half16<T>::pack(o[n][2] * inv1, o[n][3] * inv1);
       }
@@ -285,15 +296,15 @@ swinv2_attn_f32_kernel(const float* __restrict__ qkv, const float* __restrict__ 
   }
 }
 
-template <typename T>
+template <typename T, int WS>
 static int launch_v2_t(const void* qkv, const float* bias_tab, const float* logit_scale, void* out, int num_windows, int C, int heads,
                        const WinGeom& g, int nW, float mask_value, cudaStream_t stream) {
-  auto kern = swinv2_attn_kernel<T>;
-  const int smem = v2_smem_bytes(g.ws);
-  static int configured = 0;
-  if (configured < smem) {
-    CSVIT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, v2_smem_bytes(16)));
-    configured = v2_smem_bytes(16);
+  auto kern = swinv2_attn_kernel<T, WS>;
+  const int smem = v2_smem_bytes(WS);
+  static bool configured = false;
+  if (!configured) {
+    CSVIT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
   }
   int per_head = num_windows;
   const int cap = (num_sms() * 4) / heads > 0 ? (num_sms() * 4) / heads : 1;
@@ -308,8 +319,8 @@ int launch_swinv2_window_attention(const void* qkv, const float* bias_tab, const
                                    int W, int C, int heads, int ws, int shift, int mask_repeat, cudaStream_t stream) {
   CSVIT_REQUIRE(C == heads * 32, "swinv2_window_attention: head_dim must be 32 (C=%d heads=%d)", C, heads);
   CSVIT_REQUIRE(ws > 0 && H % ws == 0 && W % ws == 0, "swinv2_window_attention: %dx%d not divisible by window %d", H, W, ws);
-  CSVIT_REQUIRE((ws * ws) % 16 == 0 && ws * ws <= V2_MAXL, "swinv2_window_attention: window %d not built (ws^2 must be a multiple of 16, <= %d)",
-                ws, V2_MAXL);
+  CSVIT_REQUIRE(ws * ws <= V2_MAXL, "swinv2_window_attention: window %d not built (at most %d tokens per window)", ws, V2_MAXL);
+  CSVIT_REQUIRE(dtype == DT_F32 || ws == 16 || ws == 8, "swinv2_window_attention: window %d not built (16-bit kernel: windows 16 and 8)", ws);
   CSVIT_REQUIRE(shift >= 0 && shift < ws, "swinv2_window_attention: shift %d outside [0,%d)", shift, ws);
   const int nW = (H / ws) * (W / ws);
   const long long items = static_cast<long long>(B) * nW * heads;
@@ -317,8 +328,10 @@ int launch_swinv2_window_attention(const void* qkv, const float* bias_tab, const
   CSVIT_REQUIRE(items < (1ll << 31), "swinv2_window_attention: too many work items");
   const WinGeom g = make_geom(H, W, ws, shift);
   const float mask_value = -100.0f * static_cast<float>(mask_repeat);
-  if (dtype == DT_BF16) return launch_v2_t<__nv_bfloat16>(qkv, bias_tab, logit_scale, out, B * nW, C, heads, g, nW, mask_value, stream);
-  if (dtype == DT_F16) return launch_v2_t<__half>(qkv, bias_tab, logit_scale, out, B * nW, C, heads, g, nW, mask_value, stream);
+  if (dtype == DT_BF16 && ws == 16) return launch_v2_t<__nv_bfloat16, 16>(qkv, bias_tab, logit_scale, out, B * nW, C, heads, g, nW, mask_value, stream);
+  if (dtype == DT_BF16) return launch_v2_t<__nv_bfloat16, 8>(qkv, bias_tab, logit_scale, out, B * nW, C, heads, g, nW, mask_value, stream);
+  if (dtype == DT_F16 && ws == 16) return launch_v2_t<__half, 16>(qkv, bias_tab, logit_scale, out, B * nW, C, heads, g, nW, mask_value, stream);
+  if (dtype == DT_F16) return launch_v2_t<__half, 8>(qkv, bias_tab, logit_scale, out, B * nW, C, heads, g, nW, mask_value, stream);
   CSVIT_REQUIRE(dtype == DT_F32, "swinv2_window_attention: bad dtype %d", dtype);
   const int L = ws * ws, tw = 2 * ws - 1;
   const int smem = (2 * L * 33 + L + 4 * L + 4 * 32 + tw * tw + L) * 4;

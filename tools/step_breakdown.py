@@ -9,11 +9,12 @@ from cs_vit.synthetic import make_inputs, make_random_backbone_dir, randomize_he
 from cs_vit.utils.mano_standin import SyntheticMANO
 
 B = int(os.environ.get("B", "256")); prec = os.environ.get("PREC", "bf16")
-bdir = make_random_backbone_dir(os.path.join(tempfile.mkdtemp(), "b"), "swin_b", 0)
+VARIANT = os.environ.get("VARIANT", "swin_b"); S = 256 if VARIANT.startswith("swinv2") else 224
+bdir = make_random_backbone_dir(os.path.join(tempfile.mkdtemp(), "b"), VARIANT, 0, image_size=S)
 torch.manual_seed(0)
-m = Poser(bdir, image_size=224, mano_layer=SyntheticMANO(), spatial_layer_type="encoder", persp_decorate="patch", precision=prec)
+m = Poser(bdir, image_size=S, mano_layer=SyntheticMANO(), spatial_layer_type="encoder", persp_decorate="patch", precision=prec)
 randomize_head_(m); m.phase(Poser.TrainingPhase.SPATIAL); m.eval(); m = m.cuda()
-inp = {k: v.cuda() for k, v in make_inputs(B, 1, 224, seed=3).items()}
+inp = {k: v.cuda() for k, v in make_inputs(B, 1, S, seed=3).items()}
 def step():
     with torch.no_grad():
         return m.predict_batch(inp["patches"], inp["square_bboxes"], inp["timestamp"], inp["focal"], inp["princpt"])
@@ -28,7 +29,7 @@ e1.record(); torch.cuda.synchronize()
 total = e0.elapsed_time(e1) / 5
 print(f"step {total:.3f} ms  -> {B / total * 1e3:.0f} img/s")
 acc = 0
-for name in ("csvit_linear", "csvit_linear_emit", "csvit_linear_lnfold", "csvit_mlp_fused", "csvit_window_attention", "csvit_layernorm", "csvit_attention", "csvit_affine_rows", "csvit_patch_im2col"):
+for name in ("csvit_linear", "csvit_linear_emit", "csvit_linear_lnfold", "csvit_mlp_fused", "csvit_window_attention", "csvit_swinv2_window_attention", "csvit_layernorm_post", "csvit_layernorm", "csvit_attention", "csvit_affine_rows", "csvit_patch_im2col"):
     ops.begin_profile(name)
     for _ in range(3): step()
     p = ops.end_profile()

@@ -199,6 +199,18 @@ def peaks():
         return 1400.0, 6650.0, "fallback"
 
 
+def gemm_traffic(a):
+    """DRAM bytes per GEMM launch from the committed ncu capture of this exact workload (profiles/r1_gemm_dram_traffic.json);
+    None for any other workload / variant / batch."""
+    if a.variant != "swin_b" or a.workload != "spatial" or a.batch != BATCH:
+        return None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_gemm_dram_traffic.json")) as f:
+            return json.load(f)["traffic_bytes_per_launch"]
+    except Exception:
+        return None
+
+
 def run_ours(a):
     import torch.distributed as dist
     from cs_vit import ops
@@ -317,7 +329,7 @@ def run_ours(a):
             ach = prof["flops"] / (prof["ms"] / 1e3) / 1e12
             out["roofline"] = {"bound": "tensor", "kernel": "gemm_tc_kernel (csvit_linear: every Linear of backbone and head)",
                                "achieved": round(ach, 1), "peak": peak_tf, "unit": "TFLOP/s", "frac": round(ach / peak_tf, 4),
-                               "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peak_kind})", "traffic": None,
+                               "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peak_kind})", "traffic": gemm_traffic(a),
                                "launches_per_step": prof["launches"] // a.steps,
                                "share_of_step": round(prof["ms"] / a.steps / (ms_total / a.steps), 3),
                                "avg_launch_us": round(1e3 * prof["ms"] / prof["launches"], 2)}

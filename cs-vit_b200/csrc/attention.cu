@@ -30,6 +30,17 @@ constexpr int WA_ROW = 64;                                    // bytes per row (
 constexpr int WA_WARP_BYTES = (3 * WA_L + 15) * WA_ROW + 64;  // + region ids
 constexpr int WA_WARPS = 4;
 constexpr int WA_BIAS_BYTES = 4 * 7 * 32 * 16;                // one head's fragment-ordered bias table
+constexpr float WA_LOG2E = 1.4426950408889634f;
+// Softmax in the log2 domain: log2(e) is folded into the logit scale, the bias table (csvit_expand_rel_bias_mma) and the mask
+// value, so each probability costs one FADD and one MUFU.EX2 (expf's range fix-up alone is four more instructions).
+__device__ __forceinline__ float wa_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+template <typename T> struct WaOnes;
+template <> struct WaOnes<__nv_bfloat16> { static constexpr uint32_t v = 0x3F803F80u; };
+template <> struct WaOnes<__half> { static constexpr uint32_t v = 0x3C003C00u; };
 __device__ __forceinline__ uint32_t wa_off(int row, int chunk) { return uint32_t(row * WA_ROW + ((chunk ^ ((row >> 1) & 3)) << 4)); }
 
 __device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const void* p) {
@@ -75,7 +86,7 @@ __global__ void expand_rel_bias_mma_kernel(const float* __restrict__ table, floa
   float v;
   if (col >= WA_L) v = -INFINITY;
   else if (row >= WA_L) v = 0.f;
-  else v = table[rel_pos_index(7, row, col) * heads + h];
+  else v = table[rel_pos_index(7, row, col) * heads + h] * WA_LOG2E;   // the kernel's logits live in the log2 domain
   out[idx] = v;
 }
 
@@ -160,8 +171,8 @@ win_attn_warp_kernel(const T* __restrict__ qkv, const float4* __restrict__ bias_
           for (int e = 0; e < 2; ++e) {
             const int c = j * 8 + (lane & 3) * 2 + e;
             const int rc = region_s[c < WA_L ? c : WA_L - 1];
-            if (rc != reg0) s[j][e] += -100.0f;
-            if (rc != reg1) s[j][2 + e] += -100.0f;
+            if (rc != reg0) s[j][e] += -100.0f * WA_LOG2E;
+            if (rc != reg1) s[j][2 + e] += -100.0f * WA_LOG2E;
           }
         }
       }
@@ -173,29 +184,19 @@ win_attn_warp_kernel(const T* __restrict__ qkv, const float4* __restrict__ bias_
       }
       mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
       mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-      float sum0 = 0.f, sum1 = 0.f;
+      // ---- O = P V with unnormalised P re-used in registers as the A operand; a ones column (o[4]) yields the row sums of the
+      //      ROUNDED probabilities on the tensor core, so the weights that multiply V sum to exactly one ----
+      float o[5][4];
 #pragma unroll
-      for (int j = 0; j < 7; ++j) {
-        s[j][0] = __expf(s[j][0] - mx0); s[j][1] = __expf(s[j][1] - mx0);
-        s[j][2] = __expf(s[j][2] - mx1); s[j][3] = __expf(s[j][3] - mx1);
-        sum0 += s[j][0] + s[j][1];
-        sum1 += s[j][2] + s[j][3];
-      }
-      sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1); sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
-      sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1); sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
-      const float inv0 = 1.0f / sum0, inv1 = 1.0f / sum1;
-      // ---- O = P V  (P re-used in registers as the A operand) ----
-      float o[4][4];
-#pragma unroll
-      for (int n = 0; n < 4; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
+      for (int n = 0; n < 5; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
 #pragma unroll
       for (int kk = 0; kk < 4; ++kk) {
         uint32_t pa[4];
-        pa[0] = Half16<T>::pack(s[2 * kk][0] * inv0, s[2 * kk][1] * inv0);
-        pa[1] = Half16<T>::pack(s[2 * kk][2] * inv1, s[2 * kk][3] * inv1);
+        pa[0] = Half16<T>::pack(wa_ex2(s[2 * kk][0] - mx0), wa_ex2(s[2 * kk][1] - mx0));
+        pa[1] = Half16<T>::pack(wa_ex2(s[2 * kk][2] - mx1), wa_ex2(s[2 * kk][3] - mx1));
         if (2 * kk + 1 < 7) {
-          pa[2] = Half16<T>::pack(s[2 * kk + 1][0] * inv0, s[2 * kk + 1][1] * inv0);
-          pa[3] = Half16<T>::pack(s[2 * kk + 1][2] * inv1, s[2 * kk + 1][3] * inv1);
+          pa[2] = Half16<T>::pack(wa_ex2(s[2 * kk + 1][0] - mx0), wa_ex2(s[2 * kk + 1][1] - mx0));
+          pa[3] = Half16<T>::pack(wa_ex2(s[2 * kk + 1][2] - mx1), wa_ex2(s[2 * kk + 1][3] - mx1));
         } else {
           pa[2] = 0u; pa[3] = 0u;
         }
@@ -206,13 +207,15 @@ win_attn_warp_kernel(const T* __restrict__ qkv, const float4* __restrict__ bias_
           mma_16816<T>(o[2 * np], pa, vb[0], vb[1]);
           mma_16816<T>(o[2 * np + 1], pa, vb[2], vb[3]);
         }
+        mma_16816<T>(o[4], pa, WaOnes<T>::v, WaOnes<T>::v);
       }
+      const float inv0 = 1.0f / o[4][0], inv1 = 1.0f / o[4][2];
       // ---- store (head merge folded into the column offset) ----
 #pragma unroll
       for (int n = 0; n < 4; ++n) {
         const int col = h * 32 + n * 8 + (lane & 3) * 2;
-        if (r0 < WA_L) *reinterpret_cast<uint32_t*>(out + (row0 + r0) * C + col) = Half16<T>::pack(o[n][0], o[n][1]);
-        if (r1 < WA_L) *reinterpret_cast<uint32_t*>(out + (row0 + r1) * C + col) = Half16<T>::pack(o[n][2], o[n][3]);
+        if (r0 < WA_L) *reinterpret_cast<uint32_t*>(out + (row0 + r0) * C + col) = Half16<T>::pack(o[n][0] * inv0, o[n][1] * inv0);
+        if (r1 < WA_L) *reinterpret_cast<uint32_t*>(out + (row0 + r1) * C + col) = Half16<T>::pack(o[n][2] * inv1, o[n][3] * inv1);
       }
     }
     __syncwarp();  // all lanes are done with this window's tiles before the next cp.async overwrites them
@@ -242,7 +245,7 @@ static int launch_wa(const void* qkv, const float* bias_frag, void* out, int num
   if (per_head > cap) per_head = cap;
   kern<<<per_head * heads, WA_WARPS * 32, smem, stream>>>(static_cast<const T*>(qkv), reinterpret_cast<const float4*>(bias_frag),
                                                           static_cast<T*>(out), num_windows, C, heads, g, nW,
-                                                          0.17677669529663687f);
+                                                          0.17677669529663687f * WA_LOG2E);
   CSVIT_CUDA(cudaGetLastError());
   return 0;
 }

@@ -131,7 +131,8 @@ CSVIT_API int csvit_set_gemm_tuning(int cluster, int tma_store, int max_ctas, in
  * bf16 / fp16: tensor-core kernel (window 7, head_dim 32).  fp32: exact kernel (validation mode).
  * fp32 reads `bias` = the [heads, L, L] table of csvit_expand_rel_bias; the 16-bit kernel reads `bias_mma` = the
  * same values pre-arranged in MMA accumulator-fragment order by csvit_expand_rel_bias_mma
- * ([heads, 4, 7, 32, 4] floats, -inf in the padding columns).  The unused one may be NULL.
+ * ([heads, 4, 7, 32, 4] floats, multiplied by log2(e) - that kernel's softmax runs in the log2 domain - with -inf in the
+ * padding columns).  The unused one may be NULL.
  * 16-bit dtypes: two kernels exist.  The mma.sync kernel (needs `bias_mma`) is the default because it is faster at
  * 49-token windows; the tcgen05/TMEM kernel (two windows per block-diagonal 128-row tile, needs `bias`) runs after
  * csvit_set_attention_impl(1) or when only `bias` is given. */

@@ -77,6 +77,15 @@ ln_rows_kernel(const float* __restrict__ x, const float* __restrict__ gamma, con
       }
     }
   }
+  // scatter destination of row row0 + r, evaluated by lane r (the map costs six integer divisions: done once per lane instead of
+  // 32 times per row, it no longer dominates the instruction stream of narrow rows)
+  int my_drow = 0;
+  const bool scatter = mode == LN_WINDOW && C >= scatter_min_c;
+  if (scatter && lane < R && row0 + lane < rows) {
+    const int row = row0 + lane;
+    const int b = row / g.N, t = row - b * g.N;
+    my_drow = b * g.N + win_token_to_row(g, t);      // rows < 2^31 (checked by the launcher's int row count)
+  }
 #pragma unroll
   for (int r = 0; r < R; ++r) {
     const int row = row0 + r;
@@ -95,10 +104,7 @@ ln_rows_kernel(const float* __restrict__ x, const float* __restrict__ gamma, con
     }
     const float rstd = rsqrtf(warp_sum(sq) / float(Cout) + eps);
     long long drow = row;
-    if (mode == LN_WINDOW && C >= scatter_min_c) {
-      const int b = row / g.N, t = row - b * g.N;
-      drow = static_cast<long long>(b) * g.N + win_token_to_row(g, t);
-    }
+    if (scatter) drow = __shfl_sync(0xffffffffu, my_drow, r);
     OutT* orow = out + drow * ldo;
 #pragma unroll
     for (int j = 0; j < MAXJ; ++j) {

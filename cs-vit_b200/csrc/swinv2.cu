@@ -397,6 +397,21 @@ ln_post_kernel(const float* y, long long ldy, const float* resid, const float* _
         }
       }
     }
+    // copy destination (row, column block) of token row0 + r, evaluated once by lane r and broadcast below
+    int my_crow = 0, my_ccol = 0;
+    if (lane < R && row0 + lane < rows) {
+      const int row = row0 + lane;
+      my_crow = row;
+      if (copy_mode == COPY_WINDOW) {
+        const int b = row / g.N, t = row - b * g.N;
+        my_crow = b * g.N + win_token_to_row(g, t);
+      } else if (copy_mode == COPY_MERGE2X2) {
+        const int b = row / g.N, t = row - b * g.N;
+        const int ty = t / g.W, tx = t - ty * g.W;
+        my_crow = b * (g.N >> 2) + (ty >> 1) * (g.W >> 1) + (tx >> 1);
+        my_ccol = ((ty & 1) + 2 * (tx & 1)) * C;
+      }
+    }
 #pragma unroll
     for (int r = 0; r < R; ++r) {
       const int row = row0 + r;
@@ -415,17 +430,8 @@ ln_post_kernel(const float* y, long long ldy, const float* resid, const float* _
         }
       }
       const float rstd = rsqrtf(warp_sum(sq) / float(C) + eps);
-      long long crow = row;
-      int ccol = 0;
-      if (copy_mode == COPY_WINDOW) {
-        const int b = row / g.N, t = row - b * g.N;
-        crow = static_cast<long long>(b) * g.N + win_token_to_row(g, t);
-      } else if (copy_mode == COPY_MERGE2X2) {
-        const int b = row / g.N, t = row - b * g.N;
-        const int ty = t / g.W, tx = t - ty * g.W;
-        crow = static_cast<long long>(b) * (g.N >> 2) + (ty >> 1) * (g.W >> 1) + (tx >> 1);
-        ccol = ((ty & 1) + 2 * (tx & 1)) * C;
-      }
+      const long long crow = __shfl_sync(0xffffffffu, my_crow, r);
+      const int ccol = __shfl_sync(0xffffffffu, my_ccol, r);
 #pragma unroll
       for (int j = 0; j < MAXJ; ++j) {
         const int i4 = lane + 32 * j;

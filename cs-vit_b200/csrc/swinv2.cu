@@ -53,6 +53,9 @@ template <> struct Ones16<__nv_bfloat16> { static constexpr uint32_t v = 0x3F803
 template <> struct Ones16<__half> { static constexpr uint32_t v = 0x3C003C00u; };
 
 constexpr float V2_LOG2E = 1.4426950408889634f;
+#ifndef V2_TILES16
+#define V2_TILES16 2   // query tiles per warp pass for 256-token windows (1 = one tile, 4 CTAs/SM; 2 = two tiles, 3 CTAs/SM)
+#endif
 
 // qkv: window-ordered tokens [B*N, 3C] (Q | K | V column blocks, head h at columns 32h), out [B*N, C] window-ordered.
 // bias_tab [heads, (2ws-1)^2] = 16 sigmoid(cpb_mlp(coords)) (V2:460-472), logit_scale [heads] = exp(min(ls, ln 100)).
@@ -64,8 +67,8 @@ constexpr float V2_LOG2E = 1.4426950408889634f;
 //   * the bias address is (per-thread row base) - (compile-time column term): one LDS with an immediate offset, no index math
 //   * row sums come out of the tensor core: P V is extended by a ones column (one extra MMA per 16 keys), which also makes the
 //     normaliser the sum of the ROUNDED probabilities that multiply V
-template <typename T, int WS>
-__global__ void __launch_bounds__(V2_THREADS, 4)
+template <typename T, int WS, int TILES>
+__global__ void __launch_bounds__(V2_THREADS, TILES == 2 ? 3 : 4)
 swinv2_attn_kernel(const T* __restrict__ qkv, const float* __restrict__ bias_tab, const float* __restrict__ logit_scale,
                    T* __restrict__ out, int num_windows, int C, int heads, WinGeom g, int nW, float mask_value) {
   static_assert(WS == 8 || WS == 16, "windows of 8x8 and 16x16 tokens");
@@ -122,100 +125,133 @@ swinv2_attn_kernel(const T* __restrict__ qkv, const float* __restrict__ bias_tab
     }
     __syncthreads();
 
+    // A warp walks TILES 16-row query tiles at once: the K / V fragments it pulls from shared memory feed TILES MMAs each and the
+    // TILES softmax chains are independent, which is what hides the MMA -> softmax -> MMA latency at 12-16 warps per SM.
 #pragma unroll 1
-    for (int mt = warp; mt < L / 16; mt += V2_THREADS / 32) {
-      const int m0 = mt * 16;
-      uint32_t qa[2][4];
+    for (int mg = warp; mg < L / (16 * TILES); mg += V2_THREADS / 32) {
+      uint32_t qa[TILES][2][4];
+      float rq0[TILES], rq1[TILES], mrun0[TILES], mrun1[TILES];
+      const float* bp0[TILES];
+      const float* bp1[TILES];
+      int reg0[TILES], reg1[TILES];
+      float o[TILES][5][4];   // o[t][4] = running row sums (ones column)
 #pragma unroll
-      for (int ks = 0; ks < 2; ++ks)
-        ldsm_x4(qa[ks], Qs + row_off(m0 + (lane & 7) + ((lane >> 3) & 1) * 8, ks * 2 + (lane >> 4)));
-      const int r0 = m0 + (lane >> 2), r1 = r0 + 8;
-      const float rq0 = rq_s[r0], rq1 = rq_s[r1];
-      // rel_pos_index(i, j) = (iy - jy + WS-1) TW + (ix - jx + WS-1): per-thread row base minus a compile-time column term
-      const float* bp0 = bias_s + ((r0 / WS) * TW + (r0 % WS) + (WS - 1) * (TW + 1) - q2);
-      const float* bp1 = bias_s + ((r1 / WS) * TW + (r1 % WS) + (WS - 1) * (TW + 1) - q2);
-      int reg0 = 0, reg1 = 0;
-      if (masked) { reg0 = region_s[r0]; reg1 = region_s[r1]; }
-      float mrun0 = -INFINITY, mrun1 = -INFINITY;
-      float o[5][4];   // o[4] = running row sums (ones column)
+      for (int t = 0; t < TILES; ++t) {
+        const int m0 = (mg * TILES + t) * 16;
 #pragma unroll
-      for (int n = 0; n < 5; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
+        for (int ks = 0; ks < 2; ++ks)
+          ldsm_x4(qa[t][ks], Qs + row_off(m0 + (lane & 7) + ((lane >> 3) & 1) * 8, ks * 2 + (lane >> 4)));
+        const int r0 = m0 + (lane >> 2), r1 = r0 + 8;
+        rq0[t] = rq_s[r0]; rq1[t] = rq_s[r1];
+        // rel_pos_index(i, j) = (iy - jy + WS-1) TW + (ix - jx + WS-1): per-thread row base minus a compile-time column term
+        bp0[t] = bias_s + ((r0 / WS) * TW + (r0 % WS) + (WS - 1) * (TW + 1) - q2);
+        bp1[t] = bias_s + ((r1 / WS) * TW + (r1 % WS) + (WS - 1) * (TW + 1) - q2);
+        reg0[t] = reg1[t] = 0;
+        if (masked) { reg0[t] = region_s[r0]; reg1[t] = region_s[r1]; }
+        mrun0[t] = mrun1[t] = -INFINITY;
+#pragma unroll
+        for (int n = 0; n < 5; ++n) o[t][n][0] = o[t][n][1] = o[t][n][2] = o[t][n][3] = 0.f;
+      }
 
 #pragma unroll 1
       for (int c0 = 0; c0 < L; c0 += 64) {
-        float s[8][4];
+        float s[TILES][8][4];
         // ---- S = Q K^T on the raw 16-bit operands ----
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
           uint32_t kb[4];
           ldsm_x4(kb, Ks + row_off(c0 + j * 8 + (lane & 7), lane >> 3));
-          mma_16816<T>(s[j], qa[0], kb[0], kb[1]);
-          mma_16816<T>(s[j], qa[1], kb[2], kb[3]);
+#pragma unroll
+          for (int t = 0; t < TILES; ++t) {
+            s[t][j][0] = s[t][j][1] = s[t][j][2] = s[t][j][3] = 0.f;
+            mma_16816<T>(s[t][j], qa[t][0], kb[0], kb[1]);
+            mma_16816<T>(s[t][j], qa[t][1], kb[2], kb[3]);
+          }
         }
         // ---- cosine scaling, continuous position bias (log2 domain, fp32) ----
-        const float* b0 = bp0 - (c0 / WS) * TW;
-        const float* b1 = bp1 - (c0 / WS) * TW;
         const float* rkp = rk_s + c0 + q2;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const int ct = (WS == 16 ? (j >> 1) * TW + 8 * (j & 1) : j * TW);     // key (c0 + 8j + q2 + e): jy * TW + jx, less q2 + e
           const float2 rk = *reinterpret_cast<const float2*>(rkp + j * 8);
-          s[j][0] = fmaf(s[j][0] * rq0, rk.x, b0[-ct]);
-          s[j][1] = fmaf(s[j][1] * rq0, rk.y, b0[-ct - 1]);
-          s[j][2] = fmaf(s[j][2] * rq1, rk.x, b1[-ct]);
-          s[j][3] = fmaf(s[j][3] * rq1, rk.y, b1[-ct - 1]);
+#pragma unroll
+          for (int t = 0; t < TILES; ++t) {
+            const float* b0 = bp0[t] - (c0 / WS) * TW;
+            const float* b1 = bp1[t] - (c0 / WS) * TW;
+            s[t][j][0] = fmaf(s[t][j][0] * rq0[t], rk.x, b0[-ct]);
+            s[t][j][1] = fmaf(s[t][j][1] * rq0[t], rk.y, b0[-ct - 1]);
+            s[t][j][2] = fmaf(s[t][j][2] * rq1[t], rk.x, b1[-ct]);
+            s[t][j][3] = fmaf(s[t][j][3] * rq1[t], rk.y, b1[-ct - 1]);
+          }
         }
         if (masked) {   // shift mask, only in the last window row / column of a shifted block
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const uint32_t rc = *reinterpret_cast<const uint16_t*>(region_s + c0 + j * 8 + q2);
             const int rc0 = static_cast<int>(rc & 0xffu), rc1 = static_cast<int>(rc >> 8);
-            if (rc0 != reg0) s[j][0] += mask_l2;
-            if (rc1 != reg0) s[j][1] += mask_l2;
-            if (rc0 != reg1) s[j][2] += mask_l2;
-            if (rc1 != reg1) s[j][3] += mask_l2;
+#pragma unroll
+            for (int t = 0; t < TILES; ++t) {
+              if (rc0 != reg0[t]) s[t][j][0] += mask_l2;
+              if (rc1 != reg0[t]) s[t][j][1] += mask_l2;
+              if (rc0 != reg1[t]) s[t][j][2] += mask_l2;
+              if (rc1 != reg1[t]) s[t][j][3] += mask_l2;
+            }
           }
         }
-        float mx0 = fmaxf(s[0][0], s[0][1]), mx1 = fmaxf(s[0][2], s[0][3]);
+        float mn0[TILES], mn1[TILES];
 #pragma unroll
-        for (int j = 1; j < 8; ++j) {
-          mx0 = fmaxf(mx0, fmaxf(s[j][0], s[j][1]));
-          mx1 = fmaxf(mx1, fmaxf(s[j][2], s[j][3]));
+        for (int t = 0; t < TILES; ++t) {
+          float mx0 = fmaxf(s[t][0][0], s[t][0][1]), mx1 = fmaxf(s[t][0][2], s[t][0][3]);
+#pragma unroll
+          for (int j = 1; j < 8; ++j) {
+            mx0 = fmaxf(mx0, fmaxf(s[t][j][0], s[t][j][1]));
+            mx1 = fmaxf(mx1, fmaxf(s[t][j][2], s[t][j][3]));
+          }
+          mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+          mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+          // ---- online softmax: rescale the running sums to the new row maximum ----
+          mn0[t] = fmaxf(mrun0[t], mx0); mn1[t] = fmaxf(mrun1[t], mx1);
+          const float corr0 = ex2_ftz(mrun0[t] - mn0[t]), corr1 = ex2_ftz(mrun1[t] - mn1[t]);
+          mrun0[t] = mn0[t]; mrun1[t] = mn1[t];
+#pragma unroll
+          for (int n = 0; n < 5; ++n) { o[t][n][0] *= corr0; o[t][n][1] *= corr0; o[t][n][2] *= corr1; o[t][n][3] *= corr1; }
         }
-        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
-        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-        // ---- online softmax: rescale the running sums to the new row maximum ----
-        const float mn0 = fmaxf(mrun0, mx0), mn1 = fmaxf(mrun1, mx1);
-        const float corr0 = ex2_ftz(mrun0 - mn0), corr1 = ex2_ftz(mrun1 - mn1);
-        mrun0 = mn0; mrun1 = mn1;
-#pragma unroll
-        for (int n = 0; n < 5; ++n) { o[n][0] *= corr0; o[n][1] *= corr0; o[n][2] *= corr1; o[n][3] *= corr1; }
         // ---- O += P V, row sums += P 1  (P re-used in registers as the A operand) ----
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
-          uint32_t pa[4];
-          pa[0] = Half16<T>::pack(ex2_ftz(s[2 * kk][0] - mn0), ex2_ftz(s[2 * kk][1] - mn0));
-          pa[1] = Half16<T>::pack(ex2_ftz(s[2 * kk][2] - mn1), ex2_ftz(s[2 * kk][3] - mn1));
-          pa[2] = Half16<T>::pack(ex2_ftz(s[2 * kk + 1][0] - mn0), ex2_ftz(s[2 * kk + 1][1] - mn0));
-          pa[3] = Half16<T>::pack(ex2_ftz(s[2 * kk + 1][2] - mn1), ex2_ftz(s[2 * kk + 1][3] - mn1));
+          uint32_t pa[TILES][4];
+#pragma unroll
+          for (int t = 0; t < TILES; ++t) {
+            pa[t][0] = Half16<T>::pack(ex2_ftz(s[t][2 * kk][0] - mn0[t]), ex2_ftz(s[t][2 * kk][1] - mn0[t]));
+            pa[t][1] = Half16<T>::pack(ex2_ftz(s[t][2 * kk][2] - mn1[t]), ex2_ftz(s[t][2 * kk][3] - mn1[t]));
+            pa[t][2] = Half16<T>::pack(ex2_ftz(s[t][2 * kk + 1][0] - mn0[t]), ex2_ftz(s[t][2 * kk + 1][1] - mn0[t]));
+            pa[t][3] = Half16<T>::pack(ex2_ftz(s[t][2 * kk + 1][2] - mn1[t]), ex2_ftz(s[t][2 * kk + 1][3] - mn1[t]));
+          }
 #pragma unroll
           for (int np = 0; np < 2; ++np) {
             uint32_t vb[4];
             ldsm_x4_t(vb, Vs + row_off(c0 + kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, np * 2 + (lane >> 4)));
-            mma_16816<T>(o[2 * np], pa, vb[0], vb[1]);
-            mma_16816<T>(o[2 * np + 1], pa, vb[2], vb[3]);
+#pragma unroll
+            for (int t = 0; t < TILES; ++t) {
+              mma_16816<T>(o[t][2 * np], pa[t], vb[0], vb[1]);
+              mma_16816<T>(o[t][2 * np + 1], pa[t], vb[2], vb[3]);
+            }
           }
-          mma_16816<T>(o[4], pa, Ones16<T>::v, Ones16<T>::v);
+#pragma unroll
+          for (int t = 0; t < TILES; ++t) mma_16816<T>(o[t][4], pa[t], Ones16<T>::v, Ones16<T>::v);
         }
       }
-      const float inv0 = 1.0f / o[4][0], inv1 = 1.0f / o[4][2];
       // ---- store (head merge folded into the column offset) ----
 #pragma unroll
-      for (int n = 0; n < 4; ++n) {
-        const int col = h * 32 + n * 8 + q2;
-        *reinterpret_cast<uint32_t*>(out + (row0 + r0) * C + col) = Half16<T>::pack(o[n][0] * inv0, o[n][1] * inv0);
-        *reinterpret_cast<uint32_t*>(out + (row0 + r1) * C + col) = Half16<T>::pack(o[n][2] * inv1, o[n][3] * inv1);
+      for (int t = 0; t < TILES; ++t) {
+        const int r0 = (mg * TILES + t) * 16 + (lane >> 2), r1 = r0 + 8;
+        const float inv0 = 1.0f / o[t][4][0], inv1 = 1.0f / o[t][4][2];
+#pragma unroll
+        for (int n = 0; n < 4; ++n) {
+          const int col = h * 32 + n * 8 + q2;
+          *reinterpret_cast<uint32_t*>(out + (row0 + r0) * C + col) = Half16<T>::pack(o[t][n][0] * inv0, o[t][n][1] * inv0);
+          *reinterpret_cast<uint32_t*>(out + (row0 + r1) * C + col) = Half16<T>::pack(o[t][n][2] * inv1, o[t][n][3] * inv1);
+        }
       }
     }
   }
@@ -296,10 +332,10 @@ swinv2_attn_f32_kernel(const float* __restrict__ qkv, const float* __restrict__ 
   }
 }
 
-template <typename T, int WS>
+template <typename T, int WS, int TILES>
 static int launch_v2_t(const void* qkv, const float* bias_tab, const float* logit_scale, void* out, int num_windows, int C, int heads,
                        const WinGeom& g, int nW, float mask_value, cudaStream_t stream) {
-  auto kern = swinv2_attn_kernel<T, WS>;
+  auto kern = swinv2_attn_kernel<T, WS, TILES>;
   const int smem = v2_smem_bytes(WS);
   static bool configured = false;
   if (!configured) {
@@ -307,7 +343,8 @@ static int launch_v2_t(const void* qkv, const float* bias_tab, const float* logi
     configured = true;
   }
   int per_head = num_windows;
-  const int cap = (num_sms() * 4) / heads > 0 ? (num_sms() * 4) / heads : 1;
+  const int resident = TILES == 2 ? 3 : 4;
+  const int cap = (num_sms() * resident) / heads > 0 ? (num_sms() * resident) / heads : 1;
   if (per_head > cap) per_head = cap;
   kern<<<per_head * heads, V2_THREADS, smem, stream>>>(static_cast<const T*>(qkv), bias_tab, logit_scale, static_cast<T*>(out),
                                                        num_windows, C, heads, g, nW, mask_value);
@@ -328,10 +365,10 @@ int launch_swinv2_window_attention(const void* qkv, const float* bias_tab, const
   CSVIT_REQUIRE(items < (1ll << 31), "swinv2_window_attention: too many work items");
   const WinGeom g = make_geom(H, W, ws, shift);
   const float mask_value = -100.0f * static_cast<float>(mask_repeat);
-  if (dtype == DT_BF16 && ws == 16) return launch_v2_t<__nv_bfloat16, 16>(qkv, bias_tab, logit_scale, out, B * nW, C, heads, g, nW, mask_value, stream);
-  if (dtype == DT_BF16) return launch_v2_t<__nv_bfloat16, 8>(qkv, bias_tab, logit_scale, out, B * nW, C, heads, g, nW, mask_value, stream);
-  if (dtype == DT_F16 && ws == 16) return launch_v2_t<__half, 16>(qkv, bias_tab, logit_scale, out, B * nW, C, heads, g, nW, mask_value, stream);
-  if (dtype == DT_F16) return launch_v2_t<__half, 8>(qkv, bias_tab, logit_scale, out, B * nW, C, heads, g, nW, mask_value, stream);
+  if (dtype == DT_BF16 && ws == 16) return launch_v2_t<__nv_bfloat16, 16, V2_TILES16>(qkv, bias_tab, logit_scale, out, B * nW, C, heads, g, nW, mask_value, stream);
+  if (dtype == DT_BF16) return launch_v2_t<__nv_bfloat16, 8, 1>(qkv, bias_tab, logit_scale, out, B * nW, C, heads, g, nW, mask_value, stream);
+  if (dtype == DT_F16 && ws == 16) return launch_v2_t<__half, 16, V2_TILES16>(qkv, bias_tab, logit_scale, out, B * nW, C, heads, g, nW, mask_value, stream);
+  if (dtype == DT_F16) return launch_v2_t<__half, 8, 1>(qkv, bias_tab, logit_scale, out, B * nW, C, heads, g, nW, mask_value, stream);
   CSVIT_REQUIRE(dtype == DT_F32, "swinv2_window_attention: bad dtype %d", dtype);
   const int L = ws * ws, tw = 2 * ws - 1;
   const int smem = (2 * L * 33 + L + 4 * L + 4 * 32 + tw * tw + L) * 4;

@@ -40,6 +40,8 @@ SIGNATURES = {
     "csvit_set_attention_impl": [c_int],
     "csvit_window_attention": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                c_void_p],
+    "csvit_window_attention_ex": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                  c_int, c_void_p],
     "csvit_attention": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_longlong, c_longlong, c_longlong, c_longlong,
                         c_int, c_int, c_int, c_int, c_float, c_void_p],
     "csvit_swinv2_window_attention": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,

@@ -112,6 +112,7 @@ class SwinBackboneB200(nn.Module):
         # overlapped with the MMAs), so it is opt-in until the A tile can be double-buffered.
         self.fuse_ln = False
         self.fuse_mlp = True   # csvit_mlp_fused for C in {128, 256}: hidden activations never leave the SM
+        self.token_order_ctx = True   # inference: attention writes token-ordered context, out-proj uses the TMA residual epilogue
         # Inference runs the batch through the whole backbone in chunks of this many images (0 = all at once).  Images are
         # independent, so the result is bit-identical; what changes is locality: a chunk's inter-kernel tensors (tens of MB)
         # stay resident in the 126 MB L2 between the kernel that writes them and the one that reads them, instead of making
@@ -205,10 +206,16 @@ class SwinBackboneB200(nn.Module):
             qkv = ops.linear(xn, wqkv, bqkv, out_dtype=act, impl=impl)
         bias_mma = None if self._fp32 else self._w(key + "relbias_mma", [sa.relative_position_bias_table],
                                                    lambda: ops.expand_rel_bias_mma(sa.relative_position_bias_table.detach(), ws))
-        ctx = ops.window_attention(qkv, bias, B, H, W, heads, ws, shift, bias_mma=bias_mma)
         proj = blk.attention.output.dense
-        ops.linear(ctx, self._weight(key + "wproj", proj.weight), self._f32(key + "bproj", proj.bias), resid=x, out=x,
-                   scatter=(H, W, ws, shift), impl=impl)
+        if bias_mma is not None and self.token_order_ctx and x.shape[1] >= 256:
+            # the attention kernel un-shifts / un-partitions on its store, so the out-proj runs on plain rows and its fp32
+            # residual update goes through the TMA-staged epilogue (wide rows only: measured faster from C = 256 up)
+            ctx = ops.window_attention(qkv, bias, B, H, W, heads, ws, shift, bias_mma=bias_mma, token_order=True)
+            ops.linear(ctx, self._weight(key + "wproj", proj.weight), self._f32(key + "bproj", proj.bias), resid=x, out=x, impl=impl)
+        else:
+            ctx = ops.window_attention(qkv, bias, B, H, W, heads, ws, shift, bias_mma=bias_mma)
+            ops.linear(ctx, self._weight(key + "wproj", proj.weight), self._f32(key + "bproj", proj.bias), resid=x, out=x,
+                       scatter=(H, W, ws, shift), impl=impl)
         fc1, fc2 = blk.intermediate.dense, blk.output.dense
         if fused_ln:
             hid = ops.ln_linear(x, self._f32(key + "ln2w", ln2.weight), self._f32(key + "ln2b", ln2.bias), eps,

@@ -246,7 +246,7 @@ def mlp_fused(xn: torch.Tensor, w1: torch.Tensor, b1: torch.Tensor, w2: torch.Te
 
 # ---------------------------------------------------------------------------------------------- attention
 def window_attention(qkv: torch.Tensor, bias_exp: torch.Tensor, B: int, H: int, W: int, heads: int, ws: int,
-                     shift: int, bias_mma: Optional[torch.Tensor] = None) -> torch.Tensor:
+                     shift: int, bias_mma: Optional[torch.Tensor] = None, token_order: bool = False) -> torch.Tensor:
     """``bias_exp``: ``expand_rel_bias`` table ``[h,L,L]`` (fp32 kernel and the tcgen05 16-bit kernel) or, for backward
     compatibility, an ``expand_rel_bias_mma`` table (5-D) which selects the mma.sync 16-bit kernel."""
     _dev(qkv, bias_exp, bias_mma)
@@ -260,6 +260,10 @@ def window_attention(qkv: torch.Tensor, bias_exp: torch.Tensor, B: int, H: int, 
     if ld != C3 or rows != B * H * W:
         raise ValueError("window_attention: qkv must be dense [B*H*W, 3C]")
     out = torch.empty(rows, C, dtype=qkv.dtype, device=qkv.device)
+    if token_order:   # rows of `out` in token order (window_reverse + un-shift folded into the store); 16-bit mma.sync kernel
+        _call("csvit_window_attention_ex", qkv.data_ptr(), _p(plain), _p(frag), out.data_ptr(), _code(qkv.dtype), B, H, W, C,
+              heads, ws, shift, 1, _stream(), nbytes=float(qkv.numel() + out.numel()) * qkv.element_size())
+        return out
     _call("csvit_window_attention", qkv.data_ptr(), _p(plain), _p(frag), out.data_ptr(), _code(qkv.dtype), B, H, W, C,
           heads, ws, shift, _stream(), nbytes=float(qkv.numel() + out.numel()) * qkv.element_size())
     return out

@@ -182,14 +182,16 @@ int csvit_set_attention_impl(int use_tcgen05) {
   return 0;
 }
 
-int csvit_window_attention(const void* qkv, const float* bias, const float* bias_mma, void* out, int dtype, int B, int H,
-                           int W, int C, int heads, int ws, int shift, void* stream) {
+static int window_attention_impl(const void* qkv, const float* bias, const float* bias_mma, void* out, int dtype, int B, int H, int W,
+                                 int C, int heads, int ws, int shift, int out_token_order, void* stream) {
   if (dtype == DT_BF16 || dtype == DT_F16) {
     // tcgen05 kernel (plain [h,L,L] bias) when that table is given, mma.sync kernel (fragment-ordered bias) otherwise
-    if (bias != nullptr && (g_attn_tc || bias_mma == nullptr)) return launch_window_attention_tc(qkv, bias, out, dtype, B, H, W, C, heads, ws, shift, S(stream));
+    if (!out_token_order && bias != nullptr && (g_attn_tc || bias_mma == nullptr))
+      return launch_window_attention_tc(qkv, bias, out, dtype, B, H, W, C, heads, ws, shift, S(stream));
     CSVIT_REQUIRE(bias_mma != nullptr, "window_attention: 16-bit path needs the csvit_expand_rel_bias_mma table");
-    return launch_window_attention_mma(qkv, bias_mma, out, dtype, B, H, W, C, heads, ws, shift, S(stream));
+    return launch_window_attention_mma(qkv, bias_mma, out, dtype, B, H, W, C, heads, ws, shift, out_token_order ? 1 : 0, S(stream));
   }
+  CSVIT_REQUIRE(!out_token_order, "window_attention: token-ordered output is built for the 16-bit kernel only");
   CSVIT_REQUIRE(bias != nullptr, "window_attention: fp32 path needs the csvit_expand_rel_bias table");
   CSVIT_REQUIRE(dtype == DT_F32, "window_attention: bad dtype %d", dtype);
   CSVIT_REQUIRE(C == heads * 32, "window_attention: head_dim must be 32 (C=%d heads=%d)", C, heads);
@@ -198,6 +200,16 @@ int csvit_window_attention(const void* qkv, const float* bias, const float* bias
   const float* q = static_cast<const float*>(qkv);
   return launch_attention_simt(q, q + C, q + 2 * C, out, DT_F32, 3ll * C, 3ll * C, 3ll * C, C, B * nW, L, L, heads,
                                0.17677669529663687f, bias, H, W, ws, shift, S(stream));
+}
+
+int csvit_window_attention(const void* qkv, const float* bias, const float* bias_mma, void* out, int dtype, int B, int H,
+                           int W, int C, int heads, int ws, int shift, void* stream) {
+  return window_attention_impl(qkv, bias, bias_mma, out, dtype, B, H, W, C, heads, ws, shift, 0, stream);
+}
+
+int csvit_window_attention_ex(const void* qkv, const float* bias, const float* bias_mma, void* out, int dtype, int B, int H,
+                              int W, int C, int heads, int ws, int shift, int out_token_order, void* stream) {
+  return window_attention_impl(qkv, bias, bias_mma, out, dtype, B, H, W, C, heads, ws, shift, out_token_order, stream);
 }
 
 int csvit_attention(const void* q, const void* k, const void* v, void* out, int dtype, long long ldq, long long ldk,

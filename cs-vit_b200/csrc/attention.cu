@@ -27,7 +27,7 @@ namespace csvit {
 // -inf bias); for V they hit the zero rows, and P is exactly 0 there.
 constexpr int WA_L = 49;
 constexpr int WA_ROW = 64;                                    // bytes per row (32 x 16 bit)
-constexpr int WA_WARP_BYTES = (3 * WA_L + 15) * WA_ROW + 64;  // + region ids
+constexpr int WA_WARP_BYTES = (3 * WA_L + 15) * WA_ROW + 64 + 128;  // + region ids + token ids of the window's 49 slots
 constexpr int WA_WARPS = 4;
 constexpr int WA_BIAS_BYTES = 4 * 7 * 32 * 16;                // one head's fragment-ordered bias table
 constexpr float WA_LOG2E = 1.4426950408889634f;
@@ -96,7 +96,7 @@ __global__ void expand_rel_bias_mma_kernel(const float* __restrict__ table, floa
 template <typename T>
 __global__ void __launch_bounds__(WA_WARPS * 32, 4)
 win_attn_warp_kernel(const T* __restrict__ qkv, const float4* __restrict__ bias_frag, T* __restrict__ out, int num_windows,
-                     int C, int heads, WinGeom g, int nW, float scale) {
+                     int C, int heads, WinGeom g, int nW, float scale, int tok_order) {
   extern __shared__ __align__(16) uint8_t wa_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float4* bias_s = reinterpret_cast<float4*>(wa_smem);
@@ -104,6 +104,7 @@ win_attn_warp_kernel(const T* __restrict__ qkv, const float4* __restrict__ bias_
   uint8_t* Ks = Qs + WA_L * WA_ROW;
   uint8_t* Vs = Ks + WA_L * WA_ROW;
   int8_t* region_s = reinterpret_cast<int8_t*>(Vs + (WA_L + 15) * WA_ROW);
+  int16_t* tok_s = reinterpret_cast<int16_t*>(region_s + 64);   // tok_order: token id (within the image) of each window slot
 
   const int h = blockIdx.x % heads;
   for (int i = threadIdx.x; i < WA_BIAS_BYTES / 16; i += WA_WARPS * 32) bias_s[i] = __ldg(bias_frag + h * (WA_BIAS_BYTES / 16) + i);
@@ -131,6 +132,12 @@ win_attn_warp_kernel(const T* __restrict__ qkv, const float4* __restrict__ bias_
     if (masked) {
       region_s[lane] = static_cast<int8_t>(win_region(g, w, lane));
       if (lane + 32 < WA_L) region_s[lane + 32] = static_cast<int8_t>(win_region(g, w, lane + 32));
+    }
+    long long orow0 = row0;          // window-ordered output: row0 + slot;  token-ordered: image base + token id of the slot
+    if (tok_order) {                 // window_reverse + roll(+shift) folded into the store, so the out-proj GEMM sees plain rows
+      tok_s[lane] = static_cast<int16_t>(win_row_to_token(g, w * WA_L + lane));
+      if (lane + 32 < WA_L) tok_s[lane + 32] = static_cast<int16_t>(win_row_to_token(g, w * WA_L + lane + 32));
+      orow0 = static_cast<long long>(wg / nW) * g.N;
     }
     cp_async_wait_all();
     __syncwarp();
@@ -211,11 +218,13 @@ win_attn_warp_kernel(const T* __restrict__ qkv, const float4* __restrict__ bias_
       }
       const float inv0 = 1.0f / o[4][0], inv1 = 1.0f / o[4][2];
       // ---- store (head merge folded into the column offset) ----
+      int or0 = r0, or1 = r1;
+      if (tok_order) { or0 = tok_s[r0 < WA_L ? r0 : 0]; or1 = tok_s[r1 < WA_L ? r1 : 0]; }
 #pragma unroll
       for (int n = 0; n < 4; ++n) {
         const int col = h * 32 + n * 8 + (lane & 3) * 2;
-        if (r0 < WA_L) *reinterpret_cast<uint32_t*>(out + (row0 + r0) * C + col) = Half16<T>::pack(o[n][0] * inv0, o[n][1] * inv0);
-        if (r1 < WA_L) *reinterpret_cast<uint32_t*>(out + (row0 + r1) * C + col) = Half16<T>::pack(o[n][2] * inv1, o[n][3] * inv1);
+        if (r0 < WA_L) *reinterpret_cast<uint32_t*>(out + (orow0 + or0) * C + col) = Half16<T>::pack(o[n][0] * inv0, o[n][1] * inv0);
+        if (r1 < WA_L) *reinterpret_cast<uint32_t*>(out + (orow0 + or1) * C + col) = Half16<T>::pack(o[n][2] * inv1, o[n][3] * inv1);
       }
     }
     __syncwarp();  // all lanes are done with this window's tiles before the next cp.async overwrites them
@@ -231,7 +240,7 @@ int launch_expand_rel_bias_mma(const float* table, float* out, int heads, cudaSt
 
 template <typename T>
 static int launch_wa(const void* qkv, const float* bias_frag, void* out, int num_windows, int C, int heads, const WinGeom& g,
-                     int nW, cudaStream_t stream) {
+                     int nW, int tok_order, cudaStream_t stream) {
   static bool configured = false;
   auto kern = win_attn_warp_kernel<T>;
   const int smem = WA_BIAS_BYTES + WA_WARPS * WA_WARP_BYTES;
@@ -245,13 +254,13 @@ static int launch_wa(const void* qkv, const float* bias_frag, void* out, int num
   if (per_head > cap) per_head = cap;
   kern<<<per_head * heads, WA_WARPS * 32, smem, stream>>>(static_cast<const T*>(qkv), reinterpret_cast<const float4*>(bias_frag),
                                                           static_cast<T*>(out), num_windows, C, heads, g, nW,
-                                                          0.17677669529663687f * WA_LOG2E);
+                                                          0.17677669529663687f * WA_LOG2E, tok_order);
   CSVIT_CUDA(cudaGetLastError());
   return 0;
 }
 
 int launch_window_attention_mma(const void* qkv, const float* bias_frag, void* out, int dtype, int B, int H, int W,
-                                int C, int heads, int ws, int shift, cudaStream_t stream) {
+                                int C, int heads, int ws, int shift, int tok_order, cudaStream_t stream) {
   CSVIT_REQUIRE(ws == 7, "window_attention(16-bit): only window 7 is built (got %d)", ws);
   CSVIT_REQUIRE(C == heads * 32, "window_attention(16-bit): head_dim must be 32 (C=%d heads=%d)", C, heads);
   CSVIT_REQUIRE(H % ws == 0 && W % ws == 0, "window_attention: %dx%d not divisible by window %d", H, W, ws);
@@ -261,8 +270,9 @@ int launch_window_attention_mma(const void* qkv, const float* bias_frag, void* o
   if (items <= 0) return 0;
   CSVIT_REQUIRE(items < (1ll << 31), "window_attention: too many work items");
   WinGeom g = make_geom(H, W, ws, shift);
-  if (dtype == DT_BF16) return launch_wa<__nv_bfloat16>(qkv, bias_frag, out, B * nW, C, heads, g, nW, stream);
-  return launch_wa<__half>(qkv, bias_frag, out, B * nW, C, heads, g, nW, stream);
+  CSVIT_REQUIRE(H * W < 32768, "window_attention: %dx%d tokens per image exceed the 16-bit token table", H, W);
+  if (dtype == DT_BF16) return launch_wa<__nv_bfloat16>(qkv, bias_frag, out, B * nW, C, heads, g, nW, tok_order, stream);
+  return launch_wa<__half>(qkv, bias_frag, out, B * nW, C, heads, g, nW, tok_order, stream);
 }
 
 }  // namespace csvit

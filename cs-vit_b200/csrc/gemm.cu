@@ -8,6 +8,7 @@
 #include <cudaTypedefs.h>
 
 #include "errors.h"
+#include <cstdlib>
 #include "gemm.cuh"
 
 namespace csvit {
@@ -46,7 +47,7 @@ struct TcCfg {
 template <int BN, int FMT, int CS>  // FMT: 0 = fp16, 1 = bf16, 2 = tf32 operands (UMMA format codes)
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const __grid_constant__ CUtensorMap tmC, int K, EpiParams ep) {
+               const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR, int K, EpiParams ep) {
   using Cfg = TcCfg<BN>;
   constexpr bool TF32 = FMT == 2;
   constexpr int STAGES = Cfg::STAGES;
@@ -65,6 +66,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* tfull = bars + 2 * STAGES;       // [2]
   uint64_t* tempty = bars + 2 * STAGES + 2;  // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  uint64_t* rbar = bars + 16;                // [kEpiWarps][2] residual-chunk arrivals (tma_f32 epilogue)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -80,7 +82,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
-    if (ep.tma_store) prefetch_tmap(&tmC);
+    if (ep.tma_store || ep.tma_f32) prefetch_tmap(&tmC);
+    if (ep.tma_f32 && ep.resid) prefetch_tmap(&tmR);
+    for (int i = 0; i < 2 * kEpiWarps; ++i) mbar_init(&rbar[i], 1);
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], CS); }
     for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], kEpiWarps); }
     fence_mbar_init();
@@ -147,7 +151,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int quad = warp & 3;            // TMEM lane quadrant this warp may read
     const int half = e >> 2;              // which half of the tile's columns
     uint8_t* stg = staging + e * 2 * kStageBufBytes;
-    uint32_t stg_sel = 0;
+    uint32_t stg_sel = 0, rph = 0;
     int as = 0; uint32_t aph = 0;
     for (int ct = cluster_id; ct < num_ctiles; ct += num_clusters) {
       const int mg = ct / num_n, n_blk = ct - mg * num_n;
@@ -157,13 +161,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (ct == cluster_id) prefetch_resid_tile<BN>(ep, m_blk, n_blk, quad, half, lane);
         if (nct < num_ctiles) prefetch_resid_tile<BN>(ep, (nct / num_n) * CS + rank, nct % num_n, quad, half, lane);
       }
-      epilogue_tile<BN>(ep, &tmC, stg, tmem_base + uint32_t(as * BN), &tfull[as], aph, m_blk, n_blk, quad, half, lane, 2, &stg_sel);
+      epilogue_tile<BN>(ep, &tmC, stg, tmem_base + uint32_t(as * BN), &tfull[as], aph, m_blk, n_blk, quad, half, lane, 2, &stg_sel,
+                        &tmR, rbar + 2 * e, &rph);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[as]);
       if (++as == 2) { as = 0; aph ^= 1u; }
     }
-    if (ep.tma_store && lane == 0) tma_store_wait_all();
+    if ((ep.tma_store || ep.tma_f32) && lane == 0) tma_store_wait_all();
   }
 
   tc_fence_before();
@@ -252,6 +257,8 @@ int make_tmap(CUtensorMap* tm, const void* ptr, long long ld, long long rows, lo
   return 0;
 }
 
+// CSVIT_TMA_F32=0 falls back to the register-staged fp32 epilogue (ablation)
+static const bool g_tma_f32 = [] { const char* e = getenv("CSVIT_TMA_F32"); return !(e && e[0] == '0'); }();
 static int g_num_sms = 0;
 int num_sms() {
   if (!g_num_sms) {
@@ -264,8 +271,8 @@ int num_sms() {
 }
 
 template <int BN, int FMT, int CS>
-static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, int K, const EpiParams& ep,
-                     int max_ctas, cudaStream_t stream) {
+static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmR, int K,
+                     const EpiParams& ep, int max_ctas, cudaStream_t stream) {
   using Cfg = TcCfg<BN>;
   static bool configured = false;
   auto kern = gemm_tc_kernel<BN, FMT, CS>;
@@ -291,16 +298,16 @@ static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUten
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  CSVIT_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, K, ep));
+  CSVIT_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, tmR, K, ep));
   return 0;
 }
 
 template <int BN, int FMT>
-static int launch_tc_cs(int cs, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c, int K, const EpiParams& ep,
-                        int max_ctas, cudaStream_t st) {
-  if (cs == 4) return launch_tc<BN, FMT, 4>(a, b, c, K, ep, max_ctas, st);
-  if (cs == 2) return launch_tc<BN, FMT, 2>(a, b, c, K, ep, max_ctas, st);
-  return launch_tc<BN, FMT, 1>(a, b, c, K, ep, max_ctas, st);
+static int launch_tc_cs(int cs, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c, const CUtensorMap& r, int K,
+                        const EpiParams& ep, int max_ctas, cudaStream_t st) {
+  if (cs == 4) return launch_tc<BN, FMT, 4>(a, b, c, r, K, ep, max_ctas, st);
+  if (cs == 2) return launch_tc<BN, FMT, 2>(a, b, c, r, K, ep, max_ctas, st);
+  return launch_tc<BN, FMT, 1>(a, b, c, r, K, ep, max_ctas, st);
 }
 
 int launch_gemm(const void* A, long long lda, const void* W, long long ldw, int in_dtype, int M, int N, int K,
@@ -334,28 +341,36 @@ int launch_gemm(const void* A, long long lda, const void* W, long long ldw, int 
   const bool can_tma_store = ep.out_dtype != DT_F32 && !ep.resid && ep.map_mode == ROWMAP_IDENTITY && (N % 64 == 0) &&
                              ep.vec_ok;
   ep.tma_store = (tune.tma_store != 0 && can_tma_store) ? 1 : 0;
-  ep.coalesced = (!ep.tma_store && tune.tma_store != 0 && ep.out_dtype == DT_F32 && ep.vec_ok && (N % 32 == 0)) ? 1 : 0;
+  // fp32 output on identity rows: residual in / result out by TMA (32 x 32 fp32 boxes).  Scattered rows keep the register path.
+  // Measured (tools/bench_gemm.py, out-proj shapes): 406 -> 475 TFLOP/s at N = 512, 749 -> 905 at N = 1024, but 157 -> 139 at
+  // N = 128, where the register path already streams at the HBM rate and a tile has only two chunks per warp: N >= 256 only.
+  ep.tma_f32 = (tune.tma_store != 0 && ep.out_dtype == DT_F32 && ep.map_mode == ROWMAP_IDENTITY && ep.vec_ok && (N % 32 == 0) && N >= 256 &&
+                ((ep.ldo * 4) % 16 == 0) && (!ep.resid || (ep.ldr * 4) % 16 == 0) && g_tma_f32) ? 1 : 0;
+  ep.coalesced = (!ep.tma_store && !ep.tma_f32 && tune.tma_store != 0 && ep.out_dtype == DT_F32 && ep.vec_ok && (N % 32 == 0)) ? 1 : 0;
   // CTA pairs (cta_group::2): 256x256 tiles with the weight tile split across the two SMs - a third less
   // shared-memory ingest per MMA than the single-CTA kernel, which is what bounds the large-K GEMMs.
   const bool pair_ok = in_dtype != DT_F32 && N % 256 == 0 && num_m * (N / 256) >= 2 * num_sms();
   if (pair_ok && tune.pair != 0) return launch_gemm_pair(A, lda, W, ldw, in_dtype, M, N, K, ep, tune, stream);
-  CUtensorMap tmA, tmB, tmC;
+  CUtensorMap tmA, tmB, tmC, tmR;
   if (int e = make_tmap(&tmA, A, lda, M, K, in_dtype, kBM, true)) return e;
   if (int e = make_tmap(&tmB, W, ldw, N, K, in_dtype, BN / cs, true)) return e;
-  if (ep.tma_store) {
+  if (ep.tma_store || ep.tma_f32) {
     if (int e = make_tmap(&tmC, ep.out, ep.ldo, M, N, ep.out_dtype, 32, false)) return e;
   } else {
     tmC = tmA;
   }
+  tmR = tmC;
+  if (ep.tma_f32 && ep.resid)
+    if (int e = make_tmap(&tmR, ep.resid, ep.ldr, M, N, DT_F32, 32, false)) return e;
   const int mc = tune.max_ctas;
   if (BN == 256) {
-    if (in_dtype == DT_F32) return launch_tc_cs<256, 2>(cs, tmA, tmB, tmC, K, ep, mc, stream);
-    if (in_dtype == DT_BF16) return launch_tc_cs<256, 1>(cs, tmA, tmB, tmC, K, ep, mc, stream);
-    return launch_tc_cs<256, 0>(cs, tmA, tmB, tmC, K, ep, mc, stream);
+    if (in_dtype == DT_F32) return launch_tc_cs<256, 2>(cs, tmA, tmB, tmC, tmR, K, ep, mc, stream);
+    if (in_dtype == DT_BF16) return launch_tc_cs<256, 1>(cs, tmA, tmB, tmC, tmR, K, ep, mc, stream);
+    return launch_tc_cs<256, 0>(cs, tmA, tmB, tmC, tmR, K, ep, mc, stream);
   }
-  if (in_dtype == DT_F32) return launch_tc_cs<128, 2>(cs, tmA, tmB, tmC, K, ep, mc, stream);
-  if (in_dtype == DT_BF16) return launch_tc_cs<128, 1>(cs, tmA, tmB, tmC, K, ep, mc, stream);
-  return launch_tc_cs<128, 0>(cs, tmA, tmB, tmC, K, ep, mc, stream);
+  if (in_dtype == DT_F32) return launch_tc_cs<128, 2>(cs, tmA, tmB, tmC, tmR, K, ep, mc, stream);
+  if (in_dtype == DT_BF16) return launch_tc_cs<128, 1>(cs, tmA, tmB, tmC, tmR, K, ep, mc, stream);
+  return launch_tc_cs<128, 0>(cs, tmA, tmB, tmC, tmR, K, ep, mc, stream);
 }
 
 }  // namespace csvit

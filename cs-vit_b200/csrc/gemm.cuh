@@ -25,6 +25,7 @@ struct EpiParams {
   int vec_ok;     // 1: rows are 16-byte aligned for 32-column chunks (ldo/ldr/N multiples of 8)
   int tma_store;  // 1: 16-bit output, identity rows, no residual -> staged through smem and written by TMA
   int coalesced;  // 1: fp32 output (+residual, +scatter) -> transposed through smem, 4 full lines per warp access
+  int tma_f32;    // 1: fp32 output on identity rows (+residual): residual chunks arrive by TMA, results leave by TMA
   int map_mode;
   WinGeom geom;
 };
@@ -187,7 +188,7 @@ constexpr uint32_t kStageBufBytes = 32 * 128;  // per epilogue warp: 32 rows x 1
 // residual epilogue was latency-bound on those reads (ncu: long-scoreboard stalls, DRAM 38 %).
 template <int BN>
 __device__ __forceinline__ void prefetch_resid_tile(const EpiParams& ep, int m_blk, int n_blk, int quad, int half, int lane) {
-  if (!ep.resid || !ep.coalesced) return;
+  if (!ep.resid || !(ep.coalesced || ep.tma_f32)) return;
   const int row = m_blk * kBM + quad * 32 + lane;
   const int col0 = n_blk * BN + half * (BN / 2);
   if (row >= ep.M || col0 >= ep.N) return;
@@ -199,7 +200,8 @@ __device__ __forceinline__ void prefetch_resid_tile(const EpiParams& ep, int m_b
 template <int BN>
 __device__ __forceinline__ void epilogue_tile(const EpiParams& ep, const CUtensorMap* tmC, uint8_t* stg, uint32_t tmem_tile,
                                               uint64_t* tfull_bar, uint32_t aph, int m_blk, int n_blk, int quad, int half,
-                                              int lane, int nbuf = 1, uint32_t* stg_sel = nullptr) {
+                                              int lane, int nbuf = 1, uint32_t* stg_sel = nullptr, const CUtensorMap* tmR = nullptr,
+                                              uint64_t* rbar = nullptr, uint32_t* rph = nullptr) {
   const bool bf = ep.out_dtype == DT_BF16;
   const int row_in_tile = quad * 32 + lane;
         const int row = m_blk * kBM + row_in_tile;
@@ -218,6 +220,77 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& ep, const CUtenso
               res[j] = *reinterpret_cast<const float4*>(ep.resid + orow8[j] * ep.ldr + gcol + 4 * q);
           }
         };
+        if (ep.tma_f32) {
+          // fp32 output on identity rows (out-proj on token-ordered context, fc2, patch embedding, merging): the warp's
+          // 32 x 32 fp32 chunks of the residual stream are fetched by TMA into its two 128B-swizzled staging buffers (the first
+          // two before the accumulator is even awaited, chunk c+2 as soon as chunk c's store has drained its buffer), each
+          // lane adds its accumulator row in place, and the chunk leaves by TMA store.  No LDG / STG, no transposition: the
+          // register-staged form of this epilogue ran at 3.4-3.6 TB/s (profiles/r1_gemm_pipeline_analysis.md).
+          constexpr int NCH = BN / 64;
+          const int row0 = m_blk * kBM + quad * 32;
+          const int colbase = n_blk * BN + half * (BN / 2);
+          const bool has_res = ep.resid != nullptr;
+          const bool rows_ok = row0 < ep.M;          // warp-uniform
+          if (lane == 0) {
+            tma_store_wait_read0();                  // the previous tile's stores have drained both buffers
+            if (has_res && rows_ok) {
+  #pragma unroll
+              for (int c = 0; c < 2 && c < NCH; ++c) {
+                if (colbase + 32 * c < ep.N) {
+                  mbar_arrive_expect_tx(&rbar[c], kStageBufBytes);
+                  tma_load_2d(stg + c * kStageBufBytes, tmR, &rbar[c], colbase + 32 * c, row0);
+                }
+              }
+            }
+          }
+          __syncwarp();
+          mbar_wait(tfull_bar, aph);
+          tc_fence_after();
+          const uint32_t t_addr = tmem_tile + (uint32_t(quad * 32) << 16);
+  #pragma unroll 1
+          for (int ci = 0; ci < NCH; ++ci) {
+            const int gcol = colbase + 32 * ci;
+            if (gcol >= ep.N) break;  // warp-uniform
+            const int b = ci & 1;
+            uint8_t* buf = stg + b * kStageBufBytes;
+            uint32_t r[32];
+            tmem_ld_32x32(t_addr + uint32_t(half * (BN / 2) + 32 * ci), r);
+            tmem_ld_wait();
+            float v[32];
+  #pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+            epi_bias_act32(ep, gcol, v);
+            if (has_res && rows_ok) {
+              mbar_wait(&rbar[b], (*rph >> b) & 1u);
+              *rph ^= (1u << b);
+            } else if (ci >= 2) {
+              if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // chunk ci-2's store has drained buf
+              __syncwarp();
+            }
+  #pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              float4* p = reinterpret_cast<float4*>(buf + lane * 128 + ((k ^ (lane & 7)) << 4));
+              float4 t = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+              if (has_res && rows_ok) {
+                const float4 x0 = *p;
+                t.x += x0.x; t.y += x0.y; t.z += x0.z; t.w += x0.w;
+              }
+              *p = t;
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0 && rows_ok) {
+              tma_store_2d(tmC, buf, gcol, row0);
+              tma_store_commit();
+              if (has_res && ci + 2 < NCH && gcol + 64 < ep.N) {
+                tma_store_wait_read0();              // that store has read buf: it can take chunk ci+2's residual
+                mbar_arrive_expect_tx(&rbar[b], kStageBufBytes);
+                tma_load_2d(buf, tmR, &rbar[b], gcol + 64, row0);
+              }
+            }
+          }
+          return;
+        }
         if (ep.coalesced) {
   #pragma unroll
           for (int j = 0; j < 8; ++j) {

@@ -30,7 +30,7 @@ constexpr size_t kPairSmem = 1024 + size_t(kPairTiles) + kPairStg + 256;
 template <int FMT>  // 0 = fp16, 1 = bf16
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
 gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const __grid_constant__ CUtensorMap tmC, int K, EpiParams ep) {
+                 const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR, int K, EpiParams ep) {
   constexpr int BN = kPairBN, STAGES = kPairStages, BK = 64;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -43,6 +43,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* tfull = bars + 2 * STAGES;       // [2]
   uint64_t* tempty = bars + 2 * STAGES + 2;  // [2]       (used in the leader)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  uint64_t* rbar = bars + 16;                // [kEpiWarps][2] residual-chunk arrivals (tma_f32 epilogue)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -55,7 +56,9 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
-    if (ep.tma_store) prefetch_tmap(&tmC);
+    if (ep.tma_store || ep.tma_f32) prefetch_tmap(&tmC);
+    if (ep.tma_f32 && ep.resid) prefetch_tmap(&tmR);
+    for (int i = 0; i < 2 * kEpiWarps; ++i) mbar_init(&rbar[i], 1);
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 2); mbar_init(&empty[s], 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 2 * kEpiWarps); }
     fence_mbar_init();
@@ -117,7 +120,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int quad = warp & 3;
     const int half = e >> 2;
     uint8_t* stg = staging + e * 2 * kStageBufBytes;
-    uint32_t stg_sel = 0;
+    uint32_t stg_sel = 0, rph = 0;
     int as = 0; uint32_t aph = 0;
     for (int pt = pair_id; pt < num_ptiles; pt += num_pairs) {
       const int mp = pt / num_n, n_blk = pt - mp * num_n;
@@ -127,13 +130,14 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (pt == pair_id) prefetch_resid_tile<BN>(ep, m_blk, n_blk, quad, half, lane);
         if (npt < num_ptiles) prefetch_resid_tile<BN>(ep, (npt / num_n) * 2 + int(rank), npt % num_n, quad, half, lane);
       }
-      epilogue_tile<BN>(ep, &tmC, stg, tmem_base + uint32_t(as * BN), &tfull[as], aph, m_blk, n_blk, quad, half, lane, 2, &stg_sel);
+      epilogue_tile<BN>(ep, &tmC, stg, tmem_base + uint32_t(as * BN), &tfull[as], aph, m_blk, n_blk, quad, half, lane, 2, &stg_sel,
+                        &tmR, rbar + 2 * e, &rph);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty[as]), 0));
       if (++as == 2) { as = 0; aph ^= 1u; }
     }
-    if (ep.tma_store && lane == 0) tma_store_wait_all();
+    if ((ep.tma_store || ep.tma_f32) && lane == 0) tma_store_wait_all();
   }
 
   tc_fence_before();
@@ -143,8 +147,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 }
 
 template <int FMT>
-static int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, int K, const EpiParams& ep,
-                       int max_ctas, cudaStream_t stream) {
+static int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmR, int K,
+                       const EpiParams& ep, int max_ctas, cudaStream_t stream) {
   static bool configured = false;
   auto kern = gemm_pair_kernel<FMT>;
   if (!configured) {
@@ -155,23 +159,26 @@ static int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   int pairs = (max_ctas > 0 ? max_ctas : num_sms()) / 2;
   if (pairs > num_mp * num_n) pairs = num_mp * num_n;
   if (pairs < 1) pairs = 1;
-  kern<<<pairs * 2, kGemmThreads, kPairSmem, stream>>>(tmA, tmB, tmC, K, ep);
+  kern<<<pairs * 2, kGemmThreads, kPairSmem, stream>>>(tmA, tmB, tmC, tmR, K, ep);
   CSVIT_CUDA(cudaGetLastError());
   return 0;
 }
 
 int launch_gemm_pair(const void* A, long long lda, const void* W, long long ldw, int in_dtype, int M, int N, int K,
                      const EpiParams& ep, const GemmTuning& tune, cudaStream_t stream) {
-  CUtensorMap tmA, tmB, tmC;
+  CUtensorMap tmA, tmB, tmC, tmR;
   if (int e = make_tmap(&tmA, A, lda, M, K, in_dtype, kBM, true)) return e;
   if (int e = make_tmap(&tmB, W, ldw, N, K, in_dtype, kPairBN / 2, true)) return e;
-  if (ep.tma_store) {
+  if (ep.tma_store || ep.tma_f32) {
     if (int e = make_tmap(&tmC, ep.out, ep.ldo, M, N, ep.out_dtype, 32, false)) return e;
   } else {
     tmC = tmA;
   }
-  if (in_dtype == DT_BF16) return launch_pair<1>(tmA, tmB, tmC, K, ep, tune.max_ctas, stream);
-  return launch_pair<0>(tmA, tmB, tmC, K, ep, tune.max_ctas, stream);
+  tmR = tmC;
+  if (ep.tma_f32 && ep.resid)
+    if (int e = make_tmap(&tmR, ep.resid, ep.ldr, M, N, DT_F32, 32, false)) return e;
+  if (in_dtype == DT_BF16) return launch_pair<1>(tmA, tmB, tmC, tmR, K, ep, tune.max_ctas, stream);
+  return launch_pair<0>(tmA, tmB, tmC, tmR, K, ep, tune.max_ctas, stream);
 }
 
 }  // namespace csvit

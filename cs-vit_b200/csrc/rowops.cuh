@@ -34,7 +34,7 @@ int launch_mlp_fused(const void* xn, long long ldxn, const void* W1, long long l
 // attention.cu
 int launch_expand_rel_bias_mma(const float* table, float* out, int heads, cudaStream_t stream);
 int launch_window_attention_mma(const void* qkv, const float* bias_frag, void* out, int dtype, int B, int H, int W,
-                                int C, int heads, int ws, int shift, cudaStream_t stream);
+                                int C, int heads, int ws, int shift, int tok_order, cudaStream_t stream);
 int launch_attention_simt(const void* q, const void* k, const void* v, void* out, int dtype, long long ldq, long long ldk,
                           long long ldv, long long ldo, int n_seq, int Lq, int S, int heads, float scale,
                           const float* bias, int mH, int mW, int mws, int mshift, cudaStream_t stream);

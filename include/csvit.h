@@ -139,6 +139,13 @@ CSVIT_API int csvit_set_gemm_tuning(int cluster, int tma_store, int max_ctas, in
 CSVIT_API int csvit_window_attention(const void* qkv, const float* bias, const float* bias_mma, void* out, int dtype,
                                      int B, int H, int W, int C, int heads, int ws, int shift, void* stream);
 
+/* Same, with out_token_order = 1 (16-bit mma.sync kernel only): out rows are TOKEN-ordered - window_reverse + roll(+shift)
+ * (HF:624-636) folded into the attention store - so that the output projection that follows runs on plain rows and its fp32
+ * residual update can use the TMA-staged epilogue of csvit_linear. */
+CSVIT_API int csvit_window_attention_ex(const void* qkv, const float* bias, const float* bias_mma, void* out, int dtype,
+                                        int B, int H, int W, int C, int heads, int ws, int shift, int out_token_order,
+                                        void* stream);
+
 CSVIT_API int csvit_set_attention_impl(int use_tcgen05);
 
 /* ---- SwinV2 ("V2:" = transformers/models/swinv2/modeling_swinv2.py) ---------------------------

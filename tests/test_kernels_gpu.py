@@ -196,6 +196,12 @@ def test_window_attention(ops, H, heads, shift, dtype):
         # `bias` alone selected the tcgen05/TMEM kernel above; the mma.sync kernel (fragment-ordered table) must agree
         out2 = ops.window_attention(qkv, ops.expand_rel_bias_mma(table, ws), B, H, W, heads, ws, shift)
         assert rel(out2, ref) < tol
+        # token-ordered output = the window-ordered rows scattered by the window index map (window_reverse + un-shift), bit for bit
+        out_tok = ops.window_attention(qkv, ops.expand_rel_bias_mma(table, ws), B, H, W, heads, ws, shift, token_order=True)
+        idx = ops.window_index_map(H, W, ws, shift).long()
+        want_tok = torch.empty_like(out2).view(B, H * W, C)
+        want_tok[:, idx] = out2.view(B, H * W, C)
+        assert torch.equal(out_tok.view(B, H * W, C), want_tok)
         try:   # explicit selection with both tables present
             ops.set_attention_impl(True)
             out3 = ops.window_attention(qkv, bias, B, H, W, heads, ws, shift, bias_mma=ops.expand_rel_bias_mma(table, ws))

@@ -197,11 +197,35 @@ __device__ __forceinline__ void prefetch_resid_tile(const EpiParams& ep, int m_b
   for (int o = 0; o < bytes; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + o));
 }
 
+// tma_f32 epilogue, first half: once the previous tile's stores have drained the warp's two staging buffers, request the first
+// two 32 x 32 residual chunks of tile (m_blk, n_blk).  epilogue_tile() does this itself unless told that the caller already did
+// (the fused MLP issues it at tile start, several microseconds before the accumulator is ready).
+template <int BN>
+__device__ __forceinline__ void tma_f32_prefetch(const EpiParams& ep, const CUtensorMap* tmR, uint8_t* stg, uint64_t* rbar, int m_blk,
+                                                 int n_blk, int quad, int half, int lane) {
+  constexpr int NCH = BN / 64;
+  const int row0 = m_blk * kBM + quad * 32;
+  const int colbase = n_blk * BN + half * (BN / 2);
+  if (lane == 0) {
+    tma_store_wait_read0();                  // the previous tile's stores have drained both buffers
+    if (ep.resid != nullptr && row0 < ep.M) {
+#pragma unroll
+      for (int c = 0; c < 2 && c < NCH; ++c) {
+        if (colbase + 32 * c < ep.N) {
+          mbar_arrive_expect_tx(&rbar[c], kStageBufBytes);
+          tma_load_2d(stg + c * kStageBufBytes, tmR, &rbar[c], colbase + 32 * c, row0);
+        }
+      }
+    }
+  }
+  __syncwarp();
+}
+
 template <int BN>
 __device__ __forceinline__ void epilogue_tile(const EpiParams& ep, const CUtensorMap* tmC, uint8_t* stg, uint32_t tmem_tile,
                                               uint64_t* tfull_bar, uint32_t aph, int m_blk, int n_blk, int quad, int half,
                                               int lane, int nbuf = 1, uint32_t* stg_sel = nullptr, const CUtensorMap* tmR = nullptr,
-                                              uint64_t* rbar = nullptr, uint32_t* rph = nullptr) {
+                                              uint64_t* rbar = nullptr, uint32_t* rph = nullptr, bool prefetched = false) {
   const bool bf = ep.out_dtype == DT_BF16;
   const int row_in_tile = quad * 32 + lane;
         const int row = m_blk * kBM + row_in_tile;
@@ -231,19 +255,7 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& ep, const CUtenso
           const int colbase = n_blk * BN + half * (BN / 2);
           const bool has_res = ep.resid != nullptr;
           const bool rows_ok = row0 < ep.M;          // warp-uniform
-          if (lane == 0) {
-            tma_store_wait_read0();                  // the previous tile's stores have drained both buffers
-            if (has_res && rows_ok) {
-  #pragma unroll
-              for (int c = 0; c < 2 && c < NCH; ++c) {
-                if (colbase + 32 * c < ep.N) {
-                  mbar_arrive_expect_tx(&rbar[c], kStageBufBytes);
-                  tma_load_2d(stg + c * kStageBufBytes, tmR, &rbar[c], colbase + 32 * c, row0);
-                }
-              }
-            }
-          }
-          __syncwarp();
+          if (!prefetched) tma_f32_prefetch<BN>(ep, tmR, stg, rbar, m_blk, n_blk, quad, half, lane);
           mbar_wait(tfull_bar, aph);
           tc_fence_after();
           const uint32_t t_addr = tmem_tile + (uint32_t(quad * 32) << 16);

@@ -13,6 +13,7 @@
 //   warps 2-9  chunk epilogue (TMEM -> +b1 -> GELU -> 16 bit -> smem) and, after the last chunk, the fp32
 //              residual epilogue of the tile (same coalesced path as the GEMM engine)
 // TMEM: two 128-column GEMM1 accumulators + one C-column GEMM2 accumulator (<= 512 columns).
+#include <cstdlib>
 #include <type_traits>
 
 #include "errors.h"
@@ -28,11 +29,12 @@ struct MlpCfg {
   static constexpr int KB1 = C / 64;            // k-blocks of GEMM1
   static constexpr int N2 = C / 128;            // 128-column groups of the GEMM2 output
   static constexpr int NCH = 4 * C / 128;       // hidden chunks
-  static constexpr int WSTAGES = C == 128 ? 6 : 4;
+  static constexpr int WSTAGES = 4;             // (C = 128 gave two of its six weight stages to the second staging buffer)
+  static constexpr int STG_BUFS = C == 128 ? 2 : 1;   // C = 128: residual in / result out by TMA (tma_f32 epilogue), prefetched at tile start
   static constexpr uint32_t A1_BYTES = KB1 * kUnit;
   static constexpr uint32_t A2_BYTES = 2 * 2 * kUnit;
   static constexpr uint32_t W_BYTES = WSTAGES * kUnit;
-  static constexpr uint32_t STG_BYTES = kEpiWarps * kStageBufBytes;
+  static constexpr uint32_t STG_BYTES = STG_BUFS * kEpiWarps * kStageBufBytes;
   static constexpr size_t SMEM = 1024 + size_t(A1_BYTES) + A2_BYTES + W_BYTES + STG_BYTES + 512;
 };
 
@@ -44,7 +46,7 @@ struct MlpParams {
 template <int FMT, int C>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
-                 const __grid_constant__ CUtensorMap tmW2, MlpParams mp, EpiParams ep) {
+                 const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmR, MlpParams mp, EpiParams ep) {
   using Cfg = MlpCfg<C>;
   constexpr int KB1 = Cfg::KB1, N2 = Cfg::N2, NCH = Cfg::NCH, WS = Cfg::WSTAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -63,12 +65,15 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   uint64_t* acc2_full = acc1_full + 10;
   uint64_t* acc2_empty = acc1_full + 11;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc1_full + 12);
+  uint64_t* rbar = bars + 32;                 // [kEpiWarps][2] residual-chunk arrivals (tma_f32 epilogue, C = 128)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_tiles = (mp.M + kBM - 1) / kBM;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmX); prefetch_tmap(&tmW1); prefetch_tmap(&tmW2);
+    if (ep.tma_f32) prefetch_tmap(&tmR);
+    for (int i = 0; i < 2 * kEpiWarps; ++i) mbar_init(&rbar[i], 1);
     for (int s = 0; s < WS; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&acc1_full[b], 1); mbar_init(&acc1_empty[b], kEpiWarps);
@@ -163,10 +168,13 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     const int half = e >> 2;
     const int r = quad * 32 + lane;           // row of the tile owned by this thread
     const bool bf = FMT == 1;
-    uint8_t* stg = smem + stg_off + e * kStageBufBytes;
-    uint32_t it = 0;
+    uint8_t* stg = smem + stg_off + e * Cfg::STG_BUFS * kStageBufBytes;
+    uint32_t it = 0, rph = 0;
     uint32_t use[2] = {0, 0};
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+      // residual chunks of this tile requested now: they land while the hidden chunks are being processed
+      if (ep.tma_f32) tma_f32_prefetch<C>(ep, &tmR, stg, rbar + 2 * e, t, 0, quad, half, lane);
+      else prefetch_resid_tile<C>(ep, t, 0, quad, half, lane);   // C = 256 (no room for a second staging buffer): at least pull the lines into L2
       for (int j = 0; j < NCH; ++j) {
         const int b = j & 1;
         mbar_wait(&acc1_full[b], use[b] & 1u);
@@ -195,21 +203,22 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         ++use[b];
       }
       // tile epilogue: acc2 (+ b2) + residual -> x, coalesced fp32 path of the GEMM engine (waits on acc2_full itself)
-      epilogue_tile<C>(ep, &tmX, stg, tm_acc2, acc2_full, it & 1u, t, 0, quad, half, lane);
+      epilogue_tile<C>(ep, &tmR, stg, tm_acc2, acc2_full, it & 1u, t, 0, quad, half, lane, 1, nullptr, &tmR, rbar + 2 * e, &rph, true);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(acc2_empty);
     }
   }
 
+  if (ep.tma_f32 && warp >= 2 && lane == 0) tma_store_wait_all();
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
 template <int FMT, int C>
-static int launch_mlp(const CUtensorMap& tmX, const CUtensorMap& tmW1, const CUtensorMap& tmW2, const MlpParams& mp,
-                      const EpiParams& ep, cudaStream_t stream) {
+static int launch_mlp(const CUtensorMap& tmX, const CUtensorMap& tmW1, const CUtensorMap& tmW2, const CUtensorMap& tmR,
+                      const MlpParams& mp, const EpiParams& ep, cudaStream_t stream) {
   using Cfg = MlpCfg<C>;
   static bool configured = false;
   auto kern = mlp_fused_kernel<FMT, C>;
@@ -219,7 +228,7 @@ static int launch_mlp(const CUtensorMap& tmX, const CUtensorMap& tmW1, const CUt
   }
   const int tiles = (mp.M + kBM - 1) / kBM;
   const int ctas = tiles < num_sms() ? tiles : num_sms();
-  kern<<<ctas, kGemmThreads, Cfg::SMEM, stream>>>(tmX, tmW1, tmW2, mp, ep);
+  kern<<<ctas, kGemmThreads, Cfg::SMEM, stream>>>(tmX, tmW1, tmW2, tmR, mp, ep);
   CSVIT_CUDA(cudaGetLastError());
   return 0;
 }
@@ -239,9 +248,16 @@ int launch_mlp_fused(const void* xn, long long ldxn, const void* W1, long long l
   if (int e = make_tmap(&tmX, xn, ldxn, M, C, dtype, kBM, true)) return e;
   if (int e = make_tmap(&tmW1, W1, ldw1, 4ll * C, C, dtype, 128, true)) return e;
   if (int e = make_tmap(&tmW2, W2, ldw2, C, 4ll * C, dtype, 128, true)) return e;
+  CUtensorMap tmR = tmX;
+  static const bool tma_resid = [] { const char* e = getenv("CSVIT_MLP_TMA_RESID"); return !(e && e[0] == '0'); }();
+  if (C == 128 && tma_resid && (ldx * 4) % 16 == 0) {
+    // residual tile in / out by TMA: 32 x 32 fp32 boxes of x, both chunks of a warp requested at tile start
+    ep.tma_f32 = 1; ep.coalesced = 0;
+    if (int e = make_tmap(&tmR, x, ldx, M, C, DT_F32, 32, false)) return e;
+  }
   const bool bf = dtype == DT_BF16;
-  if (C == 128) return bf ? launch_mlp<1, 128>(tmX, tmW1, tmW2, mp, ep, stream) : launch_mlp<0, 128>(tmX, tmW1, tmW2, mp, ep, stream);
-  return bf ? launch_mlp<1, 256>(tmX, tmW1, tmW2, mp, ep, stream) : launch_mlp<0, 256>(tmX, tmW1, tmW2, mp, ep, stream);
+  if (C == 128) return bf ? launch_mlp<1, 128>(tmX, tmW1, tmW2, tmR, mp, ep, stream) : launch_mlp<0, 128>(tmX, tmW1, tmW2, tmR, mp, ep, stream);
+  return bf ? launch_mlp<1, 256>(tmX, tmW1, tmW2, tmR, mp, ep, stream) : launch_mlp<0, 256>(tmX, tmW1, tmW2, tmR, mp, ep, stream);
 }
 
 }  // namespace csvit

@@ -1,0 +1,13 @@
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.join(ROOT, "cs-vit_b200"))
+import torch
+from cs_vit import ops
+c = int(os.environ.get("C", "128")); hw = 56 if c == 128 else 28
+M = 256 * hw * hw; dt = torch.bfloat16
+g = torch.Generator(device="cuda").manual_seed(0)
+xn = torch.randn(M, c, device="cuda", generator=g).to(dt)
+w1 = (torch.randn(4 * c, c, device="cuda", generator=g) * 0.05).to(dt); b1 = torch.randn(4 * c, device="cuda", generator=g)
+w2 = (torch.randn(c, 4 * c, device="cuda", generator=g) * 0.05).to(dt); b2 = torch.randn(c, device="cuda", generator=g)
+x = torch.randn(M, c, device="cuda", generator=g)
+ops.mlp_fused(xn, w1, b1, w2, b2, x); torch.cuda.synchronize()

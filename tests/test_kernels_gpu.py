@@ -113,6 +113,32 @@ def test_mlp_fused_matches_unfused(ops, C, M, dt):
     assert rel(fused, unfused) < 1e-4
 
 
+@pytest.mark.parametrize("M,N", [(1000, 256), (1000, 512), (777, 768), (128 * 300 + 40, 512), (128 * 150 + 5, 1024), (64, 256)])
+def test_linear_fp32_residual_tma_epilogue(ops, M, N):
+    """fp32 output on plain rows with N >= 256 takes the TMA-staged epilogue (residual chunks in, results out by TMA): ragged M,
+    in place / out of place / no residual, single-CTA and CTA-pair kernels, against fp32 torch math."""
+    g = torch.Generator(device="cuda").manual_seed(M + N)
+    K = 256
+    a = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(N, K, device="cuda", generator=g) * 0.05).bfloat16()
+    b = torch.randn(N, device="cuda", generator=g)
+    x = torch.randn(M, N, device="cuda", generator=g)
+    y = a.float() @ w.float().T + b
+    out = ops.linear(a, w, b, out_dtype=torch.float32)                       # no residual
+    assert rel(out, y) < 1e-5
+    out2 = ops.linear(a, w, b, resid=x, out_dtype=torch.float32)             # out of place
+    assert rel(out2, x + y) < 1e-5
+    xi = x.clone()
+    ops.linear(a, w, b, resid=xi, out=xi)                                    # in place
+    assert torch.equal(xi, out2)
+    big = torch.full((M + 2, N + 32), 7.0, device="cuda")                    # pitched output / residual views, untouched borders
+    view = big[1:M + 1, :N]
+    view.copy_(x)
+    ops.linear(a, w, b, resid=view, out=view)
+    assert torch.equal(view, out2)
+    assert (big[0] == 7).all() and (big[M + 1] == 7).all() and (big[:, N:] == 7).all()
+
+
 def test_linear_epilogues(ops):
     g = torch.Generator(device="cuda").manual_seed(5)
     B, H, W, C = 3, 14, 14, 256

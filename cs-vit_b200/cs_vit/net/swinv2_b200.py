@@ -11,7 +11,7 @@ Per block (res-post-norm, V2:662-715) the forward issues, on ``libcsvit_sm100.so
 
     xw (16-bit copy of x in this block's shifted-window order, written by the PREVIOUS LayerNorm kernel)
       -> QKV GEMM (no key bias) -> cosine window attention (csvit_swinv2_window_attention)
-      -> out-proj GEMM, fp32, rows scattered back to token order
+      (its store un-partitions / un-shifts: token-ordered context) -> out-proj GEMM, fp32, plain rows (TMA-store epilogue)
       -> csvit_layernorm_post: x += LN(y), and the 16-bit token-order copy of x for fc1
       -> fc1 GEMM + GELU -> fc2 GEMM (fp32)
       -> csvit_layernorm_post: x += LN(z), and the 16-bit copy of x in the NEXT block's window order (or the 2x2-merged
@@ -263,10 +263,11 @@ class Swinv2BackboneB200(nn.Module):
                     [sa.query.bias.detach().float(), torch.zeros_like(sa.query.bias, dtype=torch.float32), sa.value.bias.detach().float()], 0).contiguous())
                 bias_tab, lscale = self._attn_tables(sa, key, ws, cfg.pretrained_window_sizes[s])
                 qkv = ops.linear(xw, wqkv, bqkv, out_dtype=act, impl=impl)
-                ctx = ops.swinv2_window_attention(qkv, bias_tab, lscale, n, H, H, heads, ws, shift)
+                # the attention kernel un-partitions / un-shifts on its store: the out-proj runs on plain token rows
+                ctx = ops.swinv2_window_attention(qkv, bias_tab, lscale, n, H, H, heads, ws, shift, token_order=True)
                 proj = blk.attention.output.dense
                 ya = ops.linear(ctx, self._weight(key + "wproj", proj.weight), self._f32(key + "bproj", proj.bias), out_dtype=torch.float32,
-                                scatter=(H, H, ws, shift), impl=impl)
+                                impl=impl)
                 ln1, ln2 = blk.layernorm_before, blk.layernorm_after
                 _, x16 = ops.layernorm_post(ya, x, self._f32(key + "ln1w", ln1.weight), self._f32(key + "ln1b", ln1.bias), eps, out=x,
                                             copy_mode=ops.COPY_IDENTITY, copy_dtype=act)

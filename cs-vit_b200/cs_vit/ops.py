@@ -293,7 +293,7 @@ COPY_NONE, COPY_IDENTITY, COPY_WINDOW, COPY_MERGE2X2 = 0, 1, 2, 3
 
 
 def swinv2_window_attention(qkv: torch.Tensor, bias_tab: torch.Tensor, logit_scale: torch.Tensor, B: int, H: int, W: int, heads: int,
-                            ws: int, shift: int, mask_repeat: int = 2) -> torch.Tensor:
+                            ws: int, shift: int, mask_repeat: int = 2, token_order: bool = False) -> torch.Tensor:
     """Scaled-cosine window attention (``csvit_swinv2_window_attention``): qkv window-ordered ``[B*H*W, 3C]``, ``bias_tab`` fp32
     ``[heads, (2ws-1)^2]``, ``logit_scale`` fp32 ``[heads]`` (already clamped and exponentiated)."""
     _dev(qkv, bias_tab, logit_scale)
@@ -308,7 +308,7 @@ def swinv2_window_attention(qkv: torch.Tensor, bias_tab: torch.Tensor, logit_sca
     out = torch.empty(rows, C, dtype=qkv.dtype, device=qkv.device)
     L = ws * ws
     _call("csvit_swinv2_window_attention", qkv.data_ptr(), bias_tab.data_ptr(), logit_scale.data_ptr(), out.data_ptr(),
-          _code(qkv.dtype), B, H, W, C, heads, ws, shift, mask_repeat, _stream(),
+          _code(qkv.dtype), B, H, W, C, heads, ws, shift, mask_repeat, 1 if token_order else 0, _stream(),
           flops=4.0 * rows * L * C, nbytes=float(qkv.numel() + out.numel()) * qkv.element_size())
     return out
 

@@ -221,11 +221,12 @@ int csvit_attention(const void* q, const void* k, const void* v, void* out, int 
 
 // ---- SwinV2 ------------------------------------------------------------------------------------------------
 int csvit_swinv2_window_attention(const void* qkv, const float* bias_tab, const float* logit_scale, void* out, int dtype, int B, int H,
-                                  int W, int C, int heads, int ws, int shift, int mask_repeat, void* stream) {
+                                  int W, int C, int heads, int ws, int shift, int mask_repeat, int out_token_order, void* stream) {
   CSVIT_REQUIRE(ok_dtype(dtype), "swinv2_window_attention: bad dtype %d", dtype);
   CSVIT_REQUIRE(bias_tab != nullptr && logit_scale != nullptr, "swinv2_window_attention: bias table and logit scale are required");
   CSVIT_REQUIRE(mask_repeat >= 0 && mask_repeat <= 2, "swinv2_window_attention: mask_repeat %d outside [0,2]", mask_repeat);
-  return launch_swinv2_window_attention(qkv, bias_tab, logit_scale, out, dtype, B, H, W, C, heads, ws, shift, mask_repeat, S(stream));
+  return launch_swinv2_window_attention(qkv, bias_tab, logit_scale, out, dtype, B, H, W, C, heads, ws, shift, mask_repeat,
+                                        out_token_order ? 1 : 0, S(stream));
 }
 
 int csvit_layernorm_post(const float* y, long long ldy, const float* resid, const float* gamma, const float* beta, float eps, float* out,

@@ -60,7 +60,7 @@ int launch_attention_bwd(const void* q, const void* k, const void* v, const void
 
 // swinv2.cu
 int launch_swinv2_window_attention(const void* qkv, const float* bias_tab, const float* logit_scale, void* out, int dtype, int B, int H,
-                                   int W, int C, int heads, int ws, int shift, int mask_repeat, cudaStream_t stream);
+                                   int W, int C, int heads, int ws, int shift, int mask_repeat, int tok_order, cudaStream_t stream);
 int launch_layernorm_post(const float* y, long long ldy, const float* resid, const float* gamma, const float* beta, float eps,
                           float* xo, void* copy, int copy_dtype, long long ldc, int copy_mode, int rows, int C, const WinGeom& g,
                           cudaStream_t stream);

@@ -40,7 +40,7 @@ template <> __device__ __forceinline__ float2 unpack2<__half>(uint32_t u) {
 __host__ __device__ inline int v2_smem_bytes(int ws) {
   const int L = ws * ws, tw = 2 * ws - 1;
   const int tb = (tw * tw + 3) & ~3;
-  return tb * 4 + 2 * L * 4 + L + 3 * L * ROW_BYTES;
+  return tb * 4 + 2 * L * 4 + L + 2 * L + 3 * L * ROW_BYTES;   // bias, 1/|q|, 1/|k|, region ids, token ids, Q / K / V
 }
 
 __device__ __forceinline__ float ex2_ftz(float x) {
@@ -70,7 +70,7 @@ constexpr float V2_LOG2E = 1.4426950408889634f;
 template <typename T, int WS, int TILES>
 __global__ void __launch_bounds__(V2_THREADS, TILES == 2 ? 3 : 4)
 swinv2_attn_kernel(const T* __restrict__ qkv, const float* __restrict__ bias_tab, const float* __restrict__ logit_scale,
-                   T* __restrict__ out, int num_windows, int C, int heads, WinGeom g, int nW, float mask_value) {
+                   T* __restrict__ out, int num_windows, int C, int heads, WinGeom g, int nW, float mask_value, int tok_order) {
   static_assert(WS == 8 || WS == 16, "windows of 8x8 and 16x16 tokens");
   constexpr int L = WS * WS, TW = 2 * WS - 1, TB = TW * TW, TBP = (TB + 3) & ~3;
   extern __shared__ __align__(16) uint8_t v2_smem[];
@@ -79,7 +79,8 @@ swinv2_attn_kernel(const T* __restrict__ qkv, const float* __restrict__ bias_tab
   float* rq_s = bias_s + TBP;
   float* rk_s = rq_s + L;
   int8_t* region_s = reinterpret_cast<int8_t*>(rk_s + L);
-  uint8_t* Qs = reinterpret_cast<uint8_t*>(region_s + L);
+  int16_t* tok_s = reinterpret_cast<int16_t*>(region_s + L);    // tok_order: token id (within the image) of each window slot
+  uint8_t* Qs = reinterpret_cast<uint8_t*>(tok_s + L);
   uint8_t* Ks = Qs + L * ROW_BYTES;
   uint8_t* Vs = Ks + L * ROW_BYTES;
 
@@ -107,6 +108,11 @@ swinv2_attn_kernel(const T* __restrict__ qkv, const float* __restrict__ bias_tab
     const bool masked = g.shift > 0 && (wy == nWy - 1 || wx == g.nWx - 1);   // CTA-uniform
     if (masked)
       for (int i = tid; i < L; i += V2_THREADS) region_s[i] = static_cast<int8_t>(win_region(g, w, i));
+    long long obase = row0;          // window-ordered output: row0 + slot;  token-ordered: image base + token id of the slot
+    if (tok_order) {                 // window_reverse + roll(+shift) folded into the store: the out-proj GEMM sees plain rows
+      for (int i = tid; i < L; i += V2_THREADS) tok_s[i] = static_cast<int16_t>(win_row_to_token(g, w * L + i));
+      obase = static_cast<long long>(wg / nW) * g.N;
+    }
     cp_async_wait_all();
     __syncthreads();
     // log2(e) * logit_scale / max(|q_i|, 1e-12) and 1 / max(|k_j|, 1e-12)   (F.normalize, V2:452-455)
@@ -244,13 +250,14 @@ swinv2_attn_kernel(const T* __restrict__ qkv, const float* __restrict__ bias_tab
       // ---- store (head merge folded into the column offset) ----
 #pragma unroll
       for (int t = 0; t < TILES; ++t) {
-        const int r0 = (mg * TILES + t) * 16 + (lane >> 2), r1 = r0 + 8;
+        int r0 = (mg * TILES + t) * 16 + (lane >> 2), r1 = r0 + 8;
+        if (tok_order) { r0 = tok_s[r0]; r1 = tok_s[r1]; }
         const float inv0 = 1.0f / o[t][4][0], inv1 = 1.0f / o[t][4][2];
 #pragma unroll
         for (int n = 0; n < 4; ++n) {
           const int col = h * 32 + n * 8 + q2;
-          *reinterpret_cast<uint32_t*>(out + (row0 + r0) * C + col) = Half16<T>::pack(o[t][n][0] * inv0, o[t][n][1] * inv0);
-          *reinterpret_cast<uint32_t*>(out + (row0 + r1) * C + col) = Half16<T>::pack(o[t][n][2] * inv1, o[t][n][3] * inv1);
+          *reinterpret_cast<uint32_t*>(out + (obase + r0) * C + col) = Half16<T>::pack(o[t][n][0] * inv0, o[t][n][1] * inv0);
+          *reinterpret_cast<uint32_t*>(out + (obase + r1) * C + col) = Half16<T>::pack(o[t][n][2] * inv1, o[t][n][3] * inv1);
         }
       }
     }
@@ -263,7 +270,7 @@ swinv2_attn_kernel(const T* __restrict__ qkv, const float* __restrict__ bias_tab
 // One CTA (4 warps) per (window, head); K / V rows padded to 33 floats; warp per query row, lane per key (L / 32 keys per lane).
 __global__ void __launch_bounds__(V2_THREADS)
 swinv2_attn_f32_kernel(const float* __restrict__ qkv, const float* __restrict__ bias_tab, const float* __restrict__ logit_scale,
-                       float* __restrict__ out, int num_items, int C, int heads, WinGeom g, int nW, float mask_value) {
+                       float* __restrict__ out, int num_items, int C, int heads, WinGeom g, int nW, float mask_value, int tok_order) {
   extern __shared__ __align__(16) uint8_t v2_smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int L = g.L, ws = g.ws, tw = 2 * ws - 1, TB = tw * tw;
@@ -326,7 +333,8 @@ swinv2_attn_f32_kernel(const float* __restrict__ qkv, const float* __restrict__ 
       __syncwarp();
       float acc = 0.f;
       for (int j = 0; j < L; ++j) acc = fmaf(Ps[warp * L + j], Vs[j * 33 + lane], acc);
-      out[(row0 + i) * C + h * 32 + lane] = acc * inv;
+      const long long orow = tok_order ? static_cast<long long>(wg / nW) * g.N + win_row_to_token(g, w * L + i) : row0 + i;
+      out[orow * C + h * 32 + lane] = acc * inv;
       __syncwarp();
     }
   }
@@ -334,7 +342,7 @@ swinv2_attn_f32_kernel(const float* __restrict__ qkv, const float* __restrict__ 
 
 template <typename T, int WS, int TILES>
 static int launch_v2_t(const void* qkv, const float* bias_tab, const float* logit_scale, void* out, int num_windows, int C, int heads,
-                       const WinGeom& g, int nW, float mask_value, cudaStream_t stream) {
+                       const WinGeom& g, int nW, float mask_value, int tok_order, cudaStream_t stream) {
   auto kern = swinv2_attn_kernel<T, WS, TILES>;
   const int smem = v2_smem_bytes(WS);
   static bool configured = false;
@@ -347,28 +355,29 @@ static int launch_v2_t(const void* qkv, const float* bias_tab, const float* logi
   const int cap = (num_sms() * resident) / heads > 0 ? (num_sms() * resident) / heads : 1;
   if (per_head > cap) per_head = cap;
   kern<<<per_head * heads, V2_THREADS, smem, stream>>>(static_cast<const T*>(qkv), bias_tab, logit_scale, static_cast<T*>(out),
-                                                       num_windows, C, heads, g, nW, mask_value);
+                                                       num_windows, C, heads, g, nW, mask_value, tok_order);
   CSVIT_CUDA(cudaGetLastError());
   return 0;
 }
 
 int launch_swinv2_window_attention(const void* qkv, const float* bias_tab, const float* logit_scale, void* out, int dtype, int B, int H,
-                                   int W, int C, int heads, int ws, int shift, int mask_repeat, cudaStream_t stream) {
+                                   int W, int C, int heads, int ws, int shift, int mask_repeat, int tok_order, cudaStream_t stream) {
   CSVIT_REQUIRE(C == heads * 32, "swinv2_window_attention: head_dim must be 32 (C=%d heads=%d)", C, heads);
   CSVIT_REQUIRE(ws > 0 && H % ws == 0 && W % ws == 0, "swinv2_window_attention: %dx%d not divisible by window %d", H, W, ws);
   CSVIT_REQUIRE(ws * ws <= V2_MAXL, "swinv2_window_attention: window %d not built (at most %d tokens per window)", ws, V2_MAXL);
   CSVIT_REQUIRE(dtype == DT_F32 || ws == 16 || ws == 8, "swinv2_window_attention: window %d not built (16-bit kernel: windows 16 and 8)", ws);
   CSVIT_REQUIRE(shift >= 0 && shift < ws, "swinv2_window_attention: shift %d outside [0,%d)", shift, ws);
+  CSVIT_REQUIRE(H * W < 32768, "swinv2_window_attention: %dx%d tokens per image exceed the 16-bit token table", H, W);
   const int nW = (H / ws) * (W / ws);
   const long long items = static_cast<long long>(B) * nW * heads;
   if (items <= 0) return 0;
   CSVIT_REQUIRE(items < (1ll << 31), "swinv2_window_attention: too many work items");
   const WinGeom g = make_geom(H, W, ws, shift);
   const float mask_value = -100.0f * static_cast<float>(mask_repeat);
-  if (dtype == DT_BF16 && ws == 16) return launch_v2_t<__nv_bfloat16, 16, V2_TILES16>(qkv, bias_tab, logit_scale, out, B * nW, C, heads, g, nW, mask_value, stream);
-  if (dtype == DT_BF16) return launch_v2_t<__nv_bfloat16, 8, 1>(qkv, bias_tab, logit_scale, out, B * nW, C, heads, g, nW, mask_value, stream);
-  if (dtype == DT_F16 && ws == 16) return launch_v2_t<__half, 16, V2_TILES16>(qkv, bias_tab, logit_scale, out, B * nW, C, heads, g, nW, mask_value, stream);
-  if (dtype == DT_F16) return launch_v2_t<__half, 8, 1>(qkv, bias_tab, logit_scale, out, B * nW, C, heads, g, nW, mask_value, stream);
+  if (dtype == DT_BF16 && ws == 16) return launch_v2_t<__nv_bfloat16, 16, V2_TILES16>(qkv, bias_tab, logit_scale, out, B * nW, C, heads, g, nW, mask_value, tok_order, stream);
+  if (dtype == DT_BF16) return launch_v2_t<__nv_bfloat16, 8, 1>(qkv, bias_tab, logit_scale, out, B * nW, C, heads, g, nW, mask_value, tok_order, stream);
+  if (dtype == DT_F16 && ws == 16) return launch_v2_t<__half, 16, V2_TILES16>(qkv, bias_tab, logit_scale, out, B * nW, C, heads, g, nW, mask_value, tok_order, stream);
+  if (dtype == DT_F16) return launch_v2_t<__half, 8, 1>(qkv, bias_tab, logit_scale, out, B * nW, C, heads, g, nW, mask_value, tok_order, stream);
   CSVIT_REQUIRE(dtype == DT_F32, "swinv2_window_attention: bad dtype %d", dtype);
   const int L = ws * ws, tw = 2 * ws - 1;
   const int smem = (2 * L * 33 + L + 4 * L + 4 * 32 + tw * tw + L) * 4;
@@ -382,7 +391,7 @@ int launch_swinv2_window_attention(const void* qkv, const float* bias_tab, const
   const int blocks = static_cast<int>(items < num_sms() * 8 ? items : num_sms() * 8);
   swinv2_attn_f32_kernel<<<blocks, V2_THREADS, smem, stream>>>(static_cast<const float*>(qkv), bias_tab, logit_scale,
                                                                static_cast<float*>(out), static_cast<int>(items), C, heads, g, nW,
-                                                               mask_value);
+                                                               mask_value, tok_order);
   CSVIT_CUDA(cudaGetLastError());
   return 0;
 }

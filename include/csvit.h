@@ -155,11 +155,12 @@ CSVIT_API int csvit_set_attention_impl(int use_tcgen05);
  *   bias_tab    [heads, (2ws-1)^2] fp32 = 16 sigmoid(continuous_position_bias_mlp(relative_coords_table))  V2:460-472, 489-510
  *   logit_scale [heads] fp32 = exp(min(logit_scale, ln 100))                                      V2:455
  *   mask_repeat how often the {0,-100} shift mask is added (HF adds it twice, V2:466-474: pass 2)
+ *   out_token_order 1: out rows in TOKEN order (window_reverse + roll(+shift), V2:693-701, folded into the store), 0: window order
  * ws^2 must be a multiple of 16 and <= 256 (window 16: 256 tokens; window 8: 64).  bf16 / fp16: tensor-core kernel with
  * online softmax; fp32: exact kernel (validation mode). */
 CSVIT_API int csvit_swinv2_window_attention(const void* qkv, const float* bias_tab, const float* logit_scale, void* out,
                                             int dtype, int B, int H, int W, int C, int heads, int ws, int shift,
-                                            int mask_repeat, void* stream);
+                                            int mask_repeat, int out_token_order, void* stream);
 
 /* Post-norm residual LayerNorm of SwinV2 (V2:707-712, 387, 282) with the next GEMM's operand copy folded in:
  *   out[r, :] = (resid ? resid[r, :] : 0) + LayerNorm(y[r, :]) * gamma + beta        fp32, rows in token order;

@@ -50,6 +50,12 @@ def test_swinv2_window_attention(ops, H, ws, heads, shift, dtype):
     ref = (s.softmax(-1) @ v).transpose(1, 2).reshape(B * H * W, C)
     tol = {torch.bfloat16: 1.5e-2, torch.float16: 2e-3, torch.float32: 1e-5}[dtype]
     assert rel(out, ref) < tol
+    # token-ordered output = the window-ordered rows scattered by the window index map, bit for bit
+    out_tok = ops.swinv2_window_attention(qkv, tab, scale, B, H, W, heads, ws, shift, token_order=True)
+    idx = ops.window_index_map(H, W, ws, shift).long()
+    want_tok = torch.empty_like(out).view(B, H * W, C)
+    want_tok[:, idx] = out.view(B, H * W, C)
+    assert torch.equal(out_tok.view(B, H * W, C), want_tok)
     if shift:   # mask_repeat is honoured (a single add changes the result only where -100 does not already saturate)
         out1 = ops.swinv2_window_attention(qkv, tab, scale, B, H, W, heads, ws, shift, mask_repeat=0)
         assert rel(out1, ref) > tol

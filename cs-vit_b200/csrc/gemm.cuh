@@ -69,11 +69,11 @@ __device__ __forceinline__ __half2 gelu_h2(__half2 x) {
   q = __hfma2(q, ax, __float2half2_rn(-5.332621707e-02f));
   q = __hfma2(q, ax, __float2half2_rn(-4.588742488e-01f));
   q = __hfma2(q, ax, __float2half2_rn(-1.151155207e+00f));
-  q = __hmul2(q, ax);
+  q = __hfma2(q, ax, __float2half2_rn(-1.0f));            // q - 1: the exponential below is 0.5 erfc(|x| / sqrt2) = Phi(-|x|)
   __half2 e;
   asm("ex2.approx.f16x2 %0, %1;" : "=r"(*reinterpret_cast<uint32_t*>(&e)) : "r"(*reinterpret_cast<const uint32_t*>(&q)));
-  const __half2 hx = __hmul2(x, __float2half2_rn(0.5f));
-  return __hfma2(__habs2(hx), __hsub2(__float2half2_rn(1.0f), e), hx);
+  // x Phi(x) = relu(x) - |x| Phi(-|x|): two instructions (max, fma) instead of the four of hx + |hx| (1 - erfc)
+  return __hfma2(__hneg2(__habs2(x)), e, __hmax2(x, __float2half2_rn(0.0f)));
 }
 // (a, b) fp32 pre-activations -> GELU -> one packed 16-bit pair in the output format.
 __device__ __forceinline__ uint32_t gelu_pack16(bool bf, float a, float b) {

@@ -121,6 +121,85 @@ ln_rows_kernel(const float* __restrict__ x, const float* __restrict__ gamma, con
   }
 }
 
+// Narrow rows (C <= 256: Swin stages 0-1): LPR lanes share a row, so one instruction stream serves 32 / LPR rows at once and a
+// reduction takes log2(LPR) shuffle steps.  The warp-per-row form above spends ~130 warp instructions on a 512-byte row (ncu: issue
+// slots 73 % busy, 4.85 TB/s); this one ~30, which leaves the kernel to the memory system.  Each lane holds J float4 of its row
+// (element i4 = lane_in_row + LPR * j: a group's LPR lanes read LPR * 16 contiguous bytes per load), gamma / beta stay in registers
+// across the grid-stride loop.  Modes: identity and window-scatter (as ln_rows_kernel with C >= scatter_min_c).
+template <int LPR, int J, int PASSES, typename OutT>
+__global__ void __launch_bounds__(256)
+ln_rows_sub_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                   OutT* __restrict__ out, long long ldo, int rows, int mode, WinGeom g) {
+  constexpr int C = LPR * J * 4;
+  constexpr int RPW = 32 / LPR;                      // rows per warp per pass
+  const int lane = threadIdx.x & 31;
+  const int sub = lane / LPR, li = lane % LPR;
+  const int warps_total = (gridDim.x * blockDim.x) >> 5;
+  float4 gm[J], bt[J];
+#pragma unroll
+  for (int j = 0; j < J; ++j) {
+    gm[j] = __ldg(reinterpret_cast<const float4*>(gamma) + li + LPR * j);
+    bt[j] = __ldg(reinterpret_cast<const float4*>(beta) + li + LPR * j);
+  }
+  for (int row0 = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * (RPW * PASSES); row0 < rows; row0 += warps_total * RPW * PASSES) {
+    float4 v[PASSES][J];
+#pragma unroll
+    for (int p = 0; p < PASSES; ++p) {
+      const int row = row0 + p * RPW + sub;
+      if (row < rows) {
+        const float4* src = reinterpret_cast<const float4*>(x + static_cast<long long>(row) * C);
+#pragma unroll
+        for (int j = 0; j < J; ++j) v[p][j] = src[li + LPR * j];
+      } else {
+#pragma unroll
+        for (int j = 0; j < J; ++j) v[p][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+#pragma unroll
+    for (int p = 0; p < PASSES; ++p) {
+      const int row = row0 + p * RPW + sub;
+      float sum = 0.f;
+#pragma unroll
+      for (int j = 0; j < J; ++j) sum += (v[p][j].x + v[p][j].y) + (v[p][j].z + v[p][j].w);
+#pragma unroll
+      for (int o = LPR / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      const float mean = sum * (1.0f / float(C));
+      float sq = 0.f;
+#pragma unroll
+      for (int j = 0; j < J; ++j) {
+        const float a = v[p][j].x - mean, b = v[p][j].y - mean, c = v[p][j].z - mean, d = v[p][j].w - mean;
+        sq += (a * a + b * b) + (c * c + d * d);
+      }
+#pragma unroll
+      for (int o = LPR / 2; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+      const float rstd = rsqrtf(sq * (1.0f / float(C)) + eps);
+      if (row < rows) {
+        long long drow = row;
+        if (mode == LN_WINDOW) {
+          const int b = row / g.N, t = row - b * g.N;
+          drow = static_cast<long long>(b) * g.N + win_token_to_row(g, t);
+        }
+        OutT* orow = out + drow * ldo;
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+          const int e = (li + LPR * j) << 2;
+          Store4<OutT>::st(orow + e, (v[p][j].x - mean) * rstd * gm[j].x + bt[j].x, (v[p][j].y - mean) * rstd * gm[j].y + bt[j].y,
+                           (v[p][j].z - mean) * rstd * gm[j].z + bt[j].z, (v[p][j].w - mean) * rstd * gm[j].w + bt[j].w);
+        }
+      }
+    }
+  }
+}
+
+template <int LPR, int J, typename OutT>
+static void launch_ln_sub(const float* x, const float* gamma, const float* beta, float eps, OutT* out, long long ldo, int rows,
+                          int mode, const WinGeom& g, cudaStream_t stream) {
+  constexpr int PASSES = 2;
+  const int rows_per_warp = (32 / LPR) * PASSES;
+  const int warps = (rows + rows_per_warp - 1) / rows_per_warp;
+  ln_rows_sub_kernel<LPR, J, PASSES, OutT><<<(warps + 7) / 8, 256, 0, stream>>>(x, gamma, beta, eps, out, ldo, rows, mode, g);
+}
+
 template <int MAXJ, int R, typename OutT>
 static void launch_ln_cfg(const float* x, const float* gamma, const float* beta, float eps, OutT* out, long long ldo,
                           int rows, int C, int mode, const WinGeom& g, cudaStream_t stream) {
@@ -140,6 +219,15 @@ template <typename OutT>
 static int launch_ln_t(const float* x, const float* gamma, const float* beta, float eps, OutT* out, long long ldo,
                        int rows, int C, int mode, const WinGeom& g, cudaStream_t stream) {
   const int Cout = mode == LN_MERGE2X2 ? 4 * C : C;
+  static const bool sub_rows = [] { const char* e = getenv("CSVIT_LN_SUBROWS"); return !(e && e[0] == '0'); }();
+  if (sub_rows && mode != LN_MERGE2X2 && (C == 96 || C == 128 || C == 192 || C == 256)) {   // narrow rows: several rows per warp pass
+    if (C == 128) launch_ln_sub<8, 4, OutT>(x, gamma, beta, eps, out, ldo, rows, mode, g, stream);
+    else if (C == 96) launch_ln_sub<8, 3, OutT>(x, gamma, beta, eps, out, ldo, rows, mode, g, stream);
+    else if (C == 256) launch_ln_sub<16, 4, OutT>(x, gamma, beta, eps, out, ldo, rows, mode, g, stream);
+    else launch_ln_sub<16, 3, OutT>(x, gamma, beta, eps, out, ldo, rows, mode, g, stream);
+    CSVIT_CUDA(cudaGetLastError());
+    return 0;
+  }
   if (Cout <= 128) launch_ln_cfg<1, 8, OutT>(x, gamma, beta, eps, out, ldo, rows, C, mode, g, stream);
   else if (Cout <= 256) launch_ln_cfg<2, 4, OutT>(x, gamma, beta, eps, out, ldo, rows, C, mode, g, stream);
   else if (Cout <= 512) launch_ln_cfg<4, 2, OutT>(x, gamma, beta, eps, out, ldo, rows, C, mode, g, stream);

@@ -228,6 +228,7 @@ static int launch_ln_t(const float* x, const float* gamma, const float* beta, fl
     CSVIT_CUDA(cudaGetLastError());
     return 0;
   }
+  // (the same layout with LPR = 32 at C = 512 measured 30.7 vs 29.0 us: wide rows are not instruction-bound, they keep the warp-per-row form)
   if (Cout <= 128) launch_ln_cfg<1, 8, OutT>(x, gamma, beta, eps, out, ldo, rows, C, mode, g, stream);
   else if (Cout <= 256) launch_ln_cfg<2, 4, OutT>(x, gamma, beta, eps, out, ldo, rows, C, mode, g, stream);
   else if (Cout <= 512) launch_ln_cfg<4, 2, OutT>(x, gamma, beta, eps, out, ldo, rows, C, mode, g, stream);

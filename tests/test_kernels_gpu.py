@@ -165,6 +165,26 @@ def test_linear_epilogues(ops):
         assert rel(xi, ref) < 1e-5
 
 
+@pytest.mark.parametrize("C", [96, 128, 192, 256, 384, 512])
+@pytest.mark.parametrize("rows", [1, 7, 1001, 4099])
+def test_layernorm_ragged_row_counts(ops, C, rows):
+    """Identity mode with row counts that are not multiples of the rows a warp handles per pass (narrow-row kernel: 4-16 rows per
+    warp; wide rows: 1-2), fp32 and 16-bit outputs, and the window mode of the same widths on whole images."""
+    g = torch.Generator(device="cuda").manual_seed(C + rows)
+    x = torch.randn(rows, C, device="cuda", generator=g) * 3 - 1
+    gamma = torch.randn(C, device="cuda", generator=g)
+    beta = torch.randn(C, device="cuda", generator=g)
+    ref = torch.nn.functional.layer_norm(x, (C,), gamma, beta, 1e-5)
+    assert rel(ops.layernorm(x, gamma, beta, 1e-5), ref) < 2e-6
+    assert rel(ops.layernorm(x, gamma, beta, 1e-5, out_dtype=torch.bfloat16), ref) < 4e-3
+    if rows == 1001:
+        B, H = 3, 14
+        xi = torch.randn(B * H * H, C, device="cuda", generator=g)
+        idx = ops.window_index_map(H, H, 7, 3).long()
+        want = torch.nn.functional.layer_norm(xi.view(B, H * H, C)[:, idx].reshape(-1, C), (C,), gamma, beta, 1e-5)
+        assert rel(ops.layernorm(xi, gamma, beta, 1e-5, mode=ops.LN_WINDOW, grid=(H, H), ws=7, shift=3), want) < 2e-6
+
+
 @pytest.mark.parametrize("C,mode", [(96, 0), (128, 1), (512, 1), (1024, 0), (256, 2), (512, 2)])
 def test_layernorm(ops, C, mode):
     g = torch.Generator(device="cuda").manual_seed(C + mode)

@@ -74,6 +74,47 @@ def main() -> None:
                           "weight_seed": 0, "restatement_rel_err": err,
                           "pixels_sum": float(x.double().sum()), "stage_token_stride": STAGE_TOKEN_STRIDE}
 
+    # ---- gradient golden: HF autograd through Swinv2Model under a linear loss <features, R> (the pin for the backward path that
+    # round 2 builds; the restatement's autograd is asserted against it here and in the CPU suite) -------------------------
+    from oracle.make_train_goldens import projections
+    for name, (variant, size, window, batch, seed) in {"train_swinv2_xs_w16_linear": ("swinv2_xs", 256, 16, 2, 21)}.items():
+        cfg = swinv2_config_dict(variant, size, window)
+        model = Swinv2Model(Swinv2Config(**{k: v for k, v in cfg.items() if k not in ("architectures", "model_type")}),
+                            add_pooling_layer=False).train()       # dropout / drop-path are 0: train == eval numerically
+        sd = random_swinv2_state_dict(variant, seed=0)
+        model.load_state_dict(sd, strict=True)
+        x = pixels(batch, size, seed)
+        feats = model(pixel_values=x).last_hidden_state
+        R = torch.randn(feats.shape, generator=torch.Generator().manual_seed(5))
+        loss = (feats * R).sum()
+        loss.backward()
+        _, depths, heads = SWINV2_VARIANTS[variant]
+        leaf = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+        got = v2.swinv2_forward(x, leaf, depths, heads, window=window)
+        (got * R).sum().backward()
+        gold = {"features": feats.detach().numpy().astype(np.float32), "loss": np.array(loss.item(), dtype=np.float64)}
+        names, norms, projs, worst = [], [], [], 0.0
+        for pname, p in model.named_parameters():
+            g = p.grad.detach().float()
+            go = leaf[pname].grad
+            err = ((go - g).norm() / g.norm().clamp_min(1e-30)).item()
+            worst = max(worst, err)
+            names.append(pname)
+            norms.append(g.double().norm().item())
+            projs.append(projections(g, pname))
+            if g.numel() <= 4096:
+                gold["grad/" + pname] = g.numpy().astype(np.float32)
+        assert worst < 1e-4, f"autograd of oracle/swinv2_restated.py deviates from HF's by {worst:.2e}"
+        gold["param_names"] = np.array(names)
+        gold["grad_norm"] = np.array(norms, dtype=np.float64)
+        gold["grad_proj"] = np.stack(projs).astype(np.float64)
+        np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), **gold)
+        print(f"{name}: {len(names)} parameters, global grad norm {float(np.sqrt((gold['grad_norm'] ** 2).sum())):.4e}, "
+              f"restatement autograd vs HF autograd worst parameter {worst:.2e}")
+        manifest[name] = {"variant": variant, "image_size": size, "window": window, "batch": batch, "pixel_seed": seed, "weight_seed": 0,
+                          "projection_seed": 5, "restatement_grad_rel_err": worst, "pixels_sum": float(x.double().sum()),
+                          "stage_token_stride": STAGE_TOKEN_STRIDE, "kind": "gradients"}
+
     # ---- integer goldens from HF's own functions ------------------------------------------------------------------
     ints = {}
     for H, ws, shift in [(64, 16, 0), (64, 16, 8), (32, 16, 8), (16, 16, 0), (8, 8, 0), (64, 8, 4), (32, 8, 4), (16, 8, 4)]:

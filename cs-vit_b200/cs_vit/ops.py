@@ -245,6 +245,53 @@ def mlp_fused(xn: torch.Tensor, w1: torch.Tensor, b1: torch.Tensor, w2: torch.Te
 
 
 # ---------------------------------------------------------------------------------------------- attention
+ATTN_FUSED_WIDTHS = (128, 256)
+_LOG2E = 1.4426950408889634
+
+
+def pack_attn_fused(wq: torch.Tensor, wk: torch.Tensor, wv: torch.Tensor, bq: torch.Tensor, bk: torch.Tensor, bv: torch.Tensor,
+                    table: torch.Tensor, rel_index: torch.Tensor, dtype: torch.dtype):
+    """Operands of ``csvit_swin_attn_fused`` from the HF parameters (one-time packing, layouts in include/csvit.h):
+    per-head q|k|v weight rows ``[3C, C]`` (16 bit), the matching fp32 bias with the q part pre-scaled by log2(e)/sqrt(32), and the
+    fp16 relative-position-bias operand ``[heads*64, 64]`` (key-major, log2 domain, -30000 in the padding key rows)."""
+    C = wq.shape[0]
+    heads = C // 32
+    w = torch.stack([wq.detach().view(heads, 32, C), wk.detach().view(heads, 32, C), wv.detach().view(heads, 32, C)], 1)
+    qs = _LOG2E / 32.0 ** 0.5
+    b = torch.stack([bq.detach().float().view(heads, 32) * qs, bk.detach().float().view(heads, 32), bv.detach().float().view(heads, 32)], 1)
+    L = rel_index.shape[0]
+    bias = table.detach().float()[rel_index.reshape(-1).long()].view(L, L, heads).permute(2, 0, 1)      # [h, i, j]
+    op = torch.zeros(heads, 64, 64, dtype=torch.float32, device=table.device)
+    op[:, L:, :L] = -30000.0
+    op[:, :L, :L] = bias.transpose(1, 2) * _LOG2E                                                      # [h, j, i]
+    return (w.reshape(3 * C, C).to(dtype).contiguous(), b.reshape(3 * C).contiguous(),
+            op.to(torch.float16).reshape(heads * 64, 64).contiguous())
+
+
+def swin_attn_fused(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float, wqkv_h: torch.Tensor, bqkv_h: torch.Tensor,
+                    bias_op: torch.Tensor, B: int, H: int, W: int, heads: int, ws: int, shift: int,
+                    out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """LayerNorm + shift/partition + Q/K/V + window attention + reverse/un-shift in one tcgen05 kernel (``csvit_swin_attn_fused``):
+    x fp32 ``[B*H*W, C]`` -> token-ordered 16-bit context ``[B*H*W, C]`` (the output projection follows on plain rows)."""
+    _dev(x, gamma, beta, wqkv_h, bqkv_h, bias_op, out)
+    if x.dtype != torch.float32 or not x.is_contiguous() or x.dim() != 2:
+        raise ValueError("swin_attn_fused input must be contiguous float32 [B*H*W, C]")
+    rows, C = x.shape
+    if rows != B * H * W or C != heads * 32 or C not in ATTN_FUSED_WIDTHS:
+        raise ValueError(f"swin_attn_fused: rows={rows} C={C} heads={heads} not supported (C in {ATTN_FUSED_WIDTHS}, head_dim 32)")
+    if wqkv_h.dtype not in (torch.bfloat16, torch.float16) or tuple(wqkv_h.shape) != (3 * C, C) or not wqkv_h.is_contiguous():
+        raise ValueError("swin_attn_fused: wqkv_h must be contiguous 16-bit [3C, C]")
+    if bqkv_h.dtype != torch.float32 or bqkv_h.numel() != 3 * C or bias_op.dtype != torch.float16 or tuple(bias_op.shape) != (heads * 64, 64):
+        raise ValueError("swin_attn_fused: bqkv_h must be float32 [3C] and bias_op float16 [heads*64, 64]")
+    if out is None:
+        out = torch.empty(rows, C, dtype=wqkv_h.dtype, device=x.device)
+    L = ws * ws
+    _call("csvit_swin_attn_fused", x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), float(eps), wqkv_h.data_ptr(), bqkv_h.data_ptr(),
+          bias_op.data_ptr(), out.data_ptr(), _code(wqkv_h.dtype), B, H, W, C, heads, ws, shift, _stream(),
+          flops=float(rows) * (6.0 * C * C + 4.0 * L * C), nbytes=float(rows) * C * 6.0)
+    return out
+
+
 def window_attention(qkv: torch.Tensor, bias_exp: torch.Tensor, B: int, H: int, W: int, heads: int, ws: int,
                      shift: int, bias_mma: Optional[torch.Tensor] = None, token_order: bool = False) -> torch.Tensor:
     """``bias_exp``: ``expand_rel_bias`` table ``[h,L,L]`` (fp32 kernel and the tcgen05 16-bit kernel) or, for backward

@@ -27,6 +27,11 @@ int launch_ln_gemm(const float* x, const float* gamma, const float* beta, float 
 int launch_window_attention_tc(const void* qkv, const float* bias_plain, void* out, int dtype, int B, int H, int W, int C,
                                int heads, int ws, int shift, cudaStream_t stream);
 
+// attn_fused.cu
+int launch_swin_attn_fused(const float* x, const float* gamma, const float* beta, float eps, const void* wqkv_h, const float* bqkv_h,
+                           const void* bias_op, void* ctx, int dtype, int B, int H, int W, int C, int heads, int ws, int shift,
+                           cudaStream_t stream);
+
 // mlp_fused.cu
 int launch_mlp_fused(const void* xn, long long ldxn, const void* W1, long long ldw1, const float* b1, const void* W2,
                      long long ldw2, const float* b2, float* x, long long ldx, int dtype, int M, int C, cudaStream_t stream);

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define CSVIT_ABI_VERSION 3
+#define CSVIT_ABI_VERSION 4
 
 #if defined(__GNUC__)
 #define CSVIT_API __attribute__((visibility("default")))
@@ -147,6 +147,21 @@ CSVIT_API int csvit_window_attention_ex(const void* qkv, const float* bias, cons
                                         void* stream);
 
 CSVIT_API int csvit_set_attention_impl(int use_tcgen05);
+
+/* Fused shifted-window attention (north-star kernel; tcgen05 / TMEM, C in {128, 256}, window 7, head_dim 32): one launch from the
+ * fp32 residual stream x[B*H*W, C] to the TOKEN-ordered 16-bit attention context ctx[B*H*W, C],
+ *   ctx = window_reverse(roll(+s)( softmax(Q K^T / sqrt(32) + bias + shift_mask) V )),  Q|K|V = LN(x gathered by roll(-s) + window_partition) Wqkv^T + b
+ * replacing layernorm_before, pad / roll / window_partition, query / key / value, the attention core and window_reverse / roll
+ * (HF:swin/modeling_swin.py:404-459, 556-582, 604-636).  LN output, Q, K, V, logits and probabilities stay in SMEM / TMEM: 4C bytes
+ * read + 2C written per token.  Two 49-token windows share a 128-row MMA tile (block structure in the operands, see attn_fused.cu).
+ *   wqkv_h  [3C, C] 16-bit (dtype), rows re-ordered PER HEAD: head h owns rows 96h..96h+95 = Wq[32h..] | Wk[32h..] | Wv[32h..]
+ *   bqkv_h  [3C] fp32 in the same order, the q part multiplied by log2(e)/sqrt(32) (the softmax runs in the log2 domain)
+ *   bias_op [heads*64, 64] fp16: bias_op[64h + j, i] = log2(e) * table[rel_pos_index(i, j), h] for i, j < 49; -30000 for 49 <= j
+ *           (padding key columns), 0 for i >= 49.  It enters the logits as a second K block of the S MMA against a one-hot operand.
+ * The output projection + residual (csvit_linear with resid) follows on plain rows. */
+CSVIT_API int csvit_swin_attn_fused(const float* x, const float* gamma, const float* beta, float eps, const void* wqkv_h,
+                                    const float* bqkv_h, const void* bias_op, void* ctx, int dtype, int B, int H, int W, int C,
+                                    int heads, int ws, int shift, void* stream);
 
 /* ---- SwinV2 ("V2:" = transformers/models/swinv2/modeling_swinv2.py) ---------------------------
  * Scaled-cosine window attention on window-ordered qkv[B*H*W, 3C] (layout as csvit_window_attention):

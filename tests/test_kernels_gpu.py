@@ -256,6 +256,51 @@ def test_window_attention(ops, H, heads, shift, dtype):
         assert torch.equal(out3, out)
 
 
+def fused_attention_case(ops, B, H, heads, shift, dtype, seed, zero_bias=False):
+    """Inputs + fp32 torch reference of the attention half up to the token-ordered context (HF:404-459, 604-636)."""
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    W, C, ws, L = H, heads * 32, 7, 49
+    N = H * W
+    nW = (H // ws) * (W // ws)
+    x = torch.randn(B * N, C, device="cuda", generator=g) * 1.5 + 0.3
+    gamma = 1.0 + 0.2 * torch.randn(C, device="cuda", generator=g)
+    beta = 0.1 * torch.randn(C, device="cuda", generator=g)
+    wq, wk, wv = (torch.randn(C, C, device="cuda", generator=g) * C ** -0.5 for _ in range(3))
+    bq, bk, bv = (0.2 * torch.randn(C, device="cuda", generator=g) for _ in range(3))
+    table = torch.randn(169, heads, device="cuda", generator=g) * (0.0 if zero_bias else 1.0)
+    rel_index = ops.rel_pos_index(ws).long()
+    xn = torch.nn.functional.layer_norm(x, (C,), gamma, beta, 1e-5)
+    idx = ops.window_index_map(H, W, ws, shift).long()
+    xw = xn.view(B, N, C)[:, idx].reshape(B * nW, L, C).to(dtype).float()
+    q = (xw @ wq.to(dtype).float().T + bq).view(B * nW, L, heads, 32).transpose(1, 2)
+    k = (xw @ wk.to(dtype).float().T + bk).view(B * nW, L, heads, 32).transpose(1, 2)
+    v = (xw @ wv.to(dtype).float().T + bv).view(B * nW, L, heads, 32).transpose(1, 2)
+    s = q @ k.transpose(-1, -2) / math.sqrt(32) + ops.expand_rel_bias(table, ws)[None]
+    if shift:
+        s = (s.view(B, nW, heads, L, L) + ops.shift_mask(H, W, ws, shift)[None, :, None]).view(B * nW, heads, L, L)
+    ref_win = (s.softmax(-1) @ v).transpose(1, 2).reshape(B, N, C)
+    ref = torch.empty_like(ref_win)
+    ref[:, idx] = ref_win
+    packed = ops.pack_attn_fused(wq, wk, wv, bq, bk, bv, table, rel_index, dtype)
+    return x, gamma, beta, packed, ref.reshape(B * N, C)
+
+
+@pytest.mark.parametrize("B,H,heads,shift", [(2, 56, 4, 0), (2, 56, 4, 3), (3, 28, 8, 0), (3, 28, 8, 3), (3, 14, 4, 3), (3, 7, 4, 0),
+                                            (5, 7, 8, 0), (40, 28, 4, 3)])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_swin_attn_fused(ops, B, H, heads, shift, dtype):
+    """csvit_swin_attn_fused (LN + shift/partition + QKV + window attention + reverse on tcgen05) vs fp32 torch math; odd window
+    counts (a half-empty last tile), masked and unmasked windows, both operand formats, more tiles than SMs."""
+    x, gamma, beta, (wqkv_h, bqkv_h, bias_op), ref = fused_attention_case(ops, B, H, heads, shift, dtype, seed=B * 131 + H * 7 + heads + shift)
+    out = ops.swin_attn_fused(x, gamma, beta, 1e-5, wqkv_h, bqkv_h, bias_op, B, H, H, heads, 7, shift)
+    torch.cuda.synchronize()
+    assert torch.isfinite(out.float()).all()
+    tol = 1.2e-2 if dtype == torch.bfloat16 else 2.5e-3
+    assert rel(out, ref) < tol
+    out2 = ops.swin_attn_fused(x, gamma, beta, 1e-5, wqkv_h, bqkv_h, bias_op, B, H, H, heads, 7, shift)
+    assert torch.equal(out, out2), "fused attention must be deterministic"
+
+
 @pytest.mark.parametrize("Lq,S", [(52, 52), (3, 49), (3, 3), (1, 8)])
 def test_dense_attention(ops, Lq, S):
     g = torch.Generator(device="cuda").manual_seed(Lq + S)

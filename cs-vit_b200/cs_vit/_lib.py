@@ -35,7 +35,7 @@ SIGNATURES = {
                         c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_longlong, c_void_p],
     "csvit_mlp_fused": [c_void_p, c_longlong, c_void_p, c_longlong, c_void_p, c_void_p, c_longlong, c_void_p, c_void_p,
                         c_longlong, c_int, c_int, c_int, c_void_p],
-    "csvit_swin_attn_fused": [c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+    "csvit_swin_attn_fused": [c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                               c_int, c_int, c_int, c_int, c_void_p],
     "csvit_set_gemm_tuning": [c_int, c_int, c_int, c_int],
     "csvit_expand_rel_bias_mma": [c_void_p, c_void_p, c_int, c_int, c_void_p],

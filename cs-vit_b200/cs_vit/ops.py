@@ -250,30 +250,33 @@ _LOG2E = 1.4426950408889634
 
 
 def pack_attn_fused(wq: torch.Tensor, wk: torch.Tensor, wv: torch.Tensor, bq: torch.Tensor, bk: torch.Tensor, bv: torch.Tensor,
-                    table: torch.Tensor, rel_index: torch.Tensor, dtype: torch.dtype):
+                    table: torch.Tensor, rel_index: torch.Tensor, dtype: torch.dtype, gamma: torch.Tensor, beta: torch.Tensor):
     """Operands of ``csvit_swin_attn_fused`` from the HF parameters (one-time packing, layouts in include/csvit.h):
-    per-head q|k|v weight rows ``[3C, C]`` (16 bit), the matching fp32 bias with the q part pre-scaled by log2(e)/sqrt(32), and the
-    fp16 relative-position-bias operand ``[heads*64, 64]`` (key-major, log2 domain, -30000 in the padding key rows)."""
+    per-head q|k|v weight rows ``[3C, C]`` (16 bit) with layernorm_before's ``gamma`` folded into the columns, the matching fp32
+    bias (``b + W beta``, q part pre-scaled by log2(e)/sqrt(32)), and the fp16 relative-position-bias rows ``[heads*49, 56]``
+    (query-slot-major, log2 domain)."""
     C = wq.shape[0]
     heads = C // 32
-    w = torch.stack([wq.detach().view(heads, 32, C), wk.detach().view(heads, 32, C), wv.detach().view(heads, 32, C)], 1)
+    g64, be64 = gamma.detach().double(), beta.detach().double()
+    fold_w = lambda w_: (w_.detach().double() * g64[None, :]).float()
+    fold_b = lambda w_, b_: (b_.detach().double() + w_.detach().double() @ be64).float()
+    w = torch.stack([fold_w(wq).view(heads, 32, C), fold_w(wk).view(heads, 32, C), fold_w(wv).view(heads, 32, C)], 1)
     qs = _LOG2E / 32.0 ** 0.5
-    b = torch.stack([bq.detach().float().view(heads, 32) * qs, bk.detach().float().view(heads, 32), bv.detach().float().view(heads, 32)], 1)
+    b = torch.stack([fold_b(wq, bq).view(heads, 32) * qs, fold_b(wk, bk).view(heads, 32), fold_b(wv, bv).view(heads, 32)], 1)
     L = rel_index.shape[0]
     bias = table.detach().float()[rel_index.reshape(-1).long()].view(L, L, heads).permute(2, 0, 1)      # [h, i, j]
-    op = torch.zeros(heads, 64, 64, dtype=torch.float32, device=table.device)
-    op[:, L:, :L] = -30000.0
-    op[:, :L, :L] = bias.transpose(1, 2) * _LOG2E                                                      # [h, j, i]
+    op = torch.zeros(heads, L, 56, dtype=torch.float32, device=table.device)
+    op[:, :, :L] = bias * _LOG2E                                                                        # [h, query slot, key slot]
     return (w.reshape(3 * C, C).to(dtype).contiguous(), b.reshape(3 * C).contiguous(),
-            op.to(torch.float16).reshape(heads * 64, 64).contiguous())
+            op.to(torch.float16).reshape(heads * L, 56).contiguous())
 
 
-def swin_attn_fused(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float, wqkv_h: torch.Tensor, bqkv_h: torch.Tensor,
+def swin_attn_fused(x: torch.Tensor, eps: float, wqkv_h: torch.Tensor, bqkv_h: torch.Tensor,
                     bias_op: torch.Tensor, B: int, H: int, W: int, heads: int, ws: int, shift: int,
                     out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """LayerNorm + shift/partition + Q/K/V + window attention + reverse/un-shift in one tcgen05 kernel (``csvit_swin_attn_fused``):
     x fp32 ``[B*H*W, C]`` -> token-ordered 16-bit context ``[B*H*W, C]`` (the output projection follows on plain rows)."""
-    _dev(x, gamma, beta, wqkv_h, bqkv_h, bias_op, out)
+    _dev(x, wqkv_h, bqkv_h, bias_op, out)
     if x.dtype != torch.float32 or not x.is_contiguous() or x.dim() != 2:
         raise ValueError("swin_attn_fused input must be contiguous float32 [B*H*W, C]")
     rows, C = x.shape
@@ -281,12 +284,12 @@ def swin_attn_fused(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, ep
         raise ValueError(f"swin_attn_fused: rows={rows} C={C} heads={heads} not supported (C in {ATTN_FUSED_WIDTHS}, head_dim 32)")
     if wqkv_h.dtype not in (torch.bfloat16, torch.float16) or tuple(wqkv_h.shape) != (3 * C, C) or not wqkv_h.is_contiguous():
         raise ValueError("swin_attn_fused: wqkv_h must be contiguous 16-bit [3C, C]")
-    if bqkv_h.dtype != torch.float32 or bqkv_h.numel() != 3 * C or bias_op.dtype != torch.float16 or tuple(bias_op.shape) != (heads * 64, 64):
-        raise ValueError("swin_attn_fused: bqkv_h must be float32 [3C] and bias_op float16 [heads*64, 64]")
+    if bqkv_h.dtype != torch.float32 or bqkv_h.numel() != 3 * C or bias_op.dtype != torch.float16 or tuple(bias_op.shape) != (heads * 49, 56) or not bias_op.is_contiguous():
+        raise ValueError("swin_attn_fused: bqkv_h must be float32 [3C] and bias_op contiguous float16 [heads*49, 56]")
     if out is None:
         out = torch.empty(rows, C, dtype=wqkv_h.dtype, device=x.device)
     L = ws * ws
-    _call("csvit_swin_attn_fused", x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), float(eps), wqkv_h.data_ptr(), bqkv_h.data_ptr(),
+    _call("csvit_swin_attn_fused", x.data_ptr(), float(eps), wqkv_h.data_ptr(), bqkv_h.data_ptr(),
           bias_op.data_ptr(), out.data_ptr(), _code(wqkv_h.dtype), B, H, W, C, heads, ws, shift, _stream(),
           flops=float(rows) * (6.0 * C * C + 4.0 * L * C), nbytes=float(rows) * C * 6.0)
     return out

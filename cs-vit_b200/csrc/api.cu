@@ -177,11 +177,11 @@ int csvit_expand_rel_bias_mma(const float* table, float* out, int heads, int ws,
   return launch_expand_rel_bias_mma(table, out, heads, S(stream));
 }
 
-int csvit_swin_attn_fused(const float* x, const float* gamma, const float* beta, float eps, const void* wqkv_h, const float* bqkv_h,
+int csvit_swin_attn_fused(const float* x, float eps, const void* wqkv_h, const float* bqkv_h,
                           const void* bias_op, void* ctx, int dtype, int B, int H, int W, int C, int heads, int ws, int shift,
                           void* stream) {
-  CSVIT_REQUIRE(x && gamma && beta && wqkv_h && bqkv_h && bias_op && ctx, "swin_attn_fused: null operand");
-  return launch_swin_attn_fused(x, gamma, beta, eps, wqkv_h, bqkv_h, bias_op, ctx, dtype, B, H, W, C, heads, ws, shift, S(stream));
+  CSVIT_REQUIRE(x && wqkv_h && bqkv_h && bias_op && ctx, "swin_attn_fused: null operand");
+  return launch_swin_attn_fused(x, eps, wqkv_h, bqkv_h, bias_op, ctx, dtype, B, H, W, C, heads, ws, shift, S(stream));
 }
 
 int csvit_set_attention_impl(int use_tcgen05) {

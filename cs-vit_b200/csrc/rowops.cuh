@@ -28,7 +28,7 @@ int launch_window_attention_tc(const void* qkv, const float* bias_plain, void* o
                                int heads, int ws, int shift, cudaStream_t stream);
 
 // attn_fused.cu
-int launch_swin_attn_fused(const float* x, const float* gamma, const float* beta, float eps, const void* wqkv_h, const float* bqkv_h,
+int launch_swin_attn_fused(const float* x, float eps, const void* wqkv_h, const float* bqkv_h,
                            const void* bias_op, void* ctx, int dtype, int B, int H, int W, int C, int heads, int ws, int shift,
                            cudaStream_t stream);
 

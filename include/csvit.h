@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define CSVIT_ABI_VERSION 4
+#define CSVIT_ABI_VERSION 5
 
 #if defined(__GNUC__)
 #define CSVIT_API __attribute__((visibility("default")))
@@ -154,13 +154,15 @@ CSVIT_API int csvit_set_attention_impl(int use_tcgen05);
  * replacing layernorm_before, pad / roll / window_partition, query / key / value, the attention core and window_reverse / roll
  * (HF:swin/modeling_swin.py:404-459, 556-582, 604-636).  LN output, Q, K, V, logits and probabilities stay in SMEM / TMEM: 4C bytes
  * read + 2C written per token.  Two 49-token windows share a 128-row MMA tile (block structure in the operands, see attn_fused.cu).
- *   wqkv_h  [3C, C] 16-bit (dtype), rows re-ordered PER HEAD: head h owns rows 96h..96h+95 = Wq[32h..] | Wk[32h..] | Wv[32h..]
- *   bqkv_h  [3C] fp32 in the same order, the q part multiplied by log2(e)/sqrt(32) (the softmax runs in the log2 domain)
- *   bias_op [heads*64, 64] fp16: bias_op[64h + j, i] = log2(e) * table[rel_pos_index(i, j), h] for i, j < 49; -30000 for 49 <= j
- *           (padding key columns), 0 for i >= 49.  It enters the logits as a second K block of the S MMA against a one-hot operand.
+ *   wqkv_h  [3C, C] 16-bit (dtype), rows re-ordered PER HEAD: head h owns rows 96h..96h+95 = Wq[32h..] | Wk[32h..] | Wv[32h..],
+ *           with layernorm_before's gamma folded into the columns: W' = W diag(gamma) (the kernel normalises without gamma / beta)
+ *   bqkv_h  [3C] fp32 in the same order, b' = b + W beta; the q part multiplied by log2(e)/sqrt(32) (the softmax runs in the log2
+ *           domain).  The k part is not read: a key bias adds the same q.bk to every logit of a row and cancels in the softmax.
+ *   bias_op [heads*49, 56] fp16: bias_op[49h + i, j] = log2(e) * table[rel_pos_index(i, j), h] for j < 49, 0 for j >= 49:
+ *           one head's rows are one contiguous bulk copy; the softmax thread of query slot i adds row i to its logits.
  * The output projection + residual (csvit_linear with resid) follows on plain rows. */
-CSVIT_API int csvit_swin_attn_fused(const float* x, const float* gamma, const float* beta, float eps, const void* wqkv_h,
-                                    const float* bqkv_h, const void* bias_op, void* ctx, int dtype, int B, int H, int W, int C,
+CSVIT_API int csvit_swin_attn_fused(const float* x, float eps, const void* wqkv_h, const float* bqkv_h,
+                                    const void* bias_op, void* ctx, int dtype, int B, int H, int W, int C,
                                     int heads, int ws, int shift, void* stream);
 
 /* ---- SwinV2 ("V2:" = transformers/models/swinv2/modeling_swinv2.py) ---------------------------

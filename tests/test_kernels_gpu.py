@@ -271,17 +271,17 @@ def fused_attention_case(ops, B, H, heads, shift, dtype, seed, zero_bias=False):
     rel_index = ops.rel_pos_index(ws).long()
     xn = torch.nn.functional.layer_norm(x, (C,), gamma, beta, 1e-5)
     idx = ops.window_index_map(H, W, ws, shift).long()
-    xw = xn.view(B, N, C)[:, idx].reshape(B * nW, L, C).to(dtype).float()
-    q = (xw @ wq.to(dtype).float().T + bq).view(B * nW, L, heads, 32).transpose(1, 2)
-    k = (xw @ wk.to(dtype).float().T + bk).view(B * nW, L, heads, 32).transpose(1, 2)
-    v = (xw @ wv.to(dtype).float().T + bv).view(B * nW, L, heads, 32).transpose(1, 2)
+    xw = xn.view(B, N, C)[:, idx].reshape(B * nW, L, C)      # exact fp32 math: the tolerance below is the 16-bit operand rounding
+    q = (xw @ wq.T + bq).view(B * nW, L, heads, 32).transpose(1, 2)
+    k = (xw @ wk.T + bk).view(B * nW, L, heads, 32).transpose(1, 2)
+    v = (xw @ wv.T + bv).view(B * nW, L, heads, 32).transpose(1, 2)
     s = q @ k.transpose(-1, -2) / math.sqrt(32) + ops.expand_rel_bias(table, ws)[None]
     if shift:
         s = (s.view(B, nW, heads, L, L) + ops.shift_mask(H, W, ws, shift)[None, :, None]).view(B * nW, heads, L, L)
     ref_win = (s.softmax(-1) @ v).transpose(1, 2).reshape(B, N, C)
     ref = torch.empty_like(ref_win)
     ref[:, idx] = ref_win
-    packed = ops.pack_attn_fused(wq, wk, wv, bq, bk, bv, table, rel_index, dtype)
+    packed = ops.pack_attn_fused(wq, wk, wv, bq, bk, bv, table, rel_index, dtype, gamma, beta)
     return x, gamma, beta, packed, ref.reshape(B * N, C)
 
 
@@ -292,12 +292,12 @@ def test_swin_attn_fused(ops, B, H, heads, shift, dtype):
     """csvit_swin_attn_fused (LN + shift/partition + QKV + window attention + reverse on tcgen05) vs fp32 torch math; odd window
     counts (a half-empty last tile), masked and unmasked windows, both operand formats, more tiles than SMs."""
     x, gamma, beta, (wqkv_h, bqkv_h, bias_op), ref = fused_attention_case(ops, B, H, heads, shift, dtype, seed=B * 131 + H * 7 + heads + shift)
-    out = ops.swin_attn_fused(x, gamma, beta, 1e-5, wqkv_h, bqkv_h, bias_op, B, H, H, heads, 7, shift)
+    out = ops.swin_attn_fused(x, 1e-5, wqkv_h, bqkv_h, bias_op, B, H, H, heads, 7, shift)
     torch.cuda.synchronize()
     assert torch.isfinite(out.float()).all()
     tol = 1.2e-2 if dtype == torch.bfloat16 else 2.5e-3
     assert rel(out, ref) < tol
-    out2 = ops.swin_attn_fused(x, gamma, beta, 1e-5, wqkv_h, bqkv_h, bias_op, B, H, H, heads, 7, shift)
+    out2 = ops.swin_attn_fused(x, 1e-5, wqkv_h, bqkv_h, bias_op, B, H, H, heads, 7, shift)
     assert torch.equal(out, out2), "fused attention must be deterministic"
 
 

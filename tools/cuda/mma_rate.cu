@@ -53,5 +53,8 @@ int main() {
   run<256>("M128 N256", 4, 1);
   run<256>("M128 N256", 4, 148);
   run<128>("M128 N128", 4, 148);
+  run<96>("M128 N96", 4, 148);
+  run<64>("M128 N64", 4, 148);
+  run<32>("M128 N32", 4, 148);
   return 0;
 }

@@ -13,7 +13,7 @@ from test_kernels_gpu import fused_attention_case, rel  # noqa: E402
 
 def run(B, H, heads, shift, dtype, zero_bias=False):
     x, gamma, beta, (w, b, bo), ref = fused_attention_case(ops, B, H, heads, shift, dtype, seed=1, zero_bias=zero_bias)
-    out = ops.swin_attn_fused(x, gamma, beta, 1e-5, w, b, bo, B, H, H, heads, 7, shift)
+    out = ops.swin_attn_fused(x, 1e-5, w, b, bo, B, H, H, heads, 7, shift)
     torch.cuda.synchronize()
     C, N = heads * 32, H * H
     print(f"B={B} H={H} heads={heads} shift={shift} {dtype} zero_bias={zero_bias}: rel={rel(out, ref):.3e} finite={bool(torch.isfinite(out.float()).all())}")
@@ -43,11 +43,11 @@ if __name__ == "__main__":
             x, gamma, beta, (w, b, bo), ref = fused_attention_case(ops, 256, H, heads, shift, torch.bfloat16, seed=2)
             out = torch.empty_like(ref, dtype=torch.bfloat16)
             for _ in range(3):
-                ops.swin_attn_fused(x, gamma, beta, 1e-5, w, b, bo, 256, H, H, heads, 7, shift, out=out)
+                ops.swin_attn_fused(x, 1e-5, w, b, bo, 256, H, H, heads, 7, shift, out=out)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             for _ in range(10):
-                ops.swin_attn_fused(x, gamma, beta, 1e-5, w, b, bo, 256, H, H, heads, 7, shift, out=out)
+                ops.swin_attn_fused(x, 1e-5, w, b, bo, 256, H, H, heads, 7, shift, out=out)
             e1.record()
             torch.cuda.synchronize()
             us = e0.elapsed_time(e1) * 100

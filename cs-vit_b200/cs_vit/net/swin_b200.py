@@ -111,6 +111,7 @@ class SwinBackboneB200(nn.Module):
         # csvit_layernorm + csvit_linear on B200 (profiles/r1_lnlinear_vs_unfused.txt: the LayerNorm phase is exposed, not
         # overlapped with the MMAs), so it is opt-in until the A tile can be double-buffered.
         self.fuse_ln = False
+        self.fuse_attn = True  # csvit_swin_attn_fused for C in {128, 256}: LN + QKV + window attention in one tcgen05 kernel
         self.fuse_mlp = True   # csvit_mlp_fused for C in {128, 256}: hidden activations never leave the SM
         self.token_order_ctx = True   # inference: attention writes token-ordered context, out-proj uses the TMA residual epilogue
         # Inference runs the batch through the whole backbone in chunks of this many images (0 = all at once).  Images are
@@ -189,14 +190,26 @@ class SwinBackboneB200(nn.Module):
         impl = ops.GEMM_SIMT if self._fp32 else ops.GEMM_TC
         sa = blk.attention.self
         qkv_src = [sa.query.weight, sa.key.weight, sa.value.weight]
-        wqkv = self._w(key + "wqkv", qkv_src, lambda: torch.cat([w.detach() for w in qkv_src], 0).to(act).contiguous())
         bqkv_src = [sa.query.bias, sa.key.bias, sa.value.bias]
+        eps = cfg.layer_norm_eps
+        ln1, ln2 = blk.layernorm_before, blk.layernorm_after
+        proj = blk.attention.output.dense
+        fused_ln = self.fuse_ln and not self._fp32 and x.shape[1] in ops.LN_LINEAR_WIDTHS
+        if self.fuse_attn and not self._fp32 and ws == 7 and x.shape[1] in ops.ATTN_FUSED_WIDTHS and x.shape[1] == 32 * heads:
+            # narrow stages: layernorm_before + shift/partition + Q/K/V + window attention + reverse/un-shift in ONE tcgen05
+            # kernel (csrc/attn_fused.cu); xn, qkv, logits and probabilities stay on the SM.  The out-proj follows on plain rows.
+            src = qkv_src + bqkv_src + [sa.relative_position_bias_table, ln1.weight, ln1.bias]
+            wqkv_h, bqkv_h, bias_op = self._w(key + "attn_fused", src, lambda: ops.pack_attn_fused(
+                sa.query.weight, sa.key.weight, sa.value.weight, sa.query.bias, sa.key.bias, sa.value.bias,
+                sa.relative_position_bias_table, sa.relative_position_index, act, ln1.weight, ln1.bias))
+            ctx = ops.swin_attn_fused(x, eps, wqkv_h, bqkv_h, bias_op, B, H, W, heads, ws, shift)
+            ops.linear(ctx, self._weight(key + "wproj", proj.weight), self._f32(key + "bproj", proj.bias), resid=x, out=x, impl=impl)
+            self._mlp(x, blk, key, eps, act, impl, fused_ln)
+            return
+        wqkv = self._w(key + "wqkv", qkv_src, lambda: torch.cat([w.detach() for w in qkv_src], 0).to(act).contiguous())
         bqkv = self._w(key + "bqkv", bqkv_src, lambda: torch.cat([b.detach() for b in bqkv_src], 0).float().contiguous())
         bias = self._w(key + "relbias", [sa.relative_position_bias_table],
                        lambda: ops.expand_rel_bias(sa.relative_position_bias_table.detach(), ws))
-        eps = cfg.layer_norm_eps
-        ln1, ln2 = blk.layernorm_before, blk.layernorm_after
-        fused_ln = self.fuse_ln and not self._fp32 and x.shape[1] in ops.LN_LINEAR_WIDTHS
         if fused_ln:   # LayerNorm + shift/partition gather + Q/K/V in one kernel, xn never leaves the SM
             qkv = ops.ln_linear(x, self._f32(key + "ln1w", ln1.weight), self._f32(key + "ln1b", ln1.bias), eps, wqkv, bqkv,
                                 mode=ops.LN_WINDOW, grid=(H, W), ws=ws, shift=shift)
@@ -206,7 +219,6 @@ class SwinBackboneB200(nn.Module):
             qkv = ops.linear(xn, wqkv, bqkv, out_dtype=act, impl=impl)
         bias_mma = None if self._fp32 else self._w(key + "relbias_mma", [sa.relative_position_bias_table],
                                                    lambda: ops.expand_rel_bias_mma(sa.relative_position_bias_table.detach(), ws))
-        proj = blk.attention.output.dense
         if bias_mma is not None and self.token_order_ctx and x.shape[1] >= 256:
             # the attention kernel un-shifts / un-partitions on its store, so the out-proj runs on plain rows and its fp32
             # residual update goes through the TMA-staged epilogue (wide rows only: measured faster from C = 256 up)
@@ -216,6 +228,11 @@ class SwinBackboneB200(nn.Module):
             ctx = ops.window_attention(qkv, bias, B, H, W, heads, ws, shift, bias_mma=bias_mma)
             ops.linear(ctx, self._weight(key + "wproj", proj.weight), self._f32(key + "bproj", proj.bias), resid=x, out=x,
                        scatter=(H, W, ws, shift), impl=impl)
+        self._mlp(x, blk, key, eps, act, impl, fused_ln)
+
+    def _mlp(self, x: torch.Tensor, blk: _BlockParams, key: str, eps: float, act: torch.dtype, impl: int, fused_ln: bool) -> None:
+        """layernorm_after + intermediate (GELU) + output + residual, in place on x   (HF:swin/modeling_swin.py:510-531, 648-650)."""
+        ln2 = blk.layernorm_after
         fc1, fc2 = blk.intermediate.dense, blk.output.dense
         if fused_ln:
             hid = ops.ln_linear(x, self._f32(key + "ln2w", ln2.weight), self._f32(key + "ln2b", ln2.bias), eps,

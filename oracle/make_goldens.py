@@ -49,6 +49,8 @@ CASES = {
                                                   persp_embed_method="sparse"), "spatial", 2, 1),
     # Swin-B slice of configs[1]
     "swinb_encoder_patch_spatial": ("swin_b", dict(spatial_layer_type="encoder", persp_decorate="patch"), "spatial", 1, 1),
+    # the same model on 8 images: the golden the batch-256 test of configs[1] embeds into its benched batch
+    "swinb_encoder_patch_spatial_b8": ("swin_b", dict(spatial_layer_type="encoder", persp_decorate="patch"), "spatial", 8, 1),
 }
 OUT_KEYS = ("joint_cam", "verts_cam", "pose_aa", "shape", "root_transl_norm", "root_transl")
 
@@ -67,13 +69,17 @@ def state_checksum(sd) -> str:
 
 
 # ------------------------------------------------------------------------------------------------ pass 1
-def pass_product(workdir: str) -> None:
+def selected_cases(only):
+    return {k: v for k, v in CASES.items() if not only or k in only}
+
+
+def pass_product(workdir: str, only=None) -> None:
     sys.path.insert(0, os.path.join(ROOT, "cs-vit_b200"))
     from cs_vit.net import Poser
     from cs_vit.synthetic import make_random_backbone_dir, randomize_head_
     from cs_vit.utils.mano_standin import SyntheticMANO
 
-    for name, (variant, kw, _phase, _b, _t) in CASES.items():
+    for name, (variant, kw, _phase, _b, _t) in selected_cases(only).items():
         bdir = make_random_backbone_dir(os.path.join(workdir, variant), variant, seed=0)
         torch.manual_seed(0)
         m = Poser(bdir, image_size=224, mano_layer=SyntheticMANO(), **kw)
@@ -87,7 +93,7 @@ def rel(a, b):
     return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
 
 
-def pass_reference(workdir: str) -> None:
+def pass_reference(workdir: str, only=None) -> None:
     sys.path.insert(0, ROOT)
     from oracle import head_restated as head
     from oracle import swin_restated as swin
@@ -134,12 +140,16 @@ def pass_reference(workdir: str) -> None:
         cat = pm(torch.arange(H * H, dtype=torch.float32).reshape(1, H * H, 1), (H, H)).reshape(-1, 4)
         assert torch.equal(cat.long(), swin.merge_gather_index(H, H))
         ints[f"merge_{H}"] = cat.numpy().astype(np.int32)
-    np.savez_compressed(os.path.join(GOLDEN, "integer_maps.npz"), **ints)
+    if not only:
+        np.savez_compressed(os.path.join(GOLDEN, "integer_maps.npz"), **ints)
     print(f"[reference] integer maps: {len(ints)} arrays, restatement bit-exact vs HF")
 
     # ---- float goldens ------------------------------------------------------------------------------------
     summary = {}
-    for name, (variant, kw, phase, B, T) in CASES.items():
+    if only:      # partial regeneration keeps the other cases' manifest entries (and their files) untouched
+        with open(os.path.join(GOLDEN, "MANIFEST.json")) as f:
+            summary = json.load(f)["cases"]
+    for name, (variant, kw, phase, B, T) in selected_cases(only).items():
         sd = torch.load(os.path.join(workdir, name + ".sd.pt"))
         bdir = os.path.join(workdir, variant)
         m = ref_poser.Poser(backbone=bdir, image_size=224, num_latent_layer=None, **kw)
@@ -190,16 +200,17 @@ def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--stage", choices=["all", "product", "reference"], default="all")
     ap.add_argument("--workdir", default=None)
+    ap.add_argument("--only", nargs="*", default=None, help="regenerate only these cases (the others keep their files)")
     a = ap.parse_args()
     if a.stage == "product":
-        pass_product(a.workdir)
+        pass_product(a.workdir, a.only)
     elif a.stage == "reference":
-        pass_reference(a.workdir)
+        pass_reference(a.workdir, a.only)
     else:
         with tempfile.TemporaryDirectory() as wd:
             for stage in ("product", "reference"):
-                subprocess.run([sys.executable, "-m", "oracle.make_goldens", "--stage", stage, "--workdir", wd],
-                               cwd=ROOT, check=True)
+                subprocess.run([sys.executable, "-m", "oracle.make_goldens", "--stage", stage, "--workdir", wd] +
+                               (["--only"] + a.only if a.only else []), cwd=ROOT, check=True)
 
 
 if __name__ == "__main__":

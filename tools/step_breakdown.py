@@ -18,8 +18,8 @@ inp = {k: v.cuda() for k, v in make_inputs(B, 1, S, seed=3).items()}
 def step():
     with torch.no_grad():
         return m.predict_batch(inp["patches"], inp["square_bboxes"], inp["timestamp"], inp["focal"], inp["princpt"])
-if os.environ.get("FOLD") is not None:
-    m.backbone.fold_ln = os.environ["FOLD"] == "1"
+if os.environ.get("FUSE_ATTN") is not None:
+    m.backbone.fuse_attn = os.environ["FUSE_ATTN"] == "1"
 for _ in range(3): step()
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -29,7 +29,7 @@ e1.record(); torch.cuda.synchronize()
 total = e0.elapsed_time(e1) / 5
 print(f"step {total:.3f} ms  -> {B / total * 1e3:.0f} img/s")
 acc = 0
-for name in ("csvit_linear", "csvit_linear_emit", "csvit_linear_lnfold", "csvit_mlp_fused", "csvit_window_attention", "csvit_window_attention_ex", "csvit_swinv2_window_attention", "csvit_layernorm_post", "csvit_layernorm", "csvit_attention", "csvit_affine_rows", "csvit_patch_im2col"):
+for name in ("csvit_linear", "csvit_linear_emit", "csvit_linear_lnfold", "csvit_mlp_fused", "csvit_swin_attn_fused", "csvit_window_attention", "csvit_window_attention_ex", "csvit_swinv2_window_attention", "csvit_layernorm_post", "csvit_layernorm", "csvit_attention", "csvit_affine_rows", "csvit_patch_im2col"):
     ops.begin_profile(name)
     for _ in range(3): step()
     p = ops.end_profile()

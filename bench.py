@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Headline benchmark: images/sec of the Swin-B spatial model forward (BASELINE.json configs[1]).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision bf16|fp16]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision fp16|bf16]
 
 One "step" = one ``Poser.predict_batch`` over a batch of 256 synthetic 224x224 crops per GPU (Swin-B backbone,
 "encoder" spatial head, perspective embedding added to the patches - the ``spatial_dexycb_swinb_spenc_addpat``
@@ -16,8 +16,13 @@ Keys beyond the base contract:
                 step's batch and a D2H read of the predicted joints, double-buffered on a copy stream.
   cpu_baseline  the oracle port (HF SwinModel + restated head, all six head layers executed like the
                 reference) on the host cores, on a bounded sample, rank 0 at N=1 only.
-  fp16          the same timed loop with fp16 instead of bf16 tensor-core operands (identical MMA rate; the
-                mode whose joints/vertices meet the 1e-2 parity bar, see DESIGN.md "Numerics").
+  roofline_attention / roofline_attention_fused
+                the two tcgen05 window-attention kernels (attn_core.cu: 20 launches/step, attn_fused.cu: 4), timed the same
+                way, against the measured HBM copy bandwidth (they are HBM-bound: 8C resp. 6C algorithmic bytes per token).
+  bf16          the same timed loop with bf16 instead of fp16 tensor-core operands (identical MMA rate).  The headline
+                ``dtype`` is fp16: it is the 16-bit format whose joints / vertices meet the 1e-2 parity bar on this
+                configuration (bf16 operand ROUNDING ALONE puts them at 1.2e-2 / 1.5e-2, DESIGN.md "Numerics").
+  check         joints of the timed graph-replay path vs an eager run of the same batch (must be identical) and finite.
 """
 from __future__ import annotations
 
@@ -64,7 +69,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
-    ap.add_argument("--precision", choices=["bf16", "fp16"], default="bf16")
+    ap.add_argument("--precision", choices=["bf16", "fp16"], default="fp16")
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--variant", default="swin_b")
     ap.add_argument("--workload", choices=["spatial", "temporal", "finetune"], default="spatial",
@@ -327,12 +332,32 @@ def run_ours(a):
         prof = ops.end_profile()
         if prof["launches"]:
             ach = prof["flops"] / (prof["ms"] / 1e3) / 1e12
-            out["roofline"] = {"bound": "tensor", "kernel": "gemm_tc_kernel (csvit_linear: every Linear of backbone and head)",
+            out["roofline"] = {"bound": "tensor", "kernel": "csvit_linear = gemm_pair_kernel (cta_group::2, most launches) / gemm_tc_kernel: every Linear of backbone and head",
                                "achieved": round(ach, 1), "peak": peak_tf, "unit": "TFLOP/s", "frac": round(ach / peak_tf, 4),
                                "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peak_kind})", "traffic": gemm_traffic(a),
                                "launches_per_step": prof["launches"] // a.steps,
                                "share_of_step": round(prof["ms"] / a.steps / (ms_total / a.steps), 3),
                                "avg_launch_us": round(1e3 * prof["ms"] / prof["launches"], 2)}
+        # ---- the tcgen05 window-attention kernels (HBM-bound), same instrumented pass -------------------------------
+        for key, entry, kern, bpt in (("roofline_attention", "csvit_swin_attn_core", "swin_attn_core_kernel: q/k/v tiles by TMA, QK^T and PV on tcgen05/TMEM (stages 2-3)", "8C"),
+                                     ("roofline_attention_fused", "csvit_swin_attn_fused", "swin_attn_fused_kernel: LN + QKV + attention in one tcgen05 kernel (stages 0-1)", "6C")):
+            ops.begin_profile(entry)
+            timed_loop(a.steps, eager_step)
+            prof = ops.end_profile()
+            if prof["launches"]:
+                gbs = prof["bytes"] / (prof["ms"] / 1e3) / 1e9
+                out[key] = {"bound": "hbm", "kernel": kern, "achieved": round(gbs, 1), "peak": peak_gbs, "unit": "GB/s",
+                            "frac": round(gbs / peak_gbs, 4), "algorithmic_bytes_per_token": bpt, "traffic": None,
+                            "tflops": round(prof["flops"] / (prof["ms"] / 1e3) / 1e12, 1),
+                            "launches_per_step": prof["launches"] // a.steps,
+                            "share_of_step": round(prof["ms"] / a.steps / (ms_total / a.steps), 3),
+                            "avg_launch_us": round(1e3 * prof["ms"] / prof["launches"], 2)}
+        # ---- the timed path's result against an eager run of the same batch --------------------------------------
+        g_out = step(resident)["joint_cam"].clone()
+        e_out = eager_step(resident)["joint_cam"]
+        torch.cuda.synchronize()
+        out["check"] = {"joint_cam_finite": bool(torch.isfinite(g_out).all().item()),
+                        "graph_vs_eager_max_abs_diff": float((g_out - e_out).abs().max().item())}
         # ---- end-to-end: host inputs, H2D + D2H inside the timed region, double-buffered ------------------------
         copy_stream = torch.cuda.Stream(device=dev)
         bufs = [{k: torch.empty_like(resident[k]) for k in keys} for _ in range(2)]
@@ -375,7 +400,8 @@ def run_ours(a):
         ms_e2e = e2e_loop(a.steps)
         out["e2e"] = {"value": round(world * a.batch * a.steps / (ms_e2e / 1e3), 1), "unit": "images/s",
                       "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": host_out.numel() * 4,
-                      "note": "predict_batch on pinned host tensors; H2D on a copy stream overlapped with the previous step's compute"}
+                      "note": "predict_batch on pinned host tensors; H2D on a copy stream overlapped with the previous step's compute; "
+                              "D2H returns joint_cam only (what scripts/eval.py consumes) - the other five result tensors stay on the device"}
         # ---- the other 16-bit operand format ---------------------------------------------------------------
         other = "fp16" if a.precision == "bf16" else "bf16"
         model.set_precision(other)

@@ -31,19 +31,14 @@ SIGNATURES = {
                            c_void_p],
     "csvit_linear": [c_void_p, c_longlong, c_void_p, c_longlong, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p,
                      c_longlong, c_void_p, c_longlong, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p],
-    "csvit_ln_linear": [c_void_p, c_void_p, c_void_p, c_float, c_int, c_int, c_int, c_int, c_int, c_void_p, c_longlong, c_int,
-                        c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_longlong, c_void_p],
     "csvit_mlp_fused": [c_void_p, c_longlong, c_void_p, c_longlong, c_void_p, c_void_p, c_longlong, c_void_p, c_void_p,
                         c_longlong, c_int, c_int, c_int, c_void_p],
     "csvit_swin_attn_fused": [c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                               c_int, c_int, c_int, c_int, c_void_p],
+    "csvit_swin_attn_core": [c_void_p, c_longlong, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                             c_int, c_int, c_void_p],
     "csvit_set_gemm_tuning": [c_int, c_int, c_int, c_int],
-    "csvit_expand_rel_bias_mma": [c_void_p, c_void_p, c_int, c_int, c_void_p],
-    "csvit_set_attention_impl": [c_int],
-    "csvit_window_attention": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
-                               c_void_p],
-    "csvit_window_attention_ex": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
-                                  c_int, c_void_p],
+    "csvit_window_attention": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p],
     "csvit_attention": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_longlong, c_longlong, c_longlong, c_longlong,
                         c_int, c_int, c_int, c_int, c_float, c_void_p],
     "csvit_swinv2_window_attention": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,

@@ -34,7 +34,7 @@ class SwinBlockFn(Function):
     """One SwinLayer (HF:swin/modeling_swin.py:591-653) on the fp32 residual stream ``x [B*H*W, C]``.
 
     forward(x, ln1w, ln1b, wq, bq, wk, bk, wv, bv, table, wo, bo, ln2w, ln2b, w1, b1, w2, b2, pk, meta)
-      ``pk``: packed operands {wqkv, bqkv, wo, w1, w2 (act dtype), bias (plain [h,L,L]), bias_mma or None}
+      ``pk``: packed operands {wqkv, bqkv, wo, w1, w2 (act dtype), bias (plain [h,L,L]), bias_log2 or None}
       ``meta``: (B, H, W, heads, ws, shift, eps, act dtype, impl)
     """
 
@@ -43,7 +43,7 @@ class SwinBlockFn(Function):
         B, H, W, heads, ws, shift, eps, act, impl = meta
         xn1 = ops.layernorm(x, ln1w, ln1b, eps, out_dtype=act, mode=ops.LN_WINDOW, grid=(H, W), ws=ws, shift=shift)
         qkv = ops.linear(xn1, pk["wqkv"], pk["bqkv"], out_dtype=act, impl=impl)
-        att = ops.window_attention(qkv, pk["bias"], B, H, W, heads, ws, shift, bias_mma=pk["bias_mma"])
+        att = ops.window_attention(qkv, pk["bias"], B, H, W, heads, ws, shift, bias_log2=pk["bias_log2"])
         x1 = ops.linear(att, pk["wo"], bo, resid=x, out_dtype=torch.float32, scatter=(H, W, ws, shift), impl=impl)
         xn2 = ops.layernorm(x1, ln2w, ln2b, eps, out_dtype=act)
         h = ops.linear(xn2, pk["w1"], b1, out_dtype=act, impl=impl)

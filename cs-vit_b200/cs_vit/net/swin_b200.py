@@ -107,13 +107,8 @@ class SwinBackboneB200(nn.Module):
         super().__init__()
         self.config = config
         self.precision = precision
-        # LayerNorm-prologue pair GEMM (csvit_ln_linear) for Q/K/V and fc1.  Correct and tested, but measured slower than
-        # csvit_layernorm + csvit_linear on B200 (profiles/r1_lnlinear_vs_unfused.txt: the LayerNorm phase is exposed, not
-        # overlapped with the MMAs), so it is opt-in until the A tile can be double-buffered.
-        self.fuse_ln = False
         self.fuse_attn = True  # csvit_swin_attn_fused for C in {128, 256}: LN + QKV + window attention in one tcgen05 kernel
         self.fuse_mlp = True   # csvit_mlp_fused for C in {128, 256}: hidden activations never leave the SM
-        self.token_order_ctx = True   # inference: attention writes token-ordered context, out-proj uses the TMA residual epilogue
         # Inference runs the batch through the whole backbone in chunks of this many images (0 = all at once).  Images are
         # independent, so the result is bit-identical; what changes is locality: a chunk's inter-kernel tensors (tens of MB)
         # stay resident in the 126 MB L2 between the kernel that writes them and the one that reads them, instead of making
@@ -186,67 +181,65 @@ class SwinBackboneB200(nn.Module):
         ws = cfg.window_size
         if min(H, W) <= ws:  # HF:548-554
             ws, shift = min(H, W), 0
+        C = x.shape[1]
         act = self._act_dtype
         impl = ops.GEMM_SIMT if self._fp32 else ops.GEMM_TC
         sa = blk.attention.self
         qkv_src = [sa.query.weight, sa.key.weight, sa.value.weight]
         bqkv_src = [sa.query.bias, sa.key.bias, sa.value.bias]
         eps = cfg.layer_norm_eps
-        ln1, ln2 = blk.layernorm_before, blk.layernorm_after
+        ln1 = blk.layernorm_before
         proj = blk.attention.output.dense
-        fused_ln = self.fuse_ln and not self._fp32 and x.shape[1] in ops.LN_LINEAR_WIDTHS
-        if self.fuse_attn and not self._fp32 and ws == 7 and x.shape[1] in ops.ATTN_FUSED_WIDTHS and x.shape[1] == 32 * heads:
-            # narrow stages: layernorm_before + shift/partition + Q/K/V + window attention + reverse/un-shift in ONE tcgen05
-            # kernel (csrc/attn_fused.cu); xn, qkv, logits and probabilities stay on the SM.  The out-proj follows on plain rows.
-            src = qkv_src + bqkv_src + [sa.relative_position_bias_table, ln1.weight, ln1.bias]
-            wqkv_h, bqkv_h, bias_op = self._w(key + "attn_fused", src, lambda: ops.pack_attn_fused(
-                sa.query.weight, sa.key.weight, sa.value.weight, sa.query.bias, sa.key.bias, sa.value.bias,
-                sa.relative_position_bias_table, sa.relative_position_index, act, ln1.weight, ln1.bias))
-            ctx = ops.swin_attn_fused(x, eps, wqkv_h, bqkv_h, bias_op, B, H, W, heads, ws, shift)
-            ops.linear(ctx, self._weight(key + "wproj", proj.weight), self._f32(key + "bproj", proj.bias), resid=x, out=x, impl=impl)
-            self._mlp(x, blk, key, eps, act, impl, fused_ln)
-            return
-        wqkv = self._w(key + "wqkv", qkv_src, lambda: torch.cat([w.detach() for w in qkv_src], 0).to(act).contiguous())
-        bqkv = self._w(key + "bqkv", bqkv_src, lambda: torch.cat([b.detach() for b in bqkv_src], 0).float().contiguous())
-        bias = self._w(key + "relbias", [sa.relative_position_bias_table],
-                       lambda: ops.expand_rel_bias(sa.relative_position_bias_table.detach(), ws))
-        if fused_ln:   # LayerNorm + shift/partition gather + Q/K/V in one kernel, xn never leaves the SM
-            qkv = ops.ln_linear(x, self._f32(key + "ln1w", ln1.weight), self._f32(key + "ln1b", ln1.bias), eps, wqkv, bqkv,
-                                mode=ops.LN_WINDOW, grid=(H, W), ws=ws, shift=shift)
-        else:
+        wproj, bproj = self._weight(key + "wproj", proj.weight), self._f32(key + "bproj", proj.bias)
+        if self._fp32:
+            # validation mode: exact fp32 kernels (SIMT GEMMs, fp32 attention), window-ordered context scattered by the out-proj
+            wqkv = self._w(key + "wqkv", qkv_src, lambda: torch.cat([w.detach() for w in qkv_src], 0).to(act).contiguous())
+            bqkv = self._w(key + "bqkv", bqkv_src, lambda: torch.cat([b.detach() for b in bqkv_src], 0).float().contiguous())
+            bias = self._w(key + "relbias", [sa.relative_position_bias_table],
+                           lambda: ops.expand_rel_bias(sa.relative_position_bias_table.detach(), ws))
             xn = ops.layernorm(x, self._f32(key + "ln1w", ln1.weight), self._f32(key + "ln1b", ln1.bias), eps, out_dtype=act,
                                mode=ops.LN_WINDOW, grid=(H, W), ws=ws, shift=shift)
             qkv = ops.linear(xn, wqkv, bqkv, out_dtype=act, impl=impl)
-        bias_mma = None if self._fp32 else self._w(key + "relbias_mma", [sa.relative_position_bias_table],
-                                                   lambda: ops.expand_rel_bias_mma(sa.relative_position_bias_table.detach(), ws))
-        if bias_mma is not None and self.token_order_ctx and x.shape[1] >= 256:
-            # the attention kernel un-shifts / un-partitions on its store, so the out-proj runs on plain rows and its fp32
-            # residual update goes through the TMA-staged epilogue (wide rows only: measured faster from C = 256 up)
-            ctx = ops.window_attention(qkv, bias, B, H, W, heads, ws, shift, bias_mma=bias_mma, token_order=True)
-            ops.linear(ctx, self._weight(key + "wproj", proj.weight), self._f32(key + "bproj", proj.bias), resid=x, out=x, impl=impl)
+            ctx = ops.window_attention(qkv, bias, B, H, W, heads, ws, shift)
+            ops.linear(ctx, wproj, bproj, resid=x, out=x, scatter=(H, W, ws, shift), impl=impl)
         else:
-            ctx = ops.window_attention(qkv, bias, B, H, W, heads, ws, shift, bias_mma=bias_mma)
-            ops.linear(ctx, self._weight(key + "wproj", proj.weight), self._f32(key + "bproj", proj.bias), resid=x, out=x,
-                       scatter=(H, W, ws, shift), impl=impl)
-        self._mlp(x, blk, key, eps, act, impl, fused_ln)
-
-    def _mlp(self, x: torch.Tensor, blk: _BlockParams, key: str, eps: float, act: torch.dtype, impl: int, fused_ln: bool) -> None:
-        """layernorm_after + intermediate (GELU) + output + residual, in place on x   (HF:swin/modeling_swin.py:510-531, 648-650)."""
+            if ws != 7 or C != 32 * heads:
+                raise NotImplementedError(f"the tcgen05 window-attention kernels are built for 7x7 windows and head_dim 32 "
+                                          f"(got window {ws}, C={C}, heads={heads}); use precision='fp32'")
+            if self.fuse_attn and C in ops.ATTN_FUSED_WIDTHS:
+                # narrow stages: layernorm_before + shift/partition + Q/K/V + window attention + reverse/un-shift in ONE tcgen05
+                # kernel (csrc/attn_fused.cu); xn, qkv, logits and probabilities stay on the SM.  Out-proj on plain rows.
+                src = qkv_src + bqkv_src + [sa.relative_position_bias_table, ln1.weight, ln1.bias]
+                wqkv_h, bqkv_h, bias_op = self._w(key + "attn_fused", src, lambda: ops.pack_attn_fused(
+                    sa.query.weight, sa.key.weight, sa.value.weight, sa.query.bias, sa.key.bias, sa.value.bias,
+                    sa.relative_position_bias_table, sa.relative_position_index, act, ln1.weight, ln1.bias))
+                ctx = ops.swin_attn_fused(x, eps, wqkv_h, bqkv_h, bias_op, B, H, W, heads, ws, shift)
+                ops.linear(ctx, wproj, bproj, resid=x, out=x, impl=impl)
+            else:
+                # LayerNorm (window-ordered 16-bit rows) -> Q/K/V GEMM (log2(e)/sqrt(32) folded into the q rows) -> tcgen05 attention
+                # core on TMA-loaded operand tiles (csrc/attn_core.cu), token-ordered context -> out-proj on plain rows with the
+                # TMA residual epilogue (narrow rows: the scatter epilogue of the out-proj is faster than its TMA form)
+                wqs, bqs = self._w(key + "wqkv_qs", qkv_src + bqkv_src, lambda: ops.pack_qkv_prescaled(
+                    sa.query.weight, sa.key.weight, sa.value.weight, sa.query.bias, sa.key.bias, sa.value.bias, act))
+                bias_l2 = self._w(key + "relbias_l2", [sa.relative_position_bias_table],
+                                  lambda: ops.pack_rel_bias_log2(sa.relative_position_bias_table, sa.relative_position_index))
+                xn = ops.layernorm(x, self._f32(key + "ln1w", ln1.weight), self._f32(key + "ln1b", ln1.bias), eps, out_dtype=act,
+                                   mode=ops.LN_WINDOW, grid=(H, W), ws=ws, shift=shift)
+                qkv = ops.linear(xn, wqs, bqs, out_dtype=act, impl=impl)
+                tok = C >= 256
+                ctx = ops.swin_attn_core(qkv, bias_l2, B, H, W, heads, ws, shift, token_order=tok, q_prescaled=True)
+                ops.linear(ctx, wproj, bproj, resid=x, out=x, impl=impl, **({} if tok else {"scatter": (H, W, ws, shift)}))
+        # layernorm_after + intermediate (GELU) + output + residual   (HF:510-531, 648-650)
         ln2 = blk.layernorm_after
         fc1, fc2 = blk.intermediate.dense, blk.output.dense
-        if fused_ln:
-            hid = ops.ln_linear(x, self._f32(key + "ln2w", ln2.weight), self._f32(key + "ln2b", ln2.bias), eps,
-                                self._weight(key + "w1", fc1.weight), self._f32(key + "b1", fc1.bias), act=ops.ACT_GELU)
-        elif self.fuse_mlp and not self._fp32 and x.shape[1] in ops.MLP_FUSED_WIDTHS:
+        xn = ops.layernorm(x, self._f32(key + "ln2w", ln2.weight), self._f32(key + "ln2b", ln2.bias), eps, out_dtype=act)
+        if self.fuse_mlp and not self._fp32 and C in ops.MLP_FUSED_WIDTHS:
             # narrow stages: fc1 + GELU + fc2 + residual in one kernel, the [M, 4C] hidden tensor stays on chip
-            xn = ops.layernorm(x, self._f32(key + "ln2w", ln2.weight), self._f32(key + "ln2b", ln2.bias), eps, out_dtype=act)
             ops.mlp_fused(xn, self._weight(key + "w1", fc1.weight), self._f32(key + "b1", fc1.bias),
                           self._weight(key + "w2", fc2.weight), self._f32(key + "b2", fc2.bias), x)
             return
-        else:
-            xn = ops.layernorm(x, self._f32(key + "ln2w", ln2.weight), self._f32(key + "ln2b", ln2.bias), eps, out_dtype=act)
-            hid = ops.linear(xn, self._weight(key + "w1", fc1.weight), self._f32(key + "b1", fc1.bias), act=ops.ACT_GELU,
-                             out_dtype=act, impl=impl)
+        hid = ops.linear(xn, self._weight(key + "w1", fc1.weight), self._f32(key + "b1", fc1.bias), act=ops.ACT_GELU,
+                         out_dtype=act, impl=impl)
         ops.linear(hid, self._weight(key + "w2", fc2.weight), self._f32(key + "b2", fc2.bias), resid=x, out=x, impl=impl)
 
     def forward_features(self, images: torch.Tensor, normalize: bool, return_stages: bool = False):
@@ -279,7 +272,7 @@ class SwinBackboneB200(nn.Module):
             "wqkv": self._w(key + "wqkv", qkv_src, lambda: torch.cat([w.detach() for w in qkv_src], 0).to(act).contiguous()),
             "bqkv": self._w(key + "bqkv", bqkv_src, lambda: torch.cat([b.detach() for b in bqkv_src], 0).float().contiguous()),
             "bias": self._w(key + "relbias", [tab], lambda: ops.expand_rel_bias(tab.detach(), ws)),
-            "bias_mma": None if self._fp32 else self._w(key + "relbias_mma", [tab], lambda: ops.expand_rel_bias_mma(tab.detach(), ws)),
+            "bias_log2": None if self._fp32 else self._w(key + "relbias_l2", [tab], lambda: ops.pack_rel_bias_log2(tab, sa.relative_position_index)),
             "wo": self._weight(key + "wproj", blk.attention.output.dense.weight),
             "w1": self._weight(key + "w1", blk.intermediate.dense.weight),
             "w2": self._weight(key + "w2", blk.output.dense.weight),

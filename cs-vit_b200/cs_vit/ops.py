@@ -117,16 +117,6 @@ def expand_rel_bias(table: torch.Tensor, ws: int) -> torch.Tensor:
     return out
 
 
-def expand_rel_bias_mma(table: torch.Tensor, ws: int = 7) -> torch.Tensor:
-    """Bias table in MMA accumulator-fragment order for the 16-bit window-attention kernel."""
-    _dev(table)
-    table = table.contiguous().float()
-    heads = table.shape[1]
-    out = torch.empty(heads, 4, 7, 32, 4, dtype=torch.float32, device=table.device)
-    _call("csvit_expand_rel_bias_mma", table.data_ptr(), out.data_ptr(), heads, ws, _stream())
-    return out
-
-
 # ---------------------------------------------------------------------------------------------- row kernels
 def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float, *, out_dtype=torch.float32,
               mode: int = LN_IDENTITY, grid: Tuple[int, int] = (0, 0), ws: int = 0, shift: int = 0,
@@ -209,25 +199,6 @@ def linear(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
     return out
 
 
-def ln_linear(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float, w: torch.Tensor,
-              bias: Optional[torch.Tensor] = None, *, act: int = ACT_NONE, mode: int = LN_IDENTITY,
-              grid: Tuple[int, int] = (0, 0), ws: int = 0, shift: int = 0) -> torch.Tensor:
-    """``act(LayerNorm(x rows) @ w.T + bias)`` in one kernel (see ``csvit_ln_linear``); x fp32 ``[M, C]``, w 16-bit ``[N, C]``."""
-    _dev(x, gamma, beta, w, bias)
-    if x.dtype != torch.float32 or not x.is_contiguous():
-        raise ValueError("ln_linear input must be contiguous float32")
-    M, C = x.shape
-    N, C2, ldw = _rows2d(w)
-    if C2 != C or w.dtype not in (torch.bfloat16, torch.float16):
-        raise ValueError("ln_linear: weight must be 16-bit [N, C]")
-    out = torch.empty(M, N, dtype=w.dtype, device=x.device)
-    H, W = grid
-    _call("csvit_ln_linear", x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), float(eps), mode, H, W, ws, shift, w.data_ptr(),
-          ldw, _code(w.dtype), M, N, C, _p(bias), act, out.data_ptr(), out.stride(0), _stream(), flops=2.0 * M * N * C)
-    return out
-
-
-LN_LINEAR_WIDTHS = (128, 256, 512)
 MLP_FUSED_WIDTHS = (128, 256)
 
 
@@ -263,12 +234,49 @@ def pack_attn_fused(wq: torch.Tensor, wk: torch.Tensor, wv: torch.Tensor, bq: to
     w = torch.stack([fold_w(wq).view(heads, 32, C), fold_w(wk).view(heads, 32, C), fold_w(wv).view(heads, 32, C)], 1)
     qs = _LOG2E / 32.0 ** 0.5
     b = torch.stack([fold_b(wq, bq).view(heads, 32) * qs, fold_b(wk, bk).view(heads, 32), fold_b(wv, bv).view(heads, 32)], 1)
+    return w.reshape(3 * C, C).to(dtype).contiguous(), b.reshape(3 * C).contiguous(), pack_rel_bias_log2(table, rel_index)
+
+
+def pack_rel_bias_log2(table: torch.Tensor, rel_index: torch.Tensor) -> torch.Tensor:
+    """fp16 ``[heads*49, 56]`` relative-position-bias rows of the tcgen05 attention kernels: row ``49h + i`` holds
+    ``log2(e) * table[rel_index[i, j], h]`` for key slots ``j < 49`` and zeros beyond (HF:swin/modeling_swin.py:437-444)."""
+    heads = table.shape[1]
     L = rel_index.shape[0]
+    if L != 49:
+        raise ValueError("pack_rel_bias_log2: 7x7 windows only")
     bias = table.detach().float()[rel_index.reshape(-1).long()].view(L, L, heads).permute(2, 0, 1)      # [h, i, j]
     op = torch.zeros(heads, L, 56, dtype=torch.float32, device=table.device)
     op[:, :, :L] = bias * _LOG2E                                                                        # [h, query slot, key slot]
-    return (w.reshape(3 * C, C).to(dtype).contiguous(), b.reshape(3 * C).contiguous(),
-            op.to(torch.float16).reshape(heads * L, 56).contiguous())
+    return op.to(torch.float16).reshape(heads * L, 56).contiguous()
+
+
+def pack_qkv_prescaled(wq, wk, wv, bq, bk, bv, dtype: torch.dtype):
+    """Stacked ``[3C, C]`` Q/K/V weight (16 bit) and fp32 bias with ``log2(e)/sqrt(32)`` folded into the q rows, so that the
+    logits of ``swin_attn_core(..., q_prescaled=True)`` come out of the MMA in the softmax's log2 domain."""
+    qs = _LOG2E / 32.0 ** 0.5
+    w = torch.cat([wq.detach().float() * qs, wk.detach().float(), wv.detach().float()], 0)
+    b = torch.cat([bq.detach().float() * qs, bk.detach().float(), bv.detach().float()], 0)
+    return w.to(dtype).contiguous(), b.contiguous()
+
+
+def swin_attn_core(qkv: torch.Tensor, bias_log2: torch.Tensor, B: int, H: int, W: int, heads: int, ws: int, shift: int,
+                   token_order: bool = False, q_prescaled: bool = False, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Window-attention core on tcgen05 (``csvit_swin_attn_core``): window-ordered 16-bit qkv ``[B*H*W, 3C]`` -> context
+    ``[B*H*W, C]`` in window order, or in token order (window_reverse + un-shift folded into the store)."""
+    _dev(qkv, bias_log2, out)
+    rows, C3, ld = _rows2d(qkv)
+    C = C3 // 3
+    if qkv.dtype not in (torch.bfloat16, torch.float16) or rows != B * H * W or C != heads * 32 or ws != 7:
+        raise ValueError(f"swin_attn_core: needs 16-bit qkv [B*H*W, 3C] with head_dim 32 and 7x7 windows (rows={rows} C={C} heads={heads} ws={ws})")
+    if bias_log2.dtype != torch.float16 or tuple(bias_log2.shape) != (heads * 49, 56) or not bias_log2.is_contiguous():
+        raise ValueError("swin_attn_core: bias_log2 must be contiguous float16 [heads*49, 56] (pack_rel_bias_log2)")
+    if out is None:
+        out = torch.empty(rows, C, dtype=qkv.dtype, device=qkv.device)
+    L = ws * ws
+    _call("csvit_swin_attn_core", qkv.data_ptr(), ld, bias_log2.data_ptr(), out.data_ptr(), _code(qkv.dtype), B, H, W, C, heads, ws,
+          shift, 1 if token_order else 0, 1 if q_prescaled else 0, _stream(),
+          flops=float(rows) * 4.0 * L * C, nbytes=float(rows) * C * 8.0)
+    return out
 
 
 def swin_attn_fused(x: torch.Tensor, eps: float, wqkv_h: torch.Tensor, bqkv_h: torch.Tensor,
@@ -295,32 +303,25 @@ def swin_attn_fused(x: torch.Tensor, eps: float, wqkv_h: torch.Tensor, bqkv_h: t
     return out
 
 
-def window_attention(qkv: torch.Tensor, bias_exp: torch.Tensor, B: int, H: int, W: int, heads: int, ws: int,
-                     shift: int, bias_mma: Optional[torch.Tensor] = None, token_order: bool = False) -> torch.Tensor:
-    """``bias_exp``: ``expand_rel_bias`` table ``[h,L,L]`` (fp32 kernel and the tcgen05 16-bit kernel) or, for backward
-    compatibility, an ``expand_rel_bias_mma`` table (5-D) which selects the mma.sync 16-bit kernel."""
-    _dev(qkv, bias_exp, bias_mma)
-    plain, frag = bias_exp, bias_mma
-    if bias_exp.dim() == 5:
-        plain, frag = None, bias_exp
-    if qkv.dtype != torch.float32 and plain is None and frag is None:
-        raise ValueError("window attention needs a bias table")
+def window_attention(qkv: torch.Tensor, bias_exp: Optional[torch.Tensor], B: int, H: int, W: int, heads: int, ws: int,
+                     shift: int, bias_log2: Optional[torch.Tensor] = None, token_order: bool = False) -> torch.Tensor:
+    """Window attention on window-ordered qkv ``[B*H*W, 3C]``: fp32 qkv runs the exact kernel of the validation mode with the
+    ``expand_rel_bias`` table ``[h,L,L]``; 16-bit qkv runs the tcgen05 core (``swin_attn_core``) with the ``pack_rel_bias_log2`` table."""
+    if qkv.dtype != torch.float32:
+        if bias_log2 is None:
+            raise ValueError("window_attention: 16-bit qkv needs bias_log2 (ops.pack_rel_bias_log2)")
+        return swin_attn_core(qkv, bias_log2, B, H, W, heads, ws, shift, token_order=token_order)
+    if token_order:
+        raise ValueError("window_attention: token-ordered output is built for the 16-bit kernels only")
+    _dev(qkv, bias_exp)
     rows, C3, ld = _rows2d(qkv)
     C = C3 // 3
     if ld != C3 or rows != B * H * W:
         raise ValueError("window_attention: qkv must be dense [B*H*W, 3C]")
     out = torch.empty(rows, C, dtype=qkv.dtype, device=qkv.device)
-    if token_order:   # rows of `out` in token order (window_reverse + un-shift folded into the store); 16-bit mma.sync kernel
-        _call("csvit_window_attention_ex", qkv.data_ptr(), _p(plain), _p(frag), out.data_ptr(), _code(qkv.dtype), B, H, W, C,
-              heads, ws, shift, 1, _stream(), nbytes=float(qkv.numel() + out.numel()) * qkv.element_size())
-        return out
-    _call("csvit_window_attention", qkv.data_ptr(), _p(plain), _p(frag), out.data_ptr(), _code(qkv.dtype), B, H, W, C,
+    _call("csvit_window_attention", qkv.data_ptr(), _p(bias_exp), out.data_ptr(), _code(qkv.dtype), B, H, W, C,
           heads, ws, shift, _stream(), nbytes=float(qkv.numel() + out.numel()) * qkv.element_size())
     return out
-
-
-def set_attention_impl(use_tcgen05: bool = True) -> None:
-    _lib.check(_lib.load().csvit_set_attention_impl(1 if use_tcgen05 else 0))
 
 
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, n_seq: int, Lq: int, S: int, heads: int,

@@ -33,7 +33,6 @@ static_assert(int(CSVIT_GEMM_SIMT_FP32) == int(GEMM_SIMT), "gemm impl codes");
 
 static inline cudaStream_t S(void* s) { return static_cast<cudaStream_t>(s); }
 static GemmTuning g_tune = {0, 0, -1, -1};
-static int g_attn_tc = 0;   // measured (profiles/r1_window_attention_impls.txt): the mma.sync kernel is 1.4x faster at 49-token windows
 
 extern "C" {
 
@@ -146,19 +145,6 @@ int csvit_linear(const void* A, long long lda, const void* W, long long ldw, int
   return launch_gemm(A, lda, W, ldw, in_dtype, M, N, K, ep, impl, g_tune, S(stream));
 }
 
-int csvit_ln_linear(const float* x, const float* gamma, const float* beta, float eps, int mode, int H, int W, int ws,
-                    int shift, const void* Wt, long long ldw, int dtype, int M, int N, int C, const float* bias, int act,
-                    void* out, long long ldo, void* stream) {
-  CSVIT_REQUIRE(act >= ACT_NONE && act <= ACT_RELU, "ln_linear: bad activation %d", act);
-  WinGeom g = make_geom(H > 0 ? H : 1, W > 0 ? W : 1, ws > 0 ? ws : 1, shift);
-  if (mode == LN_WINDOW) {
-    CSVIT_REQUIRE(ws > 0 && H % ws == 0 && W % ws == 0, "ln_linear(window): %dx%d not divisible by window %d", H, W, ws);
-    CSVIT_REQUIRE(shift >= 0 && shift < ws, "ln_linear(window): shift %d outside [0,%d)", shift, ws);
-    CSVIT_REQUIRE(M % (H * W) == 0, "ln_linear(window): M=%d not a multiple of %d tokens", M, H * W);
-  }
-  return launch_ln_gemm(x, gamma, beta, eps, mode, g, Wt, ldw, dtype, M, N, C, bias, act, out, ldo, S(stream));
-}
-
 int csvit_mlp_fused(const void* xn, long long ldxn, const void* W1, long long ldw1, const float* b1, const void* W2,
                     long long ldw2, const float* b2, float* x, long long ldx, int dtype, int M, int C, void* stream) {
   CSVIT_REQUIRE(ldxn >= C && ldw1 >= C && ldw2 >= 4 * C && ldx >= C, "mlp_fused: pitches smaller than the logical widths");
@@ -172,11 +158,6 @@ int csvit_set_gemm_tuning(int cluster, int tma_store, int max_ctas, int pair) {
   return 0;
 }
 
-int csvit_expand_rel_bias_mma(const float* table, float* out, int heads, int ws, void* stream) {
-  CSVIT_REQUIRE(heads > 0 && ws == 7, "expand_rel_bias_mma: heads=%d ws=%d (window 7 only)", heads, ws);
-  return launch_expand_rel_bias_mma(table, out, heads, S(stream));
-}
-
 int csvit_swin_attn_fused(const float* x, float eps, const void* wqkv_h, const float* bqkv_h,
                           const void* bias_op, void* ctx, int dtype, int B, int H, int W, int C, int heads, int ws, int shift,
                           void* stream) {
@@ -184,39 +165,22 @@ int csvit_swin_attn_fused(const float* x, float eps, const void* wqkv_h, const f
   return launch_swin_attn_fused(x, eps, wqkv_h, bqkv_h, bias_op, ctx, dtype, B, H, W, C, heads, ws, shift, S(stream));
 }
 
-int csvit_set_attention_impl(int use_tcgen05) {
-  g_attn_tc = use_tcgen05 ? 1 : 0;
-  return 0;
+int csvit_swin_attn_core(const void* qkv, long long ldq, const void* bias_log2, void* ctx, int dtype, int B, int H, int W, int C,
+                         int heads, int ws, int shift, int token_order, int q_prescaled, void* stream) {
+  CSVIT_REQUIRE(qkv && bias_log2 && ctx, "swin_attn_core: null operand");
+  return launch_swin_attn_core(qkv, ldq, bias_log2, ctx, dtype, B, H, W, C, heads, ws, shift, token_order, q_prescaled, S(stream));
 }
 
-static int window_attention_impl(const void* qkv, const float* bias, const float* bias_mma, void* out, int dtype, int B, int H, int W,
-                                 int C, int heads, int ws, int shift, int out_token_order, void* stream) {
-  if (dtype == DT_BF16 || dtype == DT_F16) {
-    // tcgen05 kernel (plain [h,L,L] bias) when that table is given, mma.sync kernel (fragment-ordered bias) otherwise
-    if (!out_token_order && bias != nullptr && (g_attn_tc || bias_mma == nullptr))
-      return launch_window_attention_tc(qkv, bias, out, dtype, B, H, W, C, heads, ws, shift, S(stream));
-    CSVIT_REQUIRE(bias_mma != nullptr, "window_attention: 16-bit path needs the csvit_expand_rel_bias_mma table");
-    return launch_window_attention_mma(qkv, bias_mma, out, dtype, B, H, W, C, heads, ws, shift, out_token_order ? 1 : 0, S(stream));
-  }
-  CSVIT_REQUIRE(!out_token_order, "window_attention: token-ordered output is built for the 16-bit kernel only");
-  CSVIT_REQUIRE(bias != nullptr, "window_attention: fp32 path needs the csvit_expand_rel_bias table");
-  CSVIT_REQUIRE(dtype == DT_F32, "window_attention: bad dtype %d", dtype);
+int csvit_window_attention(const void* qkv, const float* bias, void* out, int dtype, int B, int H, int W, int C, int heads, int ws,
+                           int shift, void* stream) {
+  CSVIT_REQUIRE(dtype == DT_F32, "window_attention: the exact fp32 kernel only (16-bit operands: csvit_swin_attn_core), dtype %d", dtype);
+  CSVIT_REQUIRE(bias != nullptr, "window_attention: needs the csvit_expand_rel_bias table");
   CSVIT_REQUIRE(C == heads * 32, "window_attention: head_dim must be 32 (C=%d heads=%d)", C, heads);
   CSVIT_REQUIRE(H % ws == 0 && W % ws == 0, "window_attention: %dx%d not divisible by window %d", H, W, ws);
   const int L = ws * ws, nW = (H / ws) * (W / ws);
   const float* q = static_cast<const float*>(qkv);
   return launch_attention_simt(q, q + C, q + 2 * C, out, DT_F32, 3ll * C, 3ll * C, 3ll * C, C, B * nW, L, L, heads,
                                0.17677669529663687f, bias, H, W, ws, shift, S(stream));
-}
-
-int csvit_window_attention(const void* qkv, const float* bias, const float* bias_mma, void* out, int dtype, int B, int H,
-                           int W, int C, int heads, int ws, int shift, void* stream) {
-  return window_attention_impl(qkv, bias, bias_mma, out, dtype, B, H, W, C, heads, ws, shift, 0, stream);
-}
-
-int csvit_window_attention_ex(const void* qkv, const float* bias, const float* bias_mma, void* out, int dtype, int B, int H,
-                              int W, int C, int heads, int ws, int shift, int out_token_order, void* stream) {
-  return window_attention_impl(qkv, bias, bias_mma, out, dtype, B, H, W, C, heads, ws, shift, out_token_order, stream);
 }
 
 int csvit_attention(const void* q, const void* k, const void* v, void* out, int dtype, long long ldq, long long ldk,

@@ -35,24 +35,21 @@
 #include "errors.h"
 #include "gemm.cuh"
 #include "rowops.cuh"
+#include "attn_common.cuh"
 
 namespace csvit {
 
 constexpr int FA_THREADS = 768;                    // 6 warpgroups: {TMA, MMA, 2 x L2 prefetch}, 3 x softmax, 2 x LayerNorm
 constexpr int FA_SM_WARP0 = 4, FA_LN_WARP0 = 16, FA_LN_WARPS = 8;
 constexpr int FA_NSLOT = 3;
-constexpr int FA_L = 49;
 constexpr int FA_ROWS = 2 * FA_L;                   // real token rows of a tile
 constexpr uint32_t FA_SLAB = 128 * 128;             // 128 rows x 64 16-bit columns
 constexpr uint32_t FA_STAGE = 96 * 128;             // ring stage: one head's 96 weight rows x 64 columns
-constexpr uint32_t FA_BIAS_BYTES = 49 * 56 * 2;     // one head's bias rows [49][56] fp16
-constexpr uint32_t FA_BIAS_STAGE = 5632;
 constexpr int FA_NBS = 2;
 constexpr int FA_NST = 4;
 constexpr uint32_t FA_QP = 0, FA_K = 16384, FA_V = 24576, FA_HB = 32768;   // per-parity head buffer: Q'/P', K', V'
 constexpr uint32_t FA_TM_SLOT = 160, FA_TM_S = 96;            // TMEM columns per slot; S' / O' offset inside it
 constexpr uint32_t FA_TAB = FA_K + 49 * 128;                  // the 15 padding key rows of K' (never read by a consumer): bias tables
-constexpr float FA_MASK_LOG2 = -100.0f * 1.4426950408889634f;
 
 template <int C>
 struct FaCfg {
@@ -79,59 +76,6 @@ struct FaParams {
   float qscale;          // log2(e) / sqrt(32)
   WinGeom g;
 };
-
-__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld_32x8(uint32_t taddr, uint32_t (&r)[8]) {
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-               : "r"(taddr)
-               : "memory");
-}
-__device__ __forceinline__ uint64_t fa_mnmajor_desc(uint32_t smem_addr) {
-  // MN-major operand of one 128-byte MN chunk (64 elements): rows = k, 8-row swizzle atoms of 1024 B (layout of gemm_ex.cu)
-  uint64_t d = 0;
-  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
-  d |= static_cast<uint64_t>(8192 >> 4) << 16;    // LBO: next MN chunk (unused, N = 64 is one chunk)
-  d |= static_cast<uint64_t>(1024 >> 4) << 32;    // SBO: next group of 8 k-rows
-  d |= static_cast<uint64_t>(1) << 46;
-  d |= static_cast<uint64_t>(2) << 61;
-  return d;
-}
-__device__ __forceinline__ float fa_exp2(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-
-__device__ __forceinline__ void tmem_ld_32x1(uint32_t taddr, uint32_t& r) {
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr) : "memory");
-}
-// a += lo(h2), b += hi(h2): fp16 addends, fp32 sums (one FHADD each)
-__device__ __forceinline__ void fa_add_h2(float& a, float& b, uint32_t h2) {
-  asm("{\n\t.reg .f16 lo, hi;\n\tmov.b32 {lo, hi}, %2;\n\tadd.rn.f32.f16 %0, lo, %0;\n\tadd.rn.f32.f16 %1, hi, %1;\n\t}" : "+f"(a), "+f"(b) : "r"(h2));
-}
-__device__ __forceinline__ void fa_bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ bool fa_elect_one() {
-  uint32_t pred;
-  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
-  return pred != 0;
-}
-__device__ __forceinline__ float fa_max3(float a, float b, float c) {
-  float d;
-  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
-  return d;
-}
 
 #ifdef CSVIT_FA_TRACE
 // Development aid (not built by default): clock64 timestamps of block 0's pipeline events, read back with csvit_debug_fa_trace.
@@ -341,7 +285,6 @@ swin_attn_fused_kernel(const __grid_constant__ CUtensorMap tmW, FaParams p) {
     const uint32_t lane_bits = uint32_t(quad * 32) << 16;
     const uint32_t ta = tmem_base + lane_bits + uint32_t(g) * FA_TM_SLOT;
     const uint32_t ts = ta + FA_TM_S;
-    const int nWy = p.g.H / p.g.ws;
     T16* ctx = static_cast<T16*>(p.ctx);
     long long tok_off = -1;
     uint32_t dm_lo = 0, dm_hi = 0;           // shift mask of this row: bit c set = key slot c lies in another region
@@ -358,22 +301,8 @@ swin_attn_fused_kernel(const __grid_constant__ CUtensorMap tmW, FaParams p) {
         if (j < FA_L && wg < p.num_windows) {
           const int b = wg / p.nW, w = wg - b * p.nW;
           tok_off = (static_cast<long long>(b) * p.g.N + win_row_to_token(p.g, w * FA_L + j)) * C;
-          if (p.g.shift > 0) {
-            const int wy = w / p.g.nWx, wx = w - wy * p.g.nWx;
-            const int iy = j / 7, ix = j - iy * 7, th = p.g.ws - p.g.shift;
-            unsigned long long dm = 0;
-            if (wy == nWy - 1) {      // key slots whose row side (iy < th) differs from mine
-              const unsigned long long rows_lo = (1ull << (7 * th)) - 1ull;
-              dm |= (iy < th) ? ~rows_lo : rows_lo;
-            }
-            if (wx == p.g.nWx - 1) {
-              unsigned long long cols_lo = 0;
-              for (int c = 0; c < FA_L; ++c) if (c % 7 < th) cols_lo |= 1ull << c;
-              dm |= (ix < th) ? ~cols_lo : cols_lo;
-            }
-            dm &= (1ull << FA_L) - 1ull;
-            dm_lo = uint32_t(dm); dm_hi = uint32_t(dm >> 32);
-          }
+          const unsigned long long dm = fa_row_mask(p.g, w, j);
+          dm_lo = uint32_t(dm); dm_hi = uint32_t(dm >> 32);
         }
       }
       // ---- D(h): projection accumulator -> Q' / K' / V'
@@ -464,13 +393,7 @@ swin_attn_fused_kernel(const __grid_constant__ CUtensorMap tmW, FaParams p) {
           if (lane == 0) mbar_arrive(&b_empty[bs]);
         }
         sv[49] = -INFINITY;
-        if ((dm_lo | dm_hi) != 0u) {
-#pragma unroll
-          for (int c = 0; c < FA_L; ++c) {
-            const uint32_t bit = c < 32 ? (dm_lo >> c) & 1u : (dm_hi >> (c - 32)) & 1u;
-            sv[c] += bit ? FA_MASK_LOG2 : 0.0f;
-          }
-        }
+        fa_add_mask(sv, dm_lo, dm_hi, p.g.ws - p.g.shift == 4);
         float mx0 = fa_max3(sv[0], sv[1], sv[2]), mx1 = fa_max3(sv[3], sv[4], sv[5]);
 #pragma unroll
         for (int c = 6; c < 48; c += 4) { mx0 = fa_max3(mx0, sv[c], sv[c + 1]); mx1 = fa_max3(mx1, sv[c + 2], sv[c + 3]); }

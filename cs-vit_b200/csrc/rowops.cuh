@@ -18,28 +18,20 @@ int launch_rel_index(int ws, int* out, cudaStream_t stream);
 int launch_merge_index_map(int H, int W, int* out, cudaStream_t stream);
 int launch_expand_rel_bias(const float* table, float* out, int heads, int ws, cudaStream_t stream);
 
-// lngemm.cu
-int launch_ln_gemm(const float* x, const float* gamma, const float* beta, float eps, int mode, const WinGeom& g,
-                   const void* W, long long ldw, int dtype, int M, int N, int C, const float* bias, int act, void* out,
-                   long long ldo, cudaStream_t stream);
-
-// attention_tc.cu
-int launch_window_attention_tc(const void* qkv, const float* bias_plain, void* out, int dtype, int B, int H, int W, int C,
-                               int heads, int ws, int shift, cudaStream_t stream);
-
 // attn_fused.cu
 int launch_swin_attn_fused(const float* x, float eps, const void* wqkv_h, const float* bqkv_h,
                            const void* bias_op, void* ctx, int dtype, int B, int H, int W, int C, int heads, int ws, int shift,
                            cudaStream_t stream);
 
+// attn_core.cu
+int launch_swin_attn_core(const void* qkv, long long ldq, const void* bias_log2, void* ctx, int dtype, int B, int H, int W, int C,
+                          int heads, int ws, int shift, int token_order, int q_prescaled, cudaStream_t stream);
+
 // mlp_fused.cu
 int launch_mlp_fused(const void* xn, long long ldxn, const void* W1, long long ldw1, const float* b1, const void* W2,
                      long long ldw2, const float* b2, float* x, long long ldx, int dtype, int M, int C, cudaStream_t stream);
 
-// attention.cu
-int launch_expand_rel_bias_mma(const float* table, float* out, int heads, cudaStream_t stream);
-int launch_window_attention_mma(const void* qkv, const float* bias_frag, void* out, int dtype, int B, int H, int W,
-                                int C, int heads, int ws, int shift, int tok_order, cudaStream_t stream);
+// attention_simt.cu
 int launch_attention_simt(const void* q, const void* k, const void* v, void* out, int dtype, long long ldq, long long ldk,
                           long long ldv, long long ldo, int n_seq, int Lq, int S, int heads, float scale,
                           const float* bias, int mH, int mW, int mws, int mshift, cudaStream_t stream);

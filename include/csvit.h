@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define CSVIT_ABI_VERSION 5
+#define CSVIT_ABI_VERSION 6
 
 #if defined(__GNUC__)
 #define CSVIT_API __attribute__((visibility("default")))
@@ -64,8 +64,6 @@ CSVIT_API int csvit_host_merge_index_map(int H, int W, int32_t* out);
 /* bias[h, i, j] = table[rel_pos_index(i, j), h]; table is [(2ws-1)^2, heads] fp32.      HF:428-434 */
 CSVIT_API int csvit_expand_rel_bias(const float* table, float* out, int heads, int ws, void* stream);
 
-CSVIT_API int csvit_expand_rel_bias_mma(const float* table, float* out, int heads, int ws, void* stream);
-
 /* ---- row kernels (HBM-bound) ----------------------------------------------------------------------------
  * LayerNorm over the last dim of fp32 x[B, H*W, C], eps inside the sqrt, output fp32 or bf16.
  *   CSVIT_LN_IDENTITY : out row r <- x row r                            HF:606/648 layernorm_*, HF:882 final norm
@@ -102,16 +100,6 @@ CSVIT_API int csvit_linear(const void* A, long long lda, const void* W, long lon
                  int out_dtype, int scatter_H, int scatter_W, int scatter_ws, int scatter_shift, int impl,
                  void* stream);
 
-/* LayerNorm fused into the GEMM that consumes it (CTA-pair tcgen05 kernel, normalised tile resident in smem):
- *   out[M, N] = act( LayerNorm(x_rows)[M, C] @ Wt[N, C]^T + bias ),  16-bit Wt / out (dtype), x fp32 [*, C].
- *   mode CSVIT_LN_IDENTITY: row r of x;  CSVIT_LN_WINDOW: rows gathered in shifted-window order (as csvit_layernorm).
- *   C in {128, 256, 512}, N a multiple of 64.
- * Replaces csvit_layernorm + csvit_linear for layernorm_before -> Q/K/V (HF:606-622, 404-406) and
- * layernorm_after -> intermediate.dense + GELU (HF:648, 514-519); the normalised activations never reach HBM. */
-CSVIT_API int csvit_ln_linear(const float* x, const float* gamma, const float* beta, float eps, int mode, int H, int W, int ws,
-                              int shift, const void* Wt, long long ldw, int dtype, int M, int N, int C, const float* bias,
-                              int act, void* out, long long ldo, void* stream);
-
 /* Fused MLP half-block for C in {128, 256}:  x[M,C] += GELU(xn[M,C] @ W1[4C,C]^T + b1) @ W2[C,4C]^T + b2, x fp32 in place,
  * xn / W1 / W2 16-bit (dtype).  The [M,4C] hidden tensor never reaches HBM (128x128 chunks: TMEM -> GELU -> smem ->
  * second tcgen05 GEMM).  Replaces intermediate.dense + GELU + output.dense + residual add   (HF:510-531, 650). */
@@ -126,27 +114,12 @@ CSVIT_API int csvit_mlp_fused(const void* xn, long long ldxn, const void* W1, lo
 CSVIT_API int csvit_set_gemm_tuning(int cluster, int tma_store, int max_ctas, int pair);
 
 /* ---- attention cores -------------------------------------------------------------------------------------
- * Swin window attention on window-ordered qkv[B*H*W, 3C] (Q|K|V column blocks, head h at columns 32h..):
+ * Swin window attention on window-ordered fp32 qkv[B*H*W, 3C] (Q|K|V column blocks, head h at columns 32h..):
  *   out[B*H*W, C] = softmax(Q K^T / sqrt(32) + bias[h] + shift_mask) V, heads merged.       HF:410-459
- * bf16 / fp16: tensor-core kernel (window 7, head_dim 32).  fp32: exact kernel (validation mode).
- * fp32 reads `bias` = the [heads, L, L] table of csvit_expand_rel_bias; the 16-bit kernel reads `bias_mma` = the
- * same values pre-arranged in MMA accumulator-fragment order by csvit_expand_rel_bias_mma
- * ([heads, 4, 7, 32, 4] floats, multiplied by log2(e) - that kernel's softmax runs in the log2 domain - with -inf in the
- * padding columns).  The unused one may be NULL.
- * 16-bit dtypes: two kernels exist.  The mma.sync kernel (needs `bias_mma`) is the default because it is faster at
- * 49-token windows; the tcgen05/TMEM kernel (two windows per block-diagonal 128-row tile, needs `bias`) runs after
- * csvit_set_attention_impl(1) or when only `bias` is given. */
-CSVIT_API int csvit_window_attention(const void* qkv, const float* bias, const float* bias_mma, void* out, int dtype,
-                                     int B, int H, int W, int C, int heads, int ws, int shift, void* stream);
-
-/* Same, with out_token_order = 1 (16-bit mma.sync kernel only): out rows are TOKEN-ordered - window_reverse + roll(+shift)
- * (HF:624-636) folded into the attention store - so that the output projection that follows runs on plain rows and its fp32
- * residual update can use the TMA-staged epilogue of csvit_linear. */
-CSVIT_API int csvit_window_attention_ex(const void* qkv, const float* bias, const float* bias_mma, void* out, int dtype,
-                                        int B, int H, int W, int C, int heads, int ws, int shift, int out_token_order,
-                                        void* stream);
-
-CSVIT_API int csvit_set_attention_impl(int use_tcgen05);
+ * Exact fp32 kernel of the validation mode (dtype must be CSVIT_F32); `bias` = the [heads, L, L] table of csvit_expand_rel_bias.
+ * 16-bit operands take csvit_swin_attn_core / csvit_swin_attn_fused (tcgen05) below. */
+CSVIT_API int csvit_window_attention(const void* qkv, const float* bias, void* out, int dtype, int B, int H, int W, int C,
+                                     int heads, int ws, int shift, void* stream);
 
 /* Fused shifted-window attention (north-star kernel; tcgen05 / TMEM, C in {128, 256}, window 7, head_dim 32): one launch from the
  * fp32 residual stream x[B*H*W, C] to the TOKEN-ordered 16-bit attention context ctx[B*H*W, C],
@@ -164,6 +137,20 @@ CSVIT_API int csvit_set_attention_impl(int use_tcgen05);
 CSVIT_API int csvit_swin_attn_fused(const float* x, float eps, const void* wqkv_h, const float* bqkv_h,
                                     const void* bias_op, void* ctx, int dtype, int B, int H, int W, int C,
                                     int heads, int ws, int shift, void* stream);
+
+/* Window-attention core on tcgen05 / TMEM for every Swin width (attn_core.cu): window-ordered 16-bit qkv[B*H*W, 3C] (row pitch ldq
+ * elements; per row q | k | v, head h in columns 32h..32h+31, as csvit_linear writes it after csvit_layernorm in window mode) ->
+ *   ctx = softmax(q k^T * qs + bias + shift_mask) v     per window and head
+ * replacing transpose_for_scores, Q K^T, the relative-position-bias gather, the mask add, softmax, P V and the head merge of
+ * HF:swin/modeling_swin.py:404-459 (mask: 556-582).  Operand tiles come in by TMA ({64 columns, 49 rows} boxes, 128-byte swizzle),
+ * both contractions run as tcgen05.mma with TMEM accumulators, four heads in flight per SM.
+ *   bias_log2    [heads*49, 56] fp16, the csvit_swin_attn_fused table: log2(e) * table[rel_pos_index(i, j), h], 0 for j >= 49
+ *   token_order  1: ctx rows in token order (window_reverse + roll(+s) folded into the store address, HF:631-636);
+ *                0: window order like qkv (the training forward)
+ *   q_prescaled  1: q already carries log2(e)/sqrt(32) (folded into the q rows of the Q/K/V weight and bias at packing time);
+ *                0: the kernel applies it to the logits */
+CSVIT_API int csvit_swin_attn_core(const void* qkv, long long ldq, const void* bias_log2, void* ctx, int dtype, int B, int H,
+                                   int W, int C, int heads, int ws, int shift, int token_order, int q_prescaled, void* stream);
 
 /* ---- SwinV2 ("V2:" = transformers/models/swinv2/modeling_swinv2.py) ---------------------------
  * Scaled-cosine window attention on window-ordered qkv[B*H*W, 3C] (layout as csvit_window_attention):

@@ -60,17 +60,25 @@ for stage, (hw, C, heads) in enumerate([(56, 128, 4), (28, 256, 8), (14, 512, 16
             ref = hf_attention_half(lg, xg[:8], hw)
         # --- GPU: this repo
         sa = lg.attention.self
-        wqkv = torch.cat([sa.query.weight, sa.key.weight, sa.value.weight], 0).detach().to(dt).contiguous()
-        bqkv = torch.cat([sa.query.bias, sa.key.bias, sa.value.bias], 0).detach().float().contiguous()
-        bias = ops.expand_rel_bias_mma(sa.relative_position_bias_table.detach(), 7)
         wo = lg.attention.output.dense.weight.detach().to(dt).contiguous(); bo = lg.attention.output.dense.bias.detach().float()
         g, b_ = lg.layernorm_before.weight.detach().float(), lg.layernorm_before.bias.detach().float()
-        def ours(xin):
-            xn = ops.layernorm(xin, g, b_, 1e-5, out_dtype=dt, mode=ops.LN_WINDOW, grid=(hw, hw), ws=7, shift=shift)
-            qkv = ops.linear(xn, wqkv, bqkv, out_dtype=dt)
-            ctx = ops.window_attention(qkv, bias, xin.shape[0] // N, hw, hw, heads, 7, shift)
-            ops.linear(ctx, wo, bo, resid=xin, out=xin, scatter=(hw, hw, 7, shift))
-            return xin
+        rel_index = ops.rel_pos_index(7).long()
+        qkvp = (sa.query.weight, sa.key.weight, sa.value.weight, sa.query.bias, sa.key.bias, sa.value.bias)
+        if C in ops.ATTN_FUSED_WIDTHS:      # the product's path per stage (cs_vit/net/swin_b200.py::_block)
+            pk = ops.pack_attn_fused(*qkvp, sa.relative_position_bias_table, rel_index, dt, g, b_)
+            def ours(xin):
+                ctx = ops.swin_attn_fused(xin, 1e-5, *pk, xin.shape[0] // N, hw, hw, heads, 7, shift)
+                ops.linear(ctx, wo, bo, resid=xin, out=xin)
+                return xin
+        else:
+            wqs, bqs = ops.pack_qkv_prescaled(*qkvp, dt)
+            bias_l2 = ops.pack_rel_bias_log2(sa.relative_position_bias_table, rel_index)
+            def ours(xin):
+                xn = ops.layernorm(xin, g, b_, 1e-5, out_dtype=dt, mode=ops.LN_WINDOW, grid=(hw, hw), ws=7, shift=shift)
+                qkv = ops.linear(xn, wqs, bqs, out_dtype=dt)
+                ctx = ops.swin_attn_core(qkv, bias_l2, xin.shape[0] // N, hw, hw, heads, 7, shift, token_order=True, q_prescaled=True)
+                ops.linear(ctx, wo, bo, resid=xin, out=xin)
+                return xin
         x2 = xg.reshape(B * N, C).clone()
         chk = ours(xg[:8].reshape(8 * N, C).clone()).view(8, N, C)
         err = ((chk - ref).norm() / ref.norm()).item()

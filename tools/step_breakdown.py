@@ -29,7 +29,7 @@ e1.record(); torch.cuda.synchronize()
 total = e0.elapsed_time(e1) / 5
 print(f"step {total:.3f} ms  -> {B / total * 1e3:.0f} img/s")
 acc = 0
-for name in ("csvit_linear", "csvit_linear_emit", "csvit_linear_lnfold", "csvit_mlp_fused", "csvit_swin_attn_fused", "csvit_window_attention", "csvit_window_attention_ex", "csvit_swinv2_window_attention", "csvit_layernorm_post", "csvit_layernorm", "csvit_attention", "csvit_affine_rows", "csvit_patch_im2col"):
+for name in ("csvit_linear", "csvit_linear_emit", "csvit_linear_lnfold", "csvit_mlp_fused", "csvit_swin_attn_fused", "csvit_swin_attn_core", "csvit_window_attention", "csvit_window_attention_ex", "csvit_swinv2_window_attention", "csvit_layernorm_post", "csvit_layernorm", "csvit_attention", "csvit_affine_rows", "csvit_patch_im2col"):
     ops.begin_profile(name)
     for _ in range(3): step()
     p = ops.end_profile()

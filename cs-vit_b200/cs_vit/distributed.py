@@ -48,7 +48,9 @@ def shard_batch(batch: Dict[str, object], rank: int, world: int) -> Dict[str, ob
 def _encode_paths(paths: Sequence[str], device) -> torch.Tensor:
     buf = torch.zeros(len(paths), PATH_BYTES, dtype=torch.uint8)
     for i, p in enumerate(paths):
-        b = p.encode("utf-8")[:PATH_BYTES]
+        b = p.encode("utf-8")
+        if len(b) > PATH_BYTES:      # the reference pads to the longest path (ref:scripts/eval.py:52-58); never truncate silently
+            raise ValueError(f"image path longer than {PATH_BYTES} bytes cannot be gathered: {p!r}")
         buf[i, : len(b)] = torch.tensor(list(b), dtype=torch.uint8)
     return buf.to(device)
 

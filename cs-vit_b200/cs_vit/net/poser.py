@@ -13,6 +13,8 @@ SURVEY.md §2.3 K18-K20 prescribes.
 """
 from __future__ import annotations
 
+import os
+
 import math
 import os.path as osp
 from enum import Enum
@@ -129,6 +131,13 @@ class PerspectiveEncoder(_KernelModule):
 def _load_mano(smplx_path: str, mano_layer: Optional[nn.Module]) -> nn.Module:
     if mano_layer is not None:
         return mano_layer
+    if os.environ.get("CSVIT_MANO") == "synthetic":
+        # explicit opt-in for boxes without the licensed MANO files (throughput / parity runs of the unmodified reference scripts,
+        # whose Poser(...) call has no mano_layer argument): the seeded stand-in used by the tests and the bench
+        import warnings
+        from ..utils.mano_standin import SyntheticMANO
+        warnings.warn("CSVIT_MANO=synthetic: using the seeded MANO stand-in, predicted meshes are NOT anatomical")
+        return SyntheticMANO()
     try:
         import smplx  # noqa: F401  (ref:cs_vit/net/ti_poser.py:12,268)
     except ImportError as e:

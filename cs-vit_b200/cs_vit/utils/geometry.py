@@ -77,3 +77,11 @@ def quaternion_to_matrix(q: torch.Tensor) -> torch.Tensor:
 
 def axis_angle_to_matrix(axis_angle: torch.Tensor) -> torch.Tensor:
     return quaternion_to_matrix(axis_angle_to_quaternion(axis_angle))
+
+
+def rotation_matrix_z(rad: torch.Tensor) -> torch.Tensor:
+    """``[b]`` angles -> ``[b,3,3]`` rotations about +z, counter-clockwise for ``R @ v``   (ref:cs_vit/utils/geometry.py:9-40;
+    the data sets' in-plane augmentation uses it, ref:cs_vit/dataset/DexYCB.py:169-172)."""
+    c, s_ = torch.cos(rad), torch.sin(rad)
+    z, o = torch.zeros_like(c), torch.ones_like(c)
+    return torch.stack([torch.stack([c, -s_, z], -1), torch.stack([s_, c, z], -1), torch.stack([z, z, o], -1)], -2)

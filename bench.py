@@ -83,6 +83,9 @@ def parse():
                     "(spatial_dexycb_swinb_spenc_addpat_ti ships 3); 0 = no latent consistency branch")
     ap.add_argument("--micro-batch", type=int, default=-1, help="images per backbone pass (L2-resident chunks); -1 = library default, 0 = whole batch")
     ap.add_argument("--no-graph", action="store_true", help="launch kernels one by one instead of replaying a CUDA graph")
+    ap.add_argument("--comm", choices=["auto", "symm", "nccl"], default="auto", help="finetune gradient transport: this library's "
+                    "allreduce kernel over symmetric memory (symm; auto picks it under NCCL groups) or NCCL all_reduce")
+    ap.add_argument("--no-finetune-record", action="store_true", help="spatial workload: skip the compact finetune sub-record")
     return ap.parse_args()
 
 
@@ -417,15 +420,27 @@ def run_ours(a):
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         rate, ms, threads, note = cpu_reference_rate(a.variant, a.cpu_sample, 2, 1)
         out["cpu_baseline"] = {"value": round(rate, 3), "unit": "images/s", "cores": threads, "kind": "port", "sample": note}
+    if not a.no_extras and not a.no_finetune_record and not temporal and a.variant == "swin_b":
+        # ---- configs[3] beside the headline, so that the driver's 1/2/4/8-GPU scaling record carries it: the graphed finetune
+        # step at batch 32/GPU with the gradient allreduce (the one collective on this target's data path)
+        del model, graphs, resident, pinned
+        torch.cuda.empty_cache()
+        fa = argparse.Namespace(**vars(a))
+        fa.batch = 32
+        ft = finetune_measure(fa, world, rank, local, dev, steps=min(a.steps, 10), warmup=2, comm=a.comm, split=False)
+        out["finetune"] = {k: ft[k] for k in ("metric", "value", "unit", "ms_per_step", "n_gpus", "steps", "skipped_steps",
+                                              "ms_per_step_without_allreduce", "allreduce_ms_exposed") if k in ft}
+        out["finetune"]["allreduce"] = ft["config"]["allreduce"]
+        out["finetune"]["launch"] = ft["config"]["launch"]
     if rank == 0:
-        print(json.dumps(out))
-    if world > 1:
-        dist.destroy_process_group()
+        print(json.dumps(out), flush=True)
+    hard_exit_if_distributed(world)
 
 
-def run_finetune(a):
+def finetune_measure(a, world, rank, local, dev, steps, warmup, comm="auto", split=True):
     """BASELINE configs[3]: Swin-B spatial finetune step (ref:scripts/finetune.py:211-227), per-GPU batch 32 (the reference's
-    value), data-parallel with the bucketed NCCL gradient allreduce of cs_vit/train.py overlapped with backward."""
+    value, SURVEY.md §6), data-parallel: the gradient buckets are reduced by cs_vit/train.py::GradReducer (this library's
+    allreduce kernel over symmetric memory, or NCCL with --comm nccl) overlapped with backward.  Returns the result dict."""
     import torch.distributed as dist
     from cs_vit import ops
     from cs_vit.net import Poser
@@ -433,17 +448,8 @@ def run_finetune(a):
     from cs_vit.train import GradReducer, GraphedFinetuneStep, broadcast_parameters, finetune_step, scaled_lr
     from cs_vit.utils.mano_standin import SyntheticMANO
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise RuntimeError("bench.py (impl ours) needs a CUDA device: there is no CPU fallback")
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    dev = torch.device("cuda", local)
     B = a.batch if a.batch != BATCH else 32
-    tmp = tempfile.mkdtemp(prefix=f"csvit_bench_{rank}_")
+    tmp = tempfile.mkdtemp(prefix=f"csvit_bench_ft_{rank}_")
     bdir = make_random_backbone_dir(os.path.join(tmp, a.variant), a.variant, seed=0)
     torch.manual_seed(0)
     model = Poser(bdir, image_size=224, mano_layer=SyntheticMANO(), spatial_layer_type="encoder", persp_decorate="patch",
@@ -453,7 +459,7 @@ def run_finetune(a):
     model = model.to(dev)
     broadcast_parameters(model)
     trainable = [p for p in model.parameters() if p.requires_grad]
-    reducer = GradReducer(trainable)
+    reducer = GradReducer(trainable, comm=comm)
     graphed = not a.no_graph
     opt = torch.optim.AdamW(trainable, lr=scaled_lr(1e-5, world, B), fused=True, capturable=graphed)
     batch = {k: v.to(dev) for k, v in make_inputs(B, 1, 224, seed=100 + rank, labels=True).items()}
@@ -464,12 +470,13 @@ def run_finetune(a):
         torch.cuda.synchronize()
 
     losses = []
+    gstep = None
     if graphed:      # the whole step (forward, loss, backward, reduction, clip, AdamW) replayed as one CUDA graph
-        gstep = GraphedFinetuneStep(model, batch, opt, reducer, warmup=max(a.warmup, 2))
+        gstep = GraphedFinetuneStep(model, batch, opt, reducer, warmup=max(warmup, 2))
         run_step = lambda: gstep(batch).clone()      # noqa: E731
     else:
         run_step = lambda: finetune_step(model, batch, opt, reducer)      # noqa: E731
-        for _ in range(max(a.warmup, 2)):              # step 1 also learns the bucket order
+        for _ in range(max(warmup, 2)):              # step 1 also learns the bucket order
             losses.append(run_step().item())
     sampler = ClockSampler(local) if rank == 0 else None
     barrier()
@@ -477,7 +484,7 @@ def run_finetune(a):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
     e0.record()
-    for _ in range(a.steps):
+    for _ in range(steps):
         last = run_step()
         losses.append(last)
     e1.record()
@@ -487,55 +494,96 @@ def run_finetune(a):
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     launches = ops.launch_count - n0
-    # forward / backward split of one more (eager) step (events, not part of the timed region)
-    from cs_vit.train import invalidate_packs
-    invalidate_packs(model)
-    reducer.zero_grad()
-    model.loss_tensors(batch)[0].backward()      # untimed: re-packs the weights for the eager path
-    reducer.finish()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
-    reducer.zero_grad()
-    ev[0].record()
-    eager_loss, _, _ = model.loss_tensors(batch)
-    ev[1].record()
-    eager_loss.backward()
-    reducer.finish()
-    ev[2].record()
-    torch.cuda.synchronize()
+    if gstep is not None:
+        launches = gstep.launches_per_step * steps       # graph replays: the captured C-ABI launches of one step, per replay
     nparams = sum(p.numel() for p in trainable)
-    value = world * B * a.steps / (ms.item() / 1e3)
+    value = world * B * steps / (ms.item() / 1e3)
     peak_tf, _, _ = peaks()
     res = {
         "metric": "images/sec Swin-B spatial finetune step (fwd+bwd+AdamW) bs32/GPU", "value": round(value, 1), "unit": "images/s",
-        "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 2), "ms_per_step": round(ms.item() / a.steps, 3),
+        "n_gpus": world, "steps": steps, "warmup": max(warmup, 2), "ms_per_step": round(ms.item() / steps, 3),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": a.precision, "data": "synthetic",
         "config": {"launch": "one CUDA graph per step (cs_vit.train.GraphedFinetuneStep)" if graphed else "eager",
                    "workload": f"{a.variant} spatial model finetune step (Poser.forward loss, backward, grad clip 5.0, fused AdamW), "
                                f"batch {B}/GPU, 224x224, train-mode BatchNorm"
                                + (f", latent consistency branch with {a.latent_layers} layers ('ti' configuration)" if a.latent_layers else ""),
                    "global_batch": B * world, "parallelism": f"dp{world}",
-                   "allreduce": f"{nparams * 4 / 1e6:.1f} MB fp32 gradients in {len(reducer.bucket_summary())} flat buckets, "
-                                f"async NCCL allreduce launched from grad-ready hooks",
+                   "allreduce": f"{nparams * 4 / 1e6:.1f} MB fp32 gradients in {len(reducer.bucket_summary())} flat buckets, reduced from "
+                                f"grad-ready hooks on a side stream; transport: {reducer.transport}",
                    "operands": f"{a.precision} tensor-core operands forward and backward, fp32 accumulate / gradients / optimizer"},
         "gpu_launches": launches,
         "model_flops_frac_of_peak": round(3 * value / world * FLOP_PER_IMAGE / (peak_tf * 1e12), 4),
-        "eager_forward_ms": round(ev[0].elapsed_time(ev[1]), 3), "eager_backward_ms": round(ev[1].elapsed_time(ev[2]), 3),
+        "skipped_steps": gstep.skipped_steps if gstep is not None else None,
         "losses": [round(float(x), 3) for x in losses],
         "clocks": sampler.window(t0, t1) if sampler else None,
     }
     if sampler:
         sampler.stop()
-    if rank == 0:
-        print(json.dumps(res), flush=True)
+    if world > 1 and graphed:
+        # exposed communication = this step minus the same graphed step with the reduction switched off (local gradients only)
+        reducer.remove()
+        local_red = GradReducer(trainable, comm="nccl")
+        local_red.world = 1
+        lstep = GraphedFinetuneStep(model, batch, opt, local_red, warmup=2)
+        barrier()
+        e0.record()
+        for _ in range(steps):
+            lstep(batch)
+        e1.record()
+        torch.cuda.synchronize()
+        ms_l = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        dist.all_reduce(ms_l, op=dist.ReduceOp.MAX)
+        res["ms_per_step_without_allreduce"] = round(ms_l.item() / steps, 3)
+        res["allreduce_ms_exposed"] = round((ms.item() - ms_l.item()) / steps, 3)
+        del lstep
+    elif split:
+        # forward / backward split of one more (eager) step (events, not part of the timed region)
+        from cs_vit.train import invalidate_packs
+        invalidate_packs(model)
+        reducer.zero_grad()
+        model.loss_tensors(batch)[0].backward()      # untimed: re-packs the weights for the eager path
+        reducer.finish()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        reducer.zero_grad()
+        ev[0].record()
+        eager_loss, _, _ = model.loss_tensors(batch)
+        ev[1].record()
+        eager_loss.backward()
+        reducer.finish()
+        ev[2].record()
+        torch.cuda.synchronize()
+        res["eager_forward_ms"] = round(ev[0].elapsed_time(ev[1]), 3)
+        res["eager_backward_ms"] = round(ev[1].elapsed_time(ev[2]), 3)
+    del gstep, run_step
+    return res
+
+
+def hard_exit_if_distributed(world):
+    """A replayable graph that holds captured communication work must be gone before the communicator is torn down (otherwise
+    destroy_process_group can wait forever); after the final barrier a hard exit is the robust teardown."""
+    import torch.distributed as dist
     if world > 1:
-        # A replayable graph that holds captured NCCL work must be gone before the communicator is torn down (otherwise
-        # destroy_process_group can wait forever); after the final barrier a hard exit is the robust teardown.
-        if graphed:
-            del gstep, run_step
         torch.cuda.synchronize()
         dist.barrier()
         sys.stdout.flush()
         os._exit(0)
+
+
+def run_finetune(a):
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py (impl ours) needs a CUDA device: there is no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    res = finetune_measure(a, world, rank, local, dev, a.steps, a.warmup, comm=a.comm)
+    if rank == 0:
+        print(json.dumps(res), flush=True)
+    hard_exit_if_distributed(world)
 
 
 def main():

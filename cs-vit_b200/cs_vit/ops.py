@@ -496,6 +496,8 @@ def layernorm_bwd(x: torch.Tensor, dy: torch.Tensor, gamma: torch.Tensor, eps: f
     if dres is not None and (dres.dtype != torch.float32 or dres.shape != x.shape or not dres.is_contiguous()):
         raise ValueError("layernorm_bwd: dres must be contiguous float32 of x's shape")
     dx = torch.empty_like(x)
+    if (dgamma is None) != (dbeta is None):
+        raise ValueError("layernorm_bwd: pass both dgamma and dbeta accumulators or neither")
     if dgamma is None:      # caller-provided accumulators must already be zeroed
         dgamma = torch.zeros(width, dtype=torch.float32, device=x.device)
         dbeta = torch.zeros(width, dtype=torch.float32, device=x.device)
@@ -557,3 +559,20 @@ def host_merge_index_map(H: int, W: int) -> torch.Tensor:
 def set_gemm_tuning(cluster: int = 0, tma_store: int = -1, max_ctas: int = 0, pair: int = -1) -> None:
     """Ablation knobs of the GEMM engine (see ``csvit_set_gemm_tuning``); defaults restore automatic choices."""
     _lib.check(_lib.load().csvit_set_gemm_tuning(cluster, tma_store, max_ctas, pair))
+
+
+# ---------------------------------------------------------------------------------------------- multi-GPU
+ALLREDUCE_FLAG_BYTES = 4096
+
+
+def allreduce_f32(buf_ptrs, flag_ptrs, multicast_ptr: int, numel: int, rank: int, world: int, scale: float, ctas: int = 0) -> None:
+    """In-place SUM * scale of one fp32 bucket held in symmetric memory by every rank (``csvit_allreduce_f32``), on the current
+    stream.  ``buf_ptrs`` / ``flag_ptrs``: the bucket's / the flag region's device address on every rank (ints, rank order);
+    ``multicast_ptr``: the bucket's NVSwitch multicast address or 0.  Collective: every rank calls it with the same arguments."""
+    import ctypes
+    if len(buf_ptrs) != world or len(flag_ptrs) != world:
+        raise ValueError("allreduce_f32: need one buffer and one flag pointer per rank")
+    bufs = (ctypes.c_void_p * world)(*[int(x) for x in buf_ptrs])
+    flags = (ctypes.c_void_p * world)(*[int(x) for x in flag_ptrs])
+    _call("csvit_allreduce_f32", bufs, flags, int(multicast_ptr) or None, int(numel), rank, world, float(scale), int(ctas), _stream(),
+          nbytes=float(numel) * 4.0)

@@ -183,6 +183,13 @@ int csvit_window_attention(const void* qkv, const float* bias, void* out, int dt
                                0.17677669529663687f, bias, H, W, ws, shift, S(stream));
 }
 
+int csvit_allreduce_f32(const void* const* bufs, const void* const* flags, void* multicast, long long n, int rank, int world, float scale,
+                        int ctas, void* stream) {
+  CSVIT_REQUIRE(bufs && flags, "allreduce_f32: null pointer tables");
+  return launch_allreduce_f32(const_cast<void* const*>(bufs), const_cast<void* const*>(flags), multicast, n, rank, world, scale, ctas,
+                              S(stream));
+}
+
 int csvit_attention(const void* q, const void* k, const void* v, void* out, int dtype, long long ldq, long long ldk,
                     long long ldv, long long ldo, int n_seq, int Lq, int S_, int heads, float scale, void* stream) {
   CSVIT_REQUIRE(ok_dtype(dtype), "attention: bad dtype %d", dtype);

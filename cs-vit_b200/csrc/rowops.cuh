@@ -27,6 +27,10 @@ int launch_swin_attn_fused(const float* x, float eps, const void* wqkv_h, const 
 int launch_swin_attn_core(const void* qkv, long long ldq, const void* bias_log2, void* ctx, int dtype, int B, int H, int W, int C,
                           int heads, int ws, int shift, int token_order, int q_prescaled, cudaStream_t stream);
 
+// allreduce.cu
+int launch_allreduce_f32(void* const* bufs, void* const* flags, void* mc, long long n, int rank, int world, float scale, int ctas,
+                         cudaStream_t stream);
+
 // mlp_fused.cu
 int launch_mlp_fused(const void* xn, long long ldxn, const void* W1, long long ldw1, const float* b1, const void* W2,
                      long long ldw2, const float* b2, float* x, long long ldx, int dtype, int M, int C, cudaStream_t stream);

@@ -152,6 +152,20 @@ CSVIT_API int csvit_swin_attn_fused(const float* x, float eps, const void* wqkv_
 CSVIT_API int csvit_swin_attn_core(const void* qkv, long long ldq, const void* bias_log2, void* ctx, int dtype, int B, int H,
                                    int W, int C, int heads, int ws, int shift, int token_order, int q_prescaled, void* stream);
 
+/* ---- data-parallel gradient allreduce over NVLink / NVSwitch peer memory (allreduce.cu) --------------------------------------
+ * In-place fp32 SUM * scale of one flat bucket that lives at bufs[r] in the symmetric memory of every rank r (HOST arrays of
+ * `world` DEVICE pointers; bufs[rank] is this GPU's own copy).  Replaces the bucketed NCCL allreduce that
+ * DistributedDataParallel issues for ref:scripts/finetune.py:133-135, 217 (loss.backward()).
+ *   flags      per rank a zero-initialised region of CSVIT_ALLREDUCE_FLAG_BYTES in symmetric memory (cross-GPU barriers)
+ *   multicast  NVSwitch multicast address of the bucket (multimem.ld_reduce / multimem.st: the switch adds), or NULL for the
+ *              two-shot form over plain P2P loads / stores
+ *   n          floats, a multiple of 4;  world <= 8;  ctas: grid size, identical on all ranks (0 = default)
+ * Every rank must call it with the same n / world / ctas, stream-ordered after the kernels that wrote its bucket; the kernel
+ * returns on a rank once every rank's result has landed in that rank's copy. */
+#define CSVIT_ALLREDUCE_FLAG_BYTES 4096
+CSVIT_API int csvit_allreduce_f32(const void* const* bufs, const void* const* flags, void* multicast, long long n, int rank, int world,
+                                  float scale, int ctas, void* stream);
+
 /* ---- SwinV2 ("V2:" = transformers/models/swinv2/modeling_swinv2.py) ---------------------------
  * Scaled-cosine window attention on window-ordered qkv[B*H*W, 3C] (layout as csvit_window_attention):
  *   out = softmax( normalize(Q) normalize(K)^T * logit_scale[h] + bias_tab[h, rel_pos_index(i, j)]

@@ -183,6 +183,80 @@ def test_grad_reducer_world2_matches_full_batch():
     assert sorted(q.get(timeout=5)[0] for _ in range(world)) == [0, 1]
 
 
+class _Branchy(torch.nn.Module):
+    """Which parameters receive a gradient depends on the data: ``extra`` is used only when ``batch["use_extra"]`` is set."""
+
+    def __init__(self):
+        super().__init__()
+        g = torch.Generator().manual_seed(5)
+        self.a = torch.nn.Linear(8, 8)
+        self.extra = torch.nn.Linear(8, 8)
+        self.late = torch.nn.Linear(8, 8)
+        for p in self.parameters():
+            with torch.no_grad():
+                p.copy_(torch.randn(p.shape, generator=g) * 0.2)
+
+    def forward(self, batch):
+        h = self.a(batch["x"])
+        if batch["use_extra"]:
+            h = h + self.extra(batch["x"])
+        if batch["use_late"]:
+            h = h + self.late(batch["x"])
+        loss = (h ** 2).mean()
+        if batch.get("poison"):
+            loss = loss * float("nan")
+        return {"loss": loss}
+
+
+def _divergent_worker(rank, world, port, q):
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "cs-vit_b200"))
+    from cs_vit import train
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        model = _Branchy()
+        reducer = train.GradReducer(model.parameters(), bucket_bytes=1 << 10)
+        opt = torch.optim.SGD(model.parameters(), lr=0.1)
+        g = torch.Generator().manual_seed(40 + rank)
+        # step 1: only rank 1 touches `extra`; step 2: only rank 0; step 3: `late` appears (on rank 1 only) after the buckets were built;
+        # step 4: rank 0's loss is NaN -> every rank skips the batch, nobody hangs, nobody steps
+        plan = [(rank == 1, False, False), (rank == 0, False, False), (False, rank == 1, False), (False, False, rank == 0)]
+        for step, (ue, ul, poison) in enumerate(plan):
+            before = [p.detach().clone() for p in model.parameters()]
+            batch = {"x": torch.randn(4, 8, generator=g), "use_extra": ue, "use_late": ul, "poison": poison}
+            train.finetune_step(model, batch, opt, reducer, max_norm=1e9)
+            flat = torch.cat([p.detach().reshape(-1) for p in model.parameters()])
+            both = [torch.zeros_like(flat) for _ in range(world)]
+            dist.all_gather(both, flat)
+            assert torch.equal(both[0], both[1]), f"replicas diverged at step {step}"
+            changed = any(not torch.equal(b, p) for b, p in zip(before, model.parameters()))
+            assert changed == (step < 3), (step, changed)
+            if step < 2:
+                assert model.extra.weight.grad is not None          # the averaged gradient reaches the rank that had none
+            if step == 2:
+                assert model.late.weight.grad is not None
+        assert train.skipped_steps == 1
+        q.put((rank, "ok"))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_grad_reducer_rank_divergent_gradients_and_nan_guard():
+    """ranks that differ in which parameters get gradients must still issue matching collectives and keep their
+    replicas identical; a non-finite loss on one rank skips the batch on all ranks (ref:scripts/finetune.py:219-222)."""
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_divergent_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert sorted(q.get(timeout=5)[0] for _ in range(world)) == [0, 1]
+
+
 def test_scaled_lr_rule():
     import sys
     sys.path.insert(0, os.path.join(ROOT, "cs-vit_b200"))

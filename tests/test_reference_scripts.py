@@ -159,3 +159,16 @@ def test_eval_flow_on_the_shim_matches_predict_batch(tmp_path, phase, T):
     assert torch.allclose(pred, want.float().cpu(), rtol=1e-5, atol=1e-3), (pred - want.float().cpu()).abs().max()
     assert torch.isfinite(torch.cat(rows["joint_reproj_pred"])).all()
     assert torch.equal(torch.cat(rows["joint_cam_gt"]), full["joint_cam"][:, -1])
+
+
+@pytest.mark.gpu
+def test_own_allreduce_kernel_two_ranks():
+    """csvit_allreduce_f32 (symmetric-memory allreduce of the finetune gradients) against NCCL on 2 GPUs: tools/multi_gpu_check.py
+    under torchrun.  Needs two devices; the driver's single-GPU test box skips it (the 8-GPU record is profiles/r2_multi_gpu_check_*.txt)."""
+    import subprocess
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29731", os.path.join(root, "tools", "multi_gpu_check.py")], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]

@@ -561,6 +561,33 @@ def set_gemm_tuning(cluster: int = 0, tma_store: int = -1, max_ctas: int = 0, pa
     _lib.check(_lib.load().csvit_set_gemm_tuning(cluster, tma_store, max_ctas, pair))
 
 
+# ---------------------------------------------------------------------------------------------- input pipeline
+def crop_resize(frames: torch.Tensor, boxes: torch.Tensor, size: int = 224, expansion_ratio: float = 0.0):
+    """On-device hand crops (``csvit_crop_resize``): ``frames`` fp32 ``[N,3,H,W]`` in [0,1] or uint8 ``[N,H,W,3]``; ``boxes`` fp32
+    ``[N,4]`` xyxy.  ``expansion_ratio > 0``: the boxes are tight boxes, made square and expanded as
+    ref:cs_vit/utils/img.py:358-370; returns ``(patches [N,3,size,size] fp32, square_boxes [N,4])`` - the ``img_tensor`` /
+    ``square_bboxes`` arguments of ``Poser.predict_batch`` (add the frame dimension with ``[:, None]``)."""
+    _dev(frames, boxes)
+    u8 = frames.dtype == torch.uint8
+    if u8:
+        if frames.dim() != 4 or frames.shape[-1] != 3:
+            raise ValueError("crop_resize: uint8 frames must be [N,H,W,3]")
+        N, H, W = frames.shape[:3]
+    elif frames.dtype == torch.float32:
+        if frames.dim() != 4 or frames.shape[1] != 3:
+            raise ValueError("crop_resize: float frames must be [N,3,H,W]")
+        N, _, H, W = frames.shape
+    else:
+        raise TypeError(f"crop_resize: frames must be float32 or uint8, got {frames.dtype}")
+    if not frames.is_contiguous() or boxes.dtype != torch.float32 or tuple(boxes.shape) != (N, 4) or not boxes.is_contiguous():
+        raise ValueError("crop_resize: frames must be contiguous and boxes contiguous float32 [N,4]")
+    out = torch.empty(N, 3, size, size, dtype=torch.float32, device=frames.device)
+    square = torch.empty(N, 4, dtype=torch.float32, device=frames.device)
+    _call("csvit_crop_resize", frames.data_ptr(), 1 if u8 else 0, N, H, W, boxes.data_ptr(), float(expansion_ratio), square.data_ptr(),
+          out.data_ptr(), size, _stream(), nbytes=float(out.numel()) * 4.0)
+    return out, square
+
+
 # ---------------------------------------------------------------------------------------------- multi-GPU
 ALLREDUCE_FLAG_BYTES = 4096
 

@@ -183,6 +183,12 @@ int csvit_window_attention(const void* qkv, const float* bias, void* out, int dt
                                0.17677669529663687f, bias, H, W, ws, shift, S(stream));
 }
 
+int csvit_crop_resize(const void* frames, int frames_u8, int N, int H, int W, const float* boxes, float expansion_ratio,
+                      float* square_boxes_out, float* out, int size, void* stream) {
+  CSVIT_REQUIRE(frames && boxes && out, "crop_resize: null operand");
+  return launch_crop_resize(frames, frames_u8, N, H, W, boxes, expansion_ratio, square_boxes_out, out, size, S(stream));
+}
+
 int csvit_allreduce_f32(const void* const* bufs, const void* const* flags, void* multicast, long long n, int rank, int world, float scale,
                         int ctas, void* stream) {
   CSVIT_REQUIRE(bufs && flags, "allreduce_f32: null pointer tables");

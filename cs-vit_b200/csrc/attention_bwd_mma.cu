@@ -291,12 +291,11 @@ win_attn_bwd_kernel(const T* __restrict__ qkv, const T* __restrict__ dout, T* __
 template <typename T>
 static int launch_wab(const void* qkv, const void* dout, void* dqkv, const float* bias, float* dbias, int num_windows, int C,
                       int heads, const WinGeom& g, int nW, cudaStream_t stream) {
-  static bool configured = false;
+  static DeviceOnce once;
   auto kern = win_attn_bwd_kernel<T>;
   const int smem = 2 * BA_TABLE_BYTES + BA_WARPS * BA_WARP_BYTES;
-  if (!configured) {
+  if (once.first()) {
     CSVIT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = true;
   }
   int per_head = (num_windows + BA_WARPS - 1) / BA_WARPS;
   const int cap = (148 * 3) / heads > 0 ? (148 * 3) / heads : 1;

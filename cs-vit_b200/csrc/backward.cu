@@ -502,11 +502,10 @@ template <typename T>
 static int launch_ab_t(const void* q, const void* k, const void* v, const void* dout, void* dq, void* dk, void* dv, long long ldq,
                        long long ldk, long long ldv, long long ldo, long long lddq, long long lddk, long long lddv, int n_seq, int Lq,
                        int S, int heads, float scale, const float* bias, float* dbias, const WinGeom& g, int nW, cudaStream_t stream) {
-  static bool configured = false;
+  static DeviceOnce once;
   auto kern = attention_bwd_kernel<T>;
-  if (!configured) {
+  if (once.first()) {
     CSVIT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(AB_SMEM)));
-    configured = true;
   }
   int per_head = (148 * 2 + heads - 1) / heads;
   if (per_head > n_seq) per_head = n_seq;

@@ -9,6 +9,20 @@ namespace csvit {
 int set_error(const char* fmt, ...);
 const char* last_error();
 
+// Function attributes (cudaFuncSetAttribute) belong to a device / context, not to the process: a launcher keeps one of these as
+// a function-local static and configures its kernel the first time it runs on EACH device.
+struct DeviceOnce {
+  unsigned long long mask = 0;
+  bool first() {
+    int d = 0;
+    cudaGetDevice(&d);
+    const unsigned long long bit = 1ull << (d & 63);
+    if (mask & bit) return false;
+    mask |= bit;
+    return true;
+  }
+};
+
 }  // namespace csvit
 
 #define CSVIT_CUDA(expr)                                                                              \

@@ -274,11 +274,10 @@ template <int BN, int FMT, int CS>
 static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmR, int K,
                      const EpiParams& ep, int max_ctas, cudaStream_t stream) {
   using Cfg = TcCfg<BN>;
-  static bool configured = false;
+  static DeviceOnce once;
   auto kern = gemm_tc_kernel<BN, FMT, CS>;
-  if (!configured) {
+  if (once.first()) {
     CSVIT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(Cfg::SMEM)));
-    configured = true;
   }
   const int num_m = (ep.M + kBM - 1) / kBM, num_n = (ep.N + BN - 1) / BN;
   const int ctiles = ((num_m + CS - 1) / CS) * num_n;

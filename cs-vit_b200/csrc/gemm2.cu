@@ -149,11 +149,10 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 template <int FMT>
 static int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmR, int K,
                        const EpiParams& ep, int max_ctas, cudaStream_t stream) {
-  static bool configured = false;
+  static DeviceOnce once;
   auto kern = gemm_pair_kernel<FMT>;
-  if (!configured) {
+  if (once.first()) {
     CSVIT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kPairSmem)));
-    configured = true;
   }
   const int num_mp = (ep.M + 2 * kBM - 1) / (2 * kBM), num_n = (ep.N + kPairBN - 1) / kPairBN;
   int pairs = (max_ctas > 0 ? max_ctas : num_sms()) / 2;

@@ -236,11 +236,10 @@ gemm_ex_simt_kernel(const float* __restrict__ A, long long lda, int a_mn, const 
 template <int FMT, bool A_MN, bool B_MN>
 static int launch_ex_t(const CUtensorMap& tmA, const CUtensorMap& tmB, int K, int splits, int atomic, const EpiParams& ep,
                        cudaStream_t stream) {
-  static bool configured = false;
+  static DeviceOnce once;
   auto kern = gemm_ex_kernel<FMT, A_MN, B_MN>;
-  if (!configured) {
+  if (once.first()) {
     CSVIT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kExSmem)));
-    configured = true;
   }
   const int items = ((ep.M + kBM - 1) / kBM) * ((ep.N + kExBN - 1) / kExBN) * splits;
   const int ctas = items < num_sms() ? items : num_sms();

@@ -220,11 +220,10 @@ template <int FMT, int C>
 static int launch_mlp(const CUtensorMap& tmX, const CUtensorMap& tmW1, const CUtensorMap& tmW2, const CUtensorMap& tmR,
                       const MlpParams& mp, const EpiParams& ep, cudaStream_t stream) {
   using Cfg = MlpCfg<C>;
-  static bool configured = false;
+  static DeviceOnce once;
   auto kern = mlp_fused_kernel<FMT, C>;
-  if (!configured) {
+  if (once.first()) {
     CSVIT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(Cfg::SMEM)));
-    configured = true;
   }
   const int tiles = (mp.M + kBM - 1) / kBM;
   const int ctas = tiles < num_sms() ? tiles : num_sms();

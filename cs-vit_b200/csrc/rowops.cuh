@@ -27,6 +27,10 @@ int launch_swin_attn_fused(const float* x, float eps, const void* wqkv_h, const 
 int launch_swin_attn_core(const void* qkv, long long ldq, const void* bias_log2, void* ctx, int dtype, int B, int H, int W, int C,
                           int heads, int ws, int shift, int token_order, int q_prescaled, cudaStream_t stream);
 
+// crop.cu
+int launch_crop_resize(const void* frames, int frames_u8, int N, int H, int W, const float* boxes, float expansion, float* square_out,
+                       float* out, int S, cudaStream_t stream);
+
 // allreduce.cu
 int launch_allreduce_f32(void* const* bufs, void* const* flags, void* mc, long long n, int rank, int world, float scale, int ctas,
                          cudaStream_t stream);

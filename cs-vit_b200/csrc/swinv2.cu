@@ -345,10 +345,9 @@ static int launch_v2_t(const void* qkv, const float* bias_tab, const float* logi
                        const WinGeom& g, int nW, float mask_value, int tok_order, cudaStream_t stream) {
   auto kern = swinv2_attn_kernel<T, WS, TILES>;
   const int smem = v2_smem_bytes(WS);
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce once;
+  if (once.first()) {
     CSVIT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = true;
   }
   int per_head = num_windows;
   const int resident = TILES == 2 ? 3 : 4;
@@ -381,12 +380,11 @@ int launch_swinv2_window_attention(const void* qkv, const float* bias_tab, const
   CSVIT_REQUIRE(dtype == DT_F32, "swinv2_window_attention: bad dtype %d", dtype);
   const int L = ws * ws, tw = 2 * ws - 1;
   const int smem = (2 * L * 33 + L + 4 * L + 4 * 32 + tw * tw + L) * 4;
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce once;
+  if (once.first()) {
     const int Lm = V2_MAXL, twm = 31;
     CSVIT_CUDA(cudaFuncSetAttribute(swinv2_attn_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (2 * Lm * 33 + Lm + 4 * Lm + 4 * 32 + twm * twm + Lm) * 4));
-    configured = true;
   }
   const int blocks = static_cast<int>(items < num_sms() * 8 ? items : num_sms() * 8);
   swinv2_attn_f32_kernel<<<blocks, V2_THREADS, smem, stream>>>(static_cast<const float*>(qkv), bias_tab, logit_scale,

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define CSVIT_ABI_VERSION 6
+#define CSVIT_ABI_VERSION 7
 
 #if defined(__GNUC__)
 #define CSVIT_API __attribute__((visibility("default")))
@@ -84,6 +84,16 @@ CSVIT_API int csvit_affine_rows(const float* x, const float* scale, const float*
  * ref:cs_vit/net/ti_poser.py:239-243,425   HF:286-295.   mean/std are HOST pointers to 3 floats. */
 CSVIT_API int csvit_patch_im2col(const float* img, void* out, int out_dtype, int B, int S, const float* mean3,
                        const float* std3, void* stream);
+
+/* On-device crop-and-resize of the hand region: out[n] = bilinear S x S resample of frames[n] over the box of image n, zeros outside
+ * the frame, endpoints inclusive (align_corners) - what ref:cs_vit/utils/img.py:339-390 crop_tensor_with_square_box computes per
+ * sample on the CPU with kornia.  frames: fp32 [N,3,H,W] in [0,1] (frames_u8 = 0) or uint8 [N,H,W,3] as decoded (frames_u8 = 1,
+ * scaled by 1/255).  boxes [N,4] xyxy pixels: with expansion_ratio > 0 they are TIGHT boxes and the kernel first makes them square
+ * on the longer side and scales them about the centre (ref :358-370), writing the boxes it cropped to square_boxes_out [N,4]
+ * (may be NULL) - the `square_bboxes` Poser.predict_batch needs; with expansion_ratio <= 0 they are cropped as given.
+ * out: fp32 [N,3,S,S]. */
+CSVIT_API int csvit_crop_resize(const void* frames, int frames_u8, int N, int H, int W, const float* boxes, float expansion_ratio,
+                                float* square_boxes_out, float* out, int S, void* stream);
 
 /* ---- GEMM engine (tcgen05 + TMEM + TMA) ----------------------------------------------------------------
  * out[orow, :N] = act(A[M,K] @ W[N,K]^T + bias) + resid[orow, :N]

@@ -52,6 +52,7 @@ SIGNATURES = {
     "csvit_col_reduce": [c_void_p, c_int, c_longlong, c_void_p, c_longlong, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                          c_int, c_int, c_void_p, c_int, c_longlong, c_void_p, c_void_p, c_void_p],
     "csvit_transpose_f32": [c_void_p, c_longlong, c_void_p, c_longlong, c_int, c_int, c_void_p],
+    "csvit_row_scale_add": [c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_int, c_void_p],
     "csvit_eltwise": [c_int, c_void_p, c_void_p, c_void_p, c_int, c_longlong, c_void_p],
     "csvit_affine2_rows": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_void_p],
     "csvit_layernorm_bwd": [c_void_p, c_void_p, c_int, c_longlong, c_void_p, c_float, c_int, c_int, c_int, c_int, c_int, c_int,

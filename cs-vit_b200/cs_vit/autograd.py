@@ -41,10 +41,17 @@ class SwinBlockFn(Function):
     @staticmethod
     def forward(ctx, x, ln1w, ln1b, wq, bq, wk, bk, wv, bv, table, wo, bo, ln2w, ln2b, w1, b1, w2, b2, pk, meta):
         B, H, W, heads, ws, shift, eps, act, impl = meta
+        keep_scale = pk.get("keep_scale")      # [B] fp32 stochastic-depth scale of this block's attention branch, or None
         xn1 = ops.layernorm(x, ln1w, ln1b, eps, out_dtype=act, mode=ops.LN_WINDOW, grid=(H, W), ws=ws, shift=shift)
         qkv = ops.linear(xn1, pk["wqkv"], pk["bqkv"], out_dtype=act, impl=impl)
         att = ops.window_attention(qkv, pk["bias"], B, H, W, heads, ws, shift, bias_log2=pk["bias_log2"])
-        x1 = ops.linear(att, pk["wo"], bo, resid=x, out_dtype=torch.float32, scatter=(H, W, ws, shift), impl=impl)
+        if keep_scale is None:
+            x1 = ops.linear(att, pk["wo"], bo, resid=x, out_dtype=torch.float32, scatter=(H, W, ws, shift), impl=impl)
+        else:   # hidden = shortcut + drop_path(attention_output): whole samples dropped, the kept ones scaled by 1 / keep (HF:646)
+            y = ops.linear(att, pk["wo"], bo, out_dtype=torch.float32, scatter=(H, W, ws, shift), impl=impl)
+            x1 = ops.row_scale_add(x, y, keep_scale, H * W)
+            del y
+        ctx.keep_scale = keep_scale
         xn2 = ops.layernorm(x1, ln2w, ln2b, eps, out_dtype=act)
         h = ops.linear(xn2, pk["w1"], b1, out_dtype=act, impl=impl)
         a = ops.eltwise(ops.EW_GELU_FWD, h)
@@ -81,7 +88,9 @@ class SwinBlockFn(Function):
         del dh
         g1, dln2w, dln2b = ops.layernorm_bwd(x1, dxn2, ln2w, eps, dres=g2, dgamma=zl2w, dbeta=zl2b)
         # attention half:  x1[token(r)] = x[token(r)] + proj(attn(qkv(LN1(x)[token(r)])))   (r = window-ordered row)
-        dbo, _, g1w = ops.col_reduce(g1, window=(H, W, ws, shift), copy_dtype=act, s1=zbo)
+        g1b = g1 if ctx.keep_scale is None else ops.row_scale_add(None, g1, ctx.keep_scale, H * W)      # the branch's share of dL/dx1
+        dbo, _, g1w = ops.col_reduce(g1b, window=(H, W, ws, shift), copy_dtype=act, s1=zbo)
+        del g1b
         dwo = ops.gemm_ex(g1w, True, att, True, out_dtype=f32, impl=impl)
         datt = ops.gemm_ex(g1w, False, pk["wo"], True, out_dtype=act, impl=impl)
         dqkv = torch.empty_like(qkv)

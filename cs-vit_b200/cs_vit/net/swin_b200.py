@@ -108,6 +108,7 @@ class SwinBackboneB200(nn.Module):
         self.config = config
         self.precision = precision
         self.fuse_attn = True  # csvit_swin_attn_fused for C in {128, 256}: LN + QKV + window attention in one tcgen05 kernel
+        self._drop_path_rand: List[torch.Tensor] = []   # test hook: the [B] uniform draws of the next stochastic-depth calls, in call order
         self.fuse_mlp = True   # csvit_mlp_fused for C in {128, 256}: hidden activations never leave the SM
         # Inference runs the batch through the whole backbone in chunks of this many images (0 = all at once).  Images are
         # independent, so the result is bit-identical; what changes is locality: a chunk's inter-kernel tensors (tens of MB)
@@ -251,13 +252,14 @@ class SwinBackboneB200(nn.Module):
         cfg = self.config
         if not images.is_cuda:
             raise RuntimeError("SwinBackboneB200 runs on CUDA tensors only (there is no CPU fallback)")
-        if self.training and cfg.drop_path_rate > 0:
-            raise NotImplementedError("stochastic depth is not built: use drop_path_rate=0 or eval mode")
         n, _, S, S2 = images.shape
         if S != S2 or S % (32 * cfg.window_size) != 0:
             raise ValueError(f"image side {S} must be a multiple of {32 * cfg.window_size} (no padding path, SURVEY.md §8b)")
-        if not return_stages and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            return self._forward_train(images, normalize)    # (return_stages is a diagnostic of the inference path)
+        wants_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+        if not return_stages and (wants_grad or (self.training and cfg.drop_path_rate > 0)):
+            # (return_stages is a diagnostic of the inference path; a train-mode forward with stochastic depth takes this path
+            # under no_grad too - HF drops paths whenever module.training is set)
+            return self._forward_train(images, normalize)
         with torch.no_grad():
             return self._forward_infer(images, normalize, return_stages)
 
@@ -293,14 +295,25 @@ class SwinBackboneB200(nn.Module):
         pe = self.embeddings.patch_embeddings.projection
         x = ag.PatchEmbedFn.apply(images.float().contiguous(), pe.weight, pe.bias, self.embeddings.norm.weight, self.embeddings.norm.bias,
                                   self._weight("pe_w", pe.weight), (normalize, eps, act, impl))
+        # stochastic depth (HF:353-377, 543, 646, 716): block k of the whole encoder drops its attention branch per sample with
+        # probability linspace(0, drop_path_rate, sum(depths))[k] in train mode
+        total_blocks = sum(cfg.depths)
+        rates = torch.linspace(0, cfg.drop_path_rate, total_blocks).tolist() if self.training and cfg.drop_path_rate > 0 else [0.0] * total_blocks
+        k = -1
         for s, stage in enumerate(self.encoder.layers):
             heads = cfg.num_heads[s]
             for i, blk in enumerate(stage.blocks):
+                k += 1
                 ws, shift = cfg.window_size, (0 if i % 2 == 0 else cfg.window_size // 2)
                 if min(H, W) <= ws:  # HF:548-554
                     ws, shift = min(H, W), 0
                 sa = blk.attention.self
-                pk = self._block_pack(blk, f"s{s}b{i}/", ws)
+                pk = dict(self._block_pack(blk, f"s{s}b{i}/", ws))
+                if rates[k] > 0.0:
+                    keep = 1.0 - rates[k]
+                    # the uniform draw HF makes per call (torch.rand((B,1,1))); tests pin it to the reference's draws
+                    u = self._drop_path_rand.pop(0).to(x.device, torch.float32) if self._drop_path_rand else torch.rand(n, device=x.device)
+                    pk["keep_scale"] = (torch.floor(keep + u) / keep).contiguous()
                 x = ag.SwinBlockFn.apply(
                     x, blk.layernorm_before.weight, blk.layernorm_before.bias, sa.query.weight, sa.query.bias, sa.key.weight,
                     sa.key.bias, sa.value.weight, sa.value.bias, sa.relative_position_bias_table, blk.attention.output.dense.weight,

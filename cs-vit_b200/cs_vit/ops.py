@@ -459,6 +459,19 @@ def col_reduce(a: torch.Tensor, mode: int = CR_SUM, *, b: Optional[torch.Tensor]
     return s1, s2, copy
 
 
+def row_scale_add(x: Optional[torch.Tensor], y: torch.Tensor, s: torch.Tensor, group_rows: int) -> torch.Tensor:
+    """``x + s[row // group_rows] * y`` (``x`` may be None) on dense fp32 ``[rows, C]`` tensors (``csvit_row_scale_add``)."""
+    _dev(x, y, s)
+    rows, C = y.shape
+    if y.dtype != torch.float32 or not y.is_contiguous() or (x is not None and (x.dtype != torch.float32 or x.shape != y.shape or not x.is_contiguous())):
+        raise ValueError("row_scale_add: dense float32 operands of one shape")
+    if s.dtype != torch.float32 or not s.is_contiguous() or s.numel() * group_rows != rows:
+        raise ValueError("row_scale_add: s must be contiguous float32 with rows / group_rows entries")
+    out = torch.empty_like(y)
+    _call("csvit_row_scale_add", _p(x), y.data_ptr(), s.data_ptr(), out.data_ptr(), rows, C, group_rows, _stream())
+    return out
+
+
 def eltwise(op: int, a: torch.Tensor, b: Optional[torch.Tensor] = None) -> torch.Tensor:
     _dev(a, b)
     if not a.is_contiguous() or (b is not None and (not b.is_contiguous() or b.dtype != a.dtype or b.shape != a.shape)):

@@ -259,6 +259,11 @@ int csvit_transpose_f32(const float* src, long long lds, float* dst, long long l
   return launch_transpose_f32(src, lds, dst, ldd, rows, cols, S(stream));
 }
 
+int csvit_row_scale_add(const float* x, const float* y, const float* s, float* out, long long rows, int C, int group_rows, void* stream) {
+  CSVIT_REQUIRE(y && s && out, "row_scale_add: null operand");
+  return launch_row_scale_add(x, y, s, out, rows, C, group_rows, S(stream));
+}
+
 int csvit_eltwise(int op, const void* a, const void* b, void* out, int dtype, long long n, void* stream) {
   CSVIT_REQUIRE(ok_dtype(dtype), "eltwise: bad dtype %d", dtype);
   return launch_eltwise(op, a, b, out, dtype, n, S(stream));

@@ -178,6 +178,34 @@ eltwise_kernel(int op, const T* __restrict__ a, const T* __restrict__ b, T* __re
   }
 }
 
+// out[r, :] = (x ? x[r, :] : 0) + s[r / group_rows] * y[r, :]   (fp32, C a multiple of 4): the per-sample stochastic-depth
+// scale of the attention branch, forward (x = shortcut) and backward (x = nullptr: the branch's share of the gradient).
+__global__ void __launch_bounds__(256)
+row_scale_add_kernel(const float4* __restrict__ x, const float4* __restrict__ y, const float* __restrict__ s, float4* __restrict__ out,
+                     long long n4, int c4, int group_rows) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float k = s[(i / c4) / group_rows];
+    const float4 b = y[i];
+    float4 a = x ? x[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    a.x = fmaf(k, b.x, a.x); a.y = fmaf(k, b.y, a.y); a.z = fmaf(k, b.z, a.z); a.w = fmaf(k, b.w, a.w);
+    out[i] = a;
+  }
+}
+
+int launch_row_scale_add(const float* x, const float* y, const float* s, float* out, long long rows, int C, int group_rows,
+                         cudaStream_t stream) {
+  CSVIT_REQUIRE(C > 0 && C % 4 == 0 && group_rows > 0 && rows % group_rows == 0, "row_scale_add: C=%d rows=%lld group=%d", C, rows, group_rows);
+  const long long n4 = rows * (C / 4);
+  if (n4 == 0) return 0;
+  long long blocks = (n4 + 255) / 256;
+  if (blocks > 148ll * 16) blocks = 148ll * 16;
+  row_scale_add_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(reinterpret_cast<const float4*>(x), reinterpret_cast<const float4*>(y), s,
+                                                                     reinterpret_cast<float4*>(out), n4, C / 4, group_rows);
+  CSVIT_CUDA(cudaGetLastError());
+  return 0;
+}
+
 int launch_eltwise(int op, const void* a, const void* b, void* out, int dtype, long long n, cudaStream_t stream) {
   CSVIT_REQUIRE(op >= EW_GELU_FWD && op <= EW_RELU_BWD, "eltwise: bad op %d", op);
   CSVIT_REQUIRE(n % 4 == 0, "eltwise: element count %lld must be a multiple of 4", n);

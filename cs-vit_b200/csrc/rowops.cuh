@@ -53,6 +53,8 @@ int launch_col_reduce(const void* a, int a_dtype, long long lda, const float* b,
                       int rows, int C, int row_mode, const WinGeom& g, void* copy, int copy_dtype, long long ldc, float* s1,
                       float* s2, cudaStream_t stream);
 int launch_transpose_f32(const float* src, long long lds, float* dst, long long ldd, int R, int C, cudaStream_t stream);
+int launch_row_scale_add(const float* x, const float* y, const float* s, float* out, long long rows, int C, int group_rows,
+                         cudaStream_t stream);
 int launch_eltwise(int op, const void* a, const void* b, void* out, int dtype, long long n, cudaStream_t stream);
 int launch_affine2_rows(const float* dy, const float* x, const float* a, const float* b, const float* c0, const float* resid,
                         float* out, long long rows, int C, cudaStream_t stream);

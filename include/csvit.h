@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define CSVIT_ABI_VERSION 7
+#define CSVIT_ABI_VERSION 8
 
 #if defined(__GNUC__)
 #define CSVIT_API __attribute__((visibility("default")))
@@ -241,6 +241,12 @@ enum { CSVIT_CR_SUM = 0, CSVIT_CR_CENTERED = 1, CSVIT_CR_DOT = 2 };
 CSVIT_API int csvit_col_reduce(const void* a, int a_dtype, long long lda, const float* b, long long ldb, const float* center,
                                int mode, int rows, int C, int row_mode, int H, int W, int ws, int shift, void* copy,
                                int copy_dtype, long long ldc, float* s1, float* s2, void* stream);
+
+/* out[r, :] = (x ? x[r, :] : 0) + s[r / group_rows] * y[r, :] on dense fp32 [rows, C] tensors (C % 4 == 0): stochastic depth of the
+ * attention branch in train mode - shortcut + drop_path(attention_output), s[b] = floor(keep + U[0,1)) / keep per sample
+ * (HF:swin/modeling_swin.py:353-366, 646); with x = NULL the same scale applied to the incoming gradient in the backward pass. */
+CSVIT_API int csvit_row_scale_add(const float* x, const float* y, const float* s, float* out, long long rows, int C, int group_rows,
+                                  void* stream);
 
 /* Elementwise, n elements (multiple of 4) of `dtype`:  GELU_FWD out = gelu(a) (exact erf, nn.GELU / HF "gelu");
  * GELU_BWD out = a * gelu'(b) (a = dY, b = pre-activation);  RELU_BWD out = b > 0 ? a : 0 (b = forward output). */

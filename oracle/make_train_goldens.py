@@ -169,6 +169,70 @@ def pass_reference(workdir: str) -> None:
         summary[name] = {"variant": variant, "kwargs": dict(spatial_layer_type="encoder", persp_decorate="patch"), "phase": "spatial",
                          "batch": B, "frames": 1, "loss": float(gold["loss"]), "params": len(names), "global_grad_norm": total,
                          "linear_loss_seed": 5}
+    # ---- the same, with stochastic depth (drop_path_rate 0.1, HF's default and what the reference trains with): HF's own
+    # SwinDropPath modules configured as HF's constructor would (HF:swin/modeling_swin.py:543, 716), with the uniform draws of
+    # drop_path() (HF:362 torch.rand) served from a seeded queue and recorded, so that the product can replay the same masks.
+    from transformers.models.swin import modeling_swin as hf_swin
+    for name, variant, B, rate in (("train_backbone_swint_linear_droppath", "swin_t", 4, 0.1),):
+        sd = torch.load(os.path.join(workdir, "train_swint_encoder_patch_spatial.sd.pt"))
+        m = ref_poser.Poser(backbone=os.path.join(workdir, variant), image_size=224, num_latent_layer=None,
+                            spatial_layer_type="encoder", persp_decorate="patch")
+        m.load_state_dict(sd, strict=True)
+        m.phase(ref_poser.Poser.TrainingPhase.SPATIAL)
+        layers = [blk for stage in m.backbone.encoder.layers for blk in stage.blocks]
+        dpr = [x.item() for x in torch.linspace(0, rate, len(layers), device="cpu")]              # HF:716
+        for blk, p_drop in zip(layers, dpr):
+            blk.drop_path = hf_swin.SwinDropPath(p_drop) if p_drop > 0.0 else torch.nn.Identity()    # HF:543
+        m.backbone.train()
+        batch = synth.make_inputs(B, 1, 224, seed=11)
+        imgs = batch["patches"].reshape(B, 3, 224, 224)
+        active = [p_drop for p_drop in dpr if p_drop > 0.0]
+
+        def dropped(seed):      # samples dropped over the whole forward with this seed
+            g_ = torch.Generator().manual_seed(seed)
+            return sum(int((torch.floor(1 - p_drop + torch.rand(B, generator=g_)) == 0).sum()) for p_drop in active)
+
+        seed = next(s_ for s_ in range(77, 500) if dropped(s_) >= 3)      # first seed that exercises the drop branch a few times
+        draws, gen, real_rand = [], torch.Generator().manual_seed(seed), torch.rand
+
+        def seeded_rand(*size, **kw):
+            shape = tuple(size[0]) if len(size) == 1 and isinstance(size[0], (tuple, list, torch.Size)) else tuple(size)
+            assert shape == (B, 1, 1), shape          # only drop_path draws random numbers in this forward
+            u = real_rand(B, generator=gen)
+            draws.append(u.clone())
+            return u.reshape(shape).to(kw.get("dtype", torch.float32))
+
+        torch.rand = seeded_rand
+        try:
+            feats = m.backbone(m.image_preprocessor(imgs)).last_hidden_state
+        finally:
+            torch.rand = real_rand
+        assert len(draws) == sum(1 for p_drop in dpr if p_drop > 0.0)
+        assert sum(int((torch.floor(1 - p_drop + u) == 0).sum()) for p_drop, u in zip(active, draws)) >= 3
+        R = torch.randn(feats.shape, generator=torch.Generator().manual_seed(5))
+        (feats * R).sum().backward()
+        gold = {"features": feats.detach().numpy().astype(np.float32), "loss": np.array((feats * R).sum().item(), dtype=np.float64),
+                "droppath_rand": torch.stack(draws).numpy().astype(np.float32)}
+        names, norms, projs = [], [], []
+        for pname, p in m.backbone.named_parameters():
+            names.append(pname)
+            g = p.grad.detach().float()
+            norms.append(g.double().norm().item())
+            projs.append(projections(g, pname))
+            if g.numel() <= FULL_GRAD_MAX:
+                gold["grad/" + pname] = g.numpy().astype(np.float32)
+        gold["param_names"] = np.array(names)
+        gold["param_has_grad"] = np.ones(len(names), dtype=bool)
+        gold["grad_norm"] = np.array(norms, dtype=np.float64)
+        gold["grad_proj"] = np.stack(projs).astype(np.float64)
+        gold["state_checksum"] = np.array(state_checksum(sd))
+        gold["input_checksum"] = np.array(state_checksum(batch))
+        np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), **gold)
+        total = float(np.sqrt((gold["grad_norm"] ** 2).sum()))
+        print(f"[reference] {name}: {len(names)} backbone parameters, global grad norm {total:.4e}, {len(draws)} drop-path draws")
+        summary[name] = {"variant": variant, "kwargs": dict(spatial_layer_type="encoder", persp_decorate="patch"), "phase": "spatial",
+                         "batch": B, "frames": 1, "loss": float(gold["loss"]), "params": len(names), "global_grad_norm": total,
+                         "linear_loss_seed": 5, "drop_path_rate": rate, "drop_path_seed": seed}
     with open(os.path.join(GOLDEN, "TRAIN_MANIFEST.json"), "w") as f:
         json.dump({"generator": "oracle/make_train_goldens.py", "torch": torch.__version__,
                    "transformers": __import__("transformers").__version__, "input_seed": 11, "weight_seed": 0,

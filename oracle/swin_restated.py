@@ -105,8 +105,18 @@ def window_self_attention(xw: Tensor, sd: Dict[str, Tensor], p: str, heads: int,
     return _lin(ctx, sd, p + ".output.dense")                                           # HF:479-483
 
 
-def swin_layer(x: Tensor, sd: Dict[str, Tensor], p: str, H: int, W: int, heads: int, ws: int, shift: int, eps: float) -> Tensor:
-    """One SwinLayer on x [B, H*W, C]   (HF:591-653).  H, W must be multiples of ws (no padding path)."""
+def drop_path(x: Tensor, drop_prob: float, u: Tensor) -> Tensor:
+    """Stochastic depth per sample with the uniform draw ``u [B]`` made explicit   (HF:353-366: ``floor(keep + rand)``, kept
+    samples divided by ``keep``)."""
+    keep = 1.0 - drop_prob
+    mask = torch.floor(keep + u.to(x.dtype)).reshape((x.shape[0],) + (1,) * (x.dim() - 1))
+    return x.div(keep) * mask
+
+
+def swin_layer(x: Tensor, sd: Dict[str, Tensor], p: str, H: int, W: int, heads: int, ws: int, shift: int, eps: float,
+               drop_prob: float = 0.0, drop_u=None) -> Tensor:
+    """One SwinLayer on x [B, H*W, C]   (HF:591-653).  H, W must be multiples of ws (no padding path).  ``drop_prob > 0`` with the
+    draw ``drop_u [B]``: train-mode stochastic depth of the attention branch (HF:543, 646)."""
     B, N, C = x.shape
     if min(H, W) <= ws:                                   # HF:548-554 set_shift_and_window_size
         shift, ws = 0, min(H, W)
@@ -120,7 +130,10 @@ def swin_layer(x: Tensor, sd: Dict[str, Tensor], p: str, H: int, W: int, heads: 
     h = window_reverse(a.reshape(-1, ws, ws, C), ws, H, W)
     if shift > 0:
         h = torch.roll(h, shifts=(shift, shift), dims=(1, 2))
-    x = shortcut + h.reshape(B, N, C)                                                    # HF:646
+    branch = h.reshape(B, N, C)
+    if drop_prob > 0.0:
+        branch = drop_path(branch, drop_prob, drop_u)
+    x = shortcut + branch                                                                # HF:646
     y = _ln(x, sd, p + ".layernorm_after", eps)
     y = F.gelu(_lin(y, sd, p + ".intermediate.dense"))                                   # exact erf, HF:510-519
     return x + _lin(y, sd, p + ".output.dense")                                          # HF:650
@@ -143,8 +156,12 @@ def patch_embed(pixels: Tensor, sd: Dict[str, Tensor], eps: float) -> Tensor:
 
 
 def swin_forward(pixels: Tensor, sd: Dict[str, Tensor], depths: Sequence[int], heads: Sequence[int], ws: int = 7,
-                 eps: float = 1e-5, return_stages: bool = False):
-    """``SwinModel.forward(...).last_hidden_state``   (HF:847-899, 734-794, 683-708)."""
+                 eps: float = 1e-5, return_stages: bool = False, drop_path_rate: float = 0.0, drop_draws=None):
+    """``SwinModel.forward(...).last_hidden_state``   (HF:847-899, 734-794, 683-708).  ``drop_path_rate > 0`` = train mode with
+    stochastic depth: block k uses ``linspace(0, rate, sum(depths))[k]`` (HF:716) and the next row of ``drop_draws [n, B]``."""
+    rates = torch.linspace(0, drop_path_rate, sum(depths)).tolist()
+    draws = list(drop_draws) if drop_draws is not None else []
+    k = -1
     S = pixels.shape[-1]
     H = W = S // 4
     x = patch_embed(pixels, sd, eps)
@@ -152,7 +169,10 @@ def swin_forward(pixels: Tensor, sd: Dict[str, Tensor], depths: Sequence[int], h
     for s, (depth, h) in enumerate(zip(depths, heads)):
         for i in range(depth):
             shift = 0 if i % 2 == 0 else ws // 2                                        # HF:672-680
-            x = swin_layer(x, sd, f"encoder.layers.{s}.blocks.{i}", H, W, h, ws, shift, eps)
+            k += 1
+            p_drop = rates[k] if drop_path_rate > 0.0 else 0.0
+            x = swin_layer(x, sd, f"encoder.layers.{s}.blocks.{i}", H, W, h, ws, shift, eps, p_drop,
+                           draws.pop(0) if p_drop > 0.0 else None)
         stage_out.append(x)
         if s < len(depths) - 1:
             x = patch_merging(x, sd, f"encoder.layers.{s}.downsample", H, W, eps)

@@ -108,3 +108,36 @@ def test_rotation_tail_backward_is_finite_at_clamped_entries():
     d6 = torch.tensor([[1.0, 0.0, 0.0, 0.0, 1.0, 0.0], [0.3, -0.2, 0.9, 0.1, 0.8, -0.5]], requires_grad=True)
     matrix_to_axis_angle(rotation_6d_to_matrix(d6)).sum().backward()
     assert torch.isfinite(d6.grad).all()
+
+
+def test_restated_stochastic_depth_matches_reference_autograd():
+    """Train-mode Swin-T backbone with drop_path_rate 0.1 under the reference's recorded uniform draws: features and gradients of
+    the restatement's autograd against the golden the unmodified HF modules produced (oracle/make_train_goldens.py)."""
+    import numpy as np
+    from helpers import GOLDEN, build_train_case
+    from oracle import head_restated as head
+    from oracle import swin_restated as swin
+    model, batch, gold, case = build_train_case("train_backbone_swint_linear_droppath", "fp32")
+    assert case["drop_path_rate"] == 0.1
+    bsd = {k[len("backbone."):]: v.detach().clone().requires_grad_(True) for k, v in model.state_dict().items()
+           if k.startswith("backbone.") and v.is_floating_point()}
+    imgs = batch["patches"].reshape(case["batch"], 3, 224, 224)
+    mean = torch.tensor(head.IMAGENET_MEAN)[None, :, None, None]
+    std = torch.tensor(head.IMAGENET_STD)[None, :, None, None]
+    from cs_vit.synthetic import SWIN_VARIANTS
+    _, depths, heads = SWIN_VARIANTS[case["variant"]]
+    feats = swin.swin_forward((imgs - mean) / std, bsd, depths, heads, drop_path_rate=0.1, drop_draws=torch.from_numpy(gold["droppath_rand"]))
+    ref = torch.from_numpy(gold["features"])
+    assert ((feats.detach() - ref).norm() / ref.norm()).item() < 1e-5
+    # the dropped samples make this differ from the plain forward: the masks really act
+    plain = np.load(os.path.join(GOLDEN, "train_backbone_swint_linear.npz"))["features"]
+    assert np.abs(plain - gold["features"]).max() > 1e-2
+    R = torch.randn(feats.shape, generator=torch.Generator().manual_seed(case["linear_loss_seed"]))
+    (feats * R).sum().backward()
+    checked = 0
+    for key in gold:
+        if key.startswith("grad/"):
+            g, want = bsd[key[5:]].grad, torch.from_numpy(gold[key])
+            assert ((g - want).norm() / want.norm().clamp_min(1e-12)).item() < 2e-4, key
+            checked += 1
+    assert checked > 100

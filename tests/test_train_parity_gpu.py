@@ -125,6 +125,36 @@ def test_backbone_backward_linear_loss(precision, tol_feat, tol_param, tol_globa
     compare_grads(model.backbone, gold, tol_param=tol_param, tol_global=tol_global)
 
 
+@pytest.mark.parametrize("precision,tol_feat,tol_param,tol_global", [("fp32", 1e-4, 2e-3, 1e-3), ("fp16", 1e-2, 2e-2, 1e-2)])
+def test_backbone_backward_with_stochastic_depth(precision, tol_feat, tol_param, tol_global):
+    """drop_path_rate = 0.1 (HF's default, what the reference trains with, ref:cs_vit/net/ti_poser.py:342 backbone.train()):
+    forward + backward of the train path with the reference's recorded per-sample draws against the unmodified HF modules'
+    autograd (HF:swin/modeling_swin.py:353-377, 646)."""
+    model, batch, gold, case = build_train_case("train_backbone_swint_linear_droppath", precision)
+    model = model.cuda()
+    model.backbone.config.drop_path_rate = case["drop_path_rate"]
+    assert model.backbone.training
+    model.backbone._drop_path_rand = [torch.from_numpy(u) for u in gold["droppath_rand"]]
+    imgs = batch["patches"].reshape(case["batch"], 3, 224, 224).cuda()
+    feats = model.backbone.forward_features(imgs, normalize=True)
+    assert not model.backbone._drop_path_rand, "every recorded draw must have been consumed"
+    ref = torch.from_numpy(gold["features"]).double()
+    assert ((feats.detach().double().cpu() - ref).norm() / ref.norm()).item() < tol_feat
+    R = torch.randn(feats.shape, generator=torch.Generator().manual_seed(case["linear_loss_seed"])).cuda()
+    (feats * R).sum().backward()
+    torch.cuda.synchronize()
+    compare_grads(model.backbone, gold, tol_param=tol_param, tol_global=tol_global)
+    # without the hook the draws come from torch.rand on the device: still a valid train step, and eval mode ignores the rate
+    feats2 = model.backbone.forward_features(imgs, normalize=True)
+    assert torch.isfinite(feats2).all()
+    model.backbone.eval()
+    with torch.no_grad():
+        a = model.backbone.forward_features(imgs, normalize=True)
+        model.backbone.config.drop_path_rate = 0.0
+        b = model.backbone.forward_features(imgs, normalize=True)
+    assert torch.equal(a, b)
+
+
 @pytest.mark.parametrize("precision,tol_loss,tol_global", [("bf16", 2e-3, 0.25), ("fp16", 1e-3, 0.2)])
 def test_finetune_step_16bit(precision, tol_loss, tol_global):
     model, predict, loss, parts, gold = run_step("train_swint_encoder_patch_spatial", precision)

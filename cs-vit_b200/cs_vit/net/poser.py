@@ -326,7 +326,10 @@ class Poser(nn.Module):
             pose_tok, shape_tok, root_tok = tokens[:, :, 0], tokens[:, :, 1], tokens[:, :, 2]
         pose_6d = self._linear_head(self.pose_decoder, pose_tok)
         pose_6d = pose_6d.reshape(*pose_6d.shape[:2], self.num_pose_query, 6)
-        pose_aa = matrix_to_axis_angle(rotation_6d_to_matrix(pose_6d))
+        if torch.is_grad_enabled() and pose_6d.requires_grad:
+            pose_aa = matrix_to_axis_angle(rotation_6d_to_matrix(pose_6d))        # differentiable torch form (training step)
+        else:
+            pose_aa = ops.rot6d_to_axis_angle(pose_6d)                             # one kernel (csrc/tail.cu)
         shape = self._linear_head(self.shape_decoder, shape_tok)
         root = self._linear_head(self.root_decoder, root_tok)
         if self.latent_trans is not None:      # rotate the transformed copy's predictions back (ref :537-557)
@@ -344,6 +347,15 @@ class Poser(nn.Module):
         """MANO forward kinematics, joint regression, de-normalisation to mm   (ref:cs_vit/net/ti_poser.py:561-607)."""
         B, T = pose_aa.shape[:2]
         flat_pose = pose_aa.reshape(B * T, -1)
+        fused = self._mano_fused_operands()
+        if fused is not None and not (torch.is_grad_enabled() and (pose_aa.requires_grad or shape.requires_grad or root_transl_norm.requires_grad)):
+            # inference: skinning, joint regression, bone length and de-normalisation in ONE kernel (csrc/tail.cu) instead of ~120
+            # elementwise / small-GEMM launches
+            layer, mode = fused
+            joint_cam, verts_cam, root_transl = ops.mano_fk(
+                flat_pose.contiguous().float(), shape.reshape(B * T, -1).contiguous().float(), root_transl_norm.reshape(B * T, 3).contiguous().float(),
+                layer, self._w_jreg(), TARGET_JOINTS_CONNECTION, rodrigues_mode=mode)
+            return joint_cam.view(B, T, -1, 3), verts_cam.view(B, T, -1, 3), root_transl.view(B, T, 3)
         mano = self.rmano_layer(betas=shape.reshape(B * T, -1), global_orient=flat_pose[:, :3], hand_pose=flat_pose[:, 3:],
                                 transl=torch.zeros(B * T, 3, device=pose_aa.device))
         verts = mano.vertices
@@ -353,6 +365,35 @@ class Poser(nn.Module):
         verts_cam = ((verts - joints[:, :1]) * 1e3).reshape(B, T, -1, 3) + root_transl[:, :, None]
         joint_cam = ((joints - joints[:, :1]) * 1e3).reshape(B, T, -1, 3) + root_transl[:, :, None]
         return joint_cam, verts_cam, root_transl
+
+    def _w_jreg(self) -> torch.Tensor:
+        j = self.J_regressor_mano
+        return j if (j.dtype == torch.float32 and j.is_contiguous()) else j.float().contiguous()
+
+    def _mano_fused_operands(self):
+        """Buffers of the MANO layer for ``ops.mano_fk`` and its Rodrigues form, or None when the layer is not one this kernel
+        restates.  The seeded stand-in is verified against its own torch forward on the GPU (tests/test_tail_gpu.py).  A real
+        ``smplx`` MANO layer (use_pca=False) is standard LBS as well and is accepted only when ``self.fused_mano_smplx`` is set:
+        its path (posedirs, hand-pose mean, smplx's Rodrigues epsilon) follows the published ``smplx.lbs`` but cannot be pinned
+        here - smplx and the licensed MANO files are not in this image."""
+        layer = self.rmano_layer
+        from ..utils.mano_standin import SyntheticMANO
+        if isinstance(layer, SyntheticMANO):
+            mode, names = 0, {}
+        elif getattr(self, "fused_mano_smplx", False) and all(hasattr(layer, a) for a in ("v_template", "shapedirs", "posedirs", "J_regressor", "lbs_weights", "parents")):
+            mode, names = 1, {"posedirs": layer.posedirs}
+            if not getattr(layer, "flat_hand_mean", True) and hasattr(layer, "hand_mean"):
+                names["pose_mean"] = layer.hand_mean
+        else:
+            return None
+        key = (id(layer), str(layer.v_template.device))
+        if getattr(self, "_mano_pack_key", None) != key:
+            f32 = lambda t: t.detach().float().contiguous()        # noqa: E731
+            parents = [int(x) for x in (layer.parents.tolist() if torch.is_tensor(layer.parents) else layer.parents)]
+            self._mano_pack = {"v_template": f32(layer.v_template), "shapedirs": f32(layer.shapedirs), "j_regressor": f32(layer.J_regressor),
+                               "lbs_weights": f32(layer.lbs_weights), "parents": [-1] + parents[1:], **{k: f32(v) for k, v in names.items()}}
+            self._mano_pack_key = key
+        return self._mano_pack, mode
 
     def _sample_persp_dir_vec(self, num_sample: int, bbox: torch.Tensor, focal: torch.Tensor, princpt: torch.Tensor):
         """Unit-ray (x, y) components on a grid over the box, ``[B,T,p,p,2]``   (ref:cs_vit/net/ti_poser.py:609-639)."""

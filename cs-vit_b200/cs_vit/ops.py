@@ -574,6 +574,46 @@ def set_gemm_tuning(cluster: int = 0, tma_store: int = -1, max_ctas: int = 0, pa
     _lib.check(_lib.load().csvit_set_gemm_tuning(cluster, tma_store, max_ctas, pair))
 
 
+# ---------------------------------------------------------------------------------------------- fp32 tail
+def rot6d_to_axis_angle(d6: torch.Tensor) -> torch.Tensor:
+    """``[..., 6]`` 6D rotations -> ``[..., 3]`` axis-angle (``csvit_rot6d_to_axis_angle``): ``matrix_to_axis_angle(
+    rotation_6d_to_matrix(d6))`` of cs_vit.utils.geometry in one kernel."""
+    _dev(d6)
+    if d6.dtype != torch.float32 or d6.shape[-1] != 6:
+        raise ValueError("rot6d_to_axis_angle: float32 [..., 6]")
+    d6 = d6.contiguous()
+    out = torch.empty(d6.shape[:-1] + (3,), dtype=torch.float32, device=d6.device)
+    _call("csvit_rot6d_to_axis_angle", d6.data_ptr(), out.data_ptr(), d6.numel() // 6, _stream())
+    return out
+
+
+def mano_fk(pose: torch.Tensor, betas: torch.Tensor, root_norm: torch.Tensor, layer: dict, j_out: torch.Tensor, edges, rodrigues_mode: int = 0):
+    """``Poser._pose_fk`` in one kernel (``csvit_mano_fk``).  ``pose [n,48]``, ``betas [n,10]``, ``root_norm [n,3]``;
+    ``layer``: contiguous fp32 device buffers ``v_template, shapedirs, j_regressor, lbs_weights`` (+ optional ``posedirs``,
+    ``pose_mean``) and the python list ``parents``; ``j_out [21,778]``; ``edges``: 20 joint pairs.
+    Returns ``(joint_cam [n,21,3], verts_cam [n,778,3], root_transl [n,3])`` in millimetres."""
+    import ctypes
+    need = [pose, betas, root_norm, layer["v_template"], layer["shapedirs"], layer["j_regressor"], layer["lbs_weights"], j_out]
+    _dev(*need, layer.get("posedirs"), layer.get("pose_mean"))
+    for t in need + [t for t in (layer.get("posedirs"), layer.get("pose_mean")) if t is not None]:
+        if t.dtype != torch.float32 or not t.is_contiguous():
+            raise ValueError("mano_fk: contiguous float32 operands only")
+    n = pose.shape[0]
+    if tuple(pose.shape) != (n, 48) or tuple(betas.shape) != (n, 10) or tuple(root_norm.shape) != (n, 3) or tuple(j_out.shape) != (21, 778) or \
+            tuple(layer["v_template"].shape) != (778, 3) or tuple(layer["shapedirs"].shape) != (778, 3, 10) or \
+            tuple(layer["j_regressor"].shape) != (16, 778) or tuple(layer["lbs_weights"].shape) != (778, 16) or len(edges) != 20:
+        raise ValueError("mano_fk: shape mismatch (MANO: 778 vertices, 16 joints, 10 betas; 21 output joints, 20 bones)")
+    parents = (ctypes.c_int * 16)(*[int(x) for x in layer["parents"]])
+    e40 = (ctypes.c_int * 40)(*[int(x) for ab in edges for x in ab])
+    joint_cam = torch.empty(n, 21, 3, dtype=torch.float32, device=pose.device)
+    verts_cam = torch.empty(n, 778, 3, dtype=torch.float32, device=pose.device)
+    root = torch.empty(n, 3, dtype=torch.float32, device=pose.device)
+    _call("csvit_mano_fk", pose.data_ptr(), betas.data_ptr(), root_norm.data_ptr(), layer["v_template"].data_ptr(), layer["shapedirs"].data_ptr(),
+          _p(layer.get("posedirs")), _p(layer.get("pose_mean")), layer["j_regressor"].data_ptr(), layer["lbs_weights"].data_ptr(), j_out.data_ptr(),
+          parents, e40, int(rodrigues_mode), joint_cam.data_ptr(), verts_cam.data_ptr(), root.data_ptr(), n, _stream())
+    return joint_cam, verts_cam, root
+
+
 # ---------------------------------------------------------------------------------------------- input pipeline
 def crop_resize(frames: torch.Tensor, boxes: torch.Tensor, size: int = 224, expansion_ratio: float = 0.0):
     """On-device hand crops (``csvit_crop_resize``): ``frames`` fp32 ``[N,3,H,W]`` in [0,1] or uint8 ``[N,H,W,3]``; ``boxes`` fp32

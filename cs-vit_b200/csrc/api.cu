@@ -189,6 +189,22 @@ int csvit_crop_resize(const void* frames, int frames_u8, int N, int H, int W, co
   return launch_crop_resize(frames, frames_u8, N, H, W, boxes, expansion_ratio, square_boxes_out, out, size, S(stream));
 }
 
+int csvit_rot6d_to_axis_angle(const float* d6, float* axis_angle, long long n, void* stream) {
+  CSVIT_REQUIRE(d6 && axis_angle, "rot6d_to_axis_angle: null operand");
+  return launch_rot6d_to_axis_angle(d6, axis_angle, n, S(stream));
+}
+
+int csvit_mano_fk(const float* pose, const float* betas, const float* root_norm, const float* v_template, const float* shapedirs,
+                  const float* posedirs, const float* pose_mean, const float* j_regressor, const float* lbs_weights,
+                  const float* j_regressor_out, const int* parents16, const int* edges40, int rodrigues_mode, float* joint_cam,
+                  float* verts_cam, float* root_transl, int n, void* stream) {
+  CSVIT_REQUIRE(pose && betas && root_norm && v_template && shapedirs && j_regressor && lbs_weights && j_regressor_out && parents16 &&
+                    edges40 && joint_cam && verts_cam && root_transl, "mano_fk: null operand");
+  CSVIT_REQUIRE(rodrigues_mode == 0 || rodrigues_mode == 1, "mano_fk: rodrigues_mode %d", rodrigues_mode);
+  return launch_mano_fk(pose, betas, root_norm, v_template, shapedirs, posedirs, pose_mean, j_regressor, lbs_weights, j_regressor_out,
+                        parents16, edges40, rodrigues_mode, joint_cam, verts_cam, root_transl, n, S(stream));
+}
+
 int csvit_allreduce_f32(const void* const* bufs, const void* const* flags, void* multicast, long long n, int rank, int world, float scale,
                         int ctas, void* stream) {
   CSVIT_REQUIRE(bufs && flags, "allreduce_f32: null pointer tables");

@@ -31,6 +31,13 @@ int launch_swin_attn_core(const void* qkv, long long ldq, const void* bias_log2,
 int launch_crop_resize(const void* frames, int frames_u8, int N, int H, int W, const float* boxes, float expansion, float* square_out,
                        float* out, int S, cudaStream_t stream);
 
+// tail.cu
+int launch_rot6d_to_axis_angle(const float* d6, float* aa, long long n, cudaStream_t stream);
+int launch_mano_fk(const float* pose, const float* betas, const float* root_norm, const float* v_template, const float* shapedirs,
+                   const float* posedirs, const float* pose_mean, const float* j_regressor, const float* lbs_weights, const float* j_out,
+                   const int* parents16, const int* edges40, int rodrigues_mode, float* joint_cam, float* verts_cam, float* root_transl,
+                   int n, cudaStream_t stream);
+
 // allreduce.cu
 int launch_allreduce_f32(void* const* bufs, void* const* flags, void* mc, long long n, int rank, int world, float scale, int ctas,
                          cudaStream_t stream);

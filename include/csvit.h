@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define CSVIT_ABI_VERSION 8
+#define CSVIT_ABI_VERSION 9
 
 #if defined(__GNUC__)
 #define CSVIT_API __attribute__((visibility("default")))
@@ -161,6 +161,25 @@ CSVIT_API int csvit_swin_attn_fused(const float* x, float eps, const void* wqkv_
  *                0: the kernel applies it to the logits */
 CSVIT_API int csvit_swin_attn_core(const void* qkv, long long ldq, const void* bias_log2, void* ctx, int dtype, int B, int H,
                                    int W, int C, int heads, int ws, int shift, int token_order, int q_prescaled, void* stream);
+
+/* ---- the fp32 tail of predict_batch (tail.cu) -------------------------------------------------------------------------------
+ * axis_angle[i] = matrix_to_axis_angle(rotation_6d_to_matrix(d6[i])) for n rotations (d6 [n,6], axis_angle [n,3]), with the
+ * reference's branch structure: Gram-Schmidt rows (b1, b2, b1 x b2), best-conditioned quaternion candidate with real part >= 0,
+ * sinc form of the half angle.   ref:cs_vit/utils/geometry.py:111-132, 150-223, 258-298; called at ref:cs_vit/net/ti_poser.py:529-534 */
+CSVIT_API int csvit_rot6d_to_axis_angle(const float* d6, float* axis_angle, long long n, void* stream);
+
+/* Poser._pose_fk in one kernel (one sample per CTA): MANO linear-blend skinning + J_regressor_mano + mean bone length +
+ * de-normalisation.   ref:cs_vit/net/ti_poser.py:561-607
+ *   pose [n,48] axis-angle (global orientation, 15 hand joints), betas [n,10], root_norm [n,3]
+ *   v_template [778,3], shapedirs [778,3,10], j_regressor [16,778], lbs_weights [778,16], parents16 (HOST, parent < child, root -1):
+ *   the buffers of the MANO layer; posedirs [135, 2334] and pose_mean [45] may be NULL (the stand-in has neither)
+ *   j_regressor_out [21,778] = Poser.J_regressor_mano; edges40 (HOST): the 20 (a, b) joint pairs of TARGET_JOINTS_CONNECTION
+ *   rodrigues_mode 0: theta = sqrt(|a|^2 + 1e-16) (cs_vit.utils.mano_standin); 1: theta = |a + 1e-8| (smplx batch_rodrigues)
+ *   out: joint_cam [n,21,3] and verts_cam [n,778,3] in mm, root-relative + root_transl [n,3] = root_norm * 1e3 * mean bone length */
+CSVIT_API int csvit_mano_fk(const float* pose, const float* betas, const float* root_norm, const float* v_template,
+                            const float* shapedirs, const float* posedirs, const float* pose_mean, const float* j_regressor,
+                            const float* lbs_weights, const float* j_regressor_out, const int* parents16, const int* edges40,
+                            int rodrigues_mode, float* joint_cam, float* verts_cam, float* root_transl, int n, void* stream);
 
 /* ---- data-parallel gradient allreduce over NVLink / NVSwitch peer memory (allreduce.cu) --------------------------------------
  * In-place fp32 SUM * scale of one flat bucket that lives at bufs[r] in the symmetric memory of every rank r (HOST arrays of

@@ -118,7 +118,7 @@ def test_eval_flow_on_the_shim_matches_predict_batch(tmp_path, phase, T):
     model = Poser(backbone_dir("swin_t"), image_size=224, mano_layer=SyntheticMANO(), spatial_layer_type="encoder", persp_decorate="patch",
                   temporal_supervision="realtime" if phase == "temporal" else "full", temporal_init_method="random", precision="fp16")
     randomize_head_(model)
-    model.phase(Poser.TrainingPhase("inference" if phase == "temporal" else "spatial"))
+    model.phase(Poser.TrainingPhase(phase))          # as ref:scripts/eval.py:150 does with cfg.phase
     created = not dist.is_initialized()
     if created:
         dist.init_process_group("nccl", init_method=f"file://{tmp_path}/pg", rank=0, world_size=1)

@@ -4,8 +4,9 @@ Every shipped CS-ViT configuration points ``backbone`` at a ``swinv2-*-patch4-wi
 (SURVEY.md §0.2); the reference loads it with ``AutoModel.from_pretrained`` (ref:cs_vit/net/ti_poser.py:246) and reads
 ``last_hidden_state`` (ref:cs_vit/net/ti_poser.py:426).  This module is that seam for ``model_type == "swinv2"``, with
 ``Swinv2Model``'s parameter names and shapes (V2: = transformers/models/swinv2/modeling_swinv2.py), so HF checkpoints and
-the reference's ``ckpt["merged"]`` (keys ``backbone.*``) load unchanged.  Inference path only (eval / frozen backbone);
-the differentiable path of the finetune step exists for Swin v1 and raises here.
+the reference's ``ckpt["merged"]`` (keys ``backbone.*``) load unchanged.  The inference path below is the tuned one; the
+differentiable path of the finetune step (``_forward_train``) is functional: kernel GEMMs / LayerNorm / GELU with kernel
+backwards, the cosine-attention core in torch.
 
 Per block (res-post-norm, V2:662-715) the forward issues, on ``libcsvit_sm100.so``:
 
@@ -134,6 +135,7 @@ class Swinv2BackboneB200(nn.Module):
         self.encoder = _holder(layers=nn.ModuleList(stages))
         self.layernorm = nn.LayerNorm(config.hidden_size, eps=eps)
         self._pack = PackCache()
+        self._drop_path_rand: List[torch.Tensor] = []   # test hook: the [B] uniform draws of the next stochastic-depth calls, in call order
 
     # ------------------------------------------------------------------------------------------ construction
     @classmethod
@@ -227,11 +229,90 @@ class Swinv2BackboneB200(nn.Module):
             res, ws, _ = cfg.stage_geometry(s)
             if res % ws != 0 or res % 2 != 0 and s + 1 < len(cfg.depths):
                 raise ValueError(f"stage {s}: {res}x{res} tokens not divisible by window {ws} (no padding path)")
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            raise NotImplementedError("the differentiable (finetune) path is built for Swin v1 backbones only; run the SwinV2 "
-                                      "backbone frozen / under torch.no_grad()")
+        wants_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+        if not return_stages and (wants_grad or (self.training and cfg.drop_path_rate > 0)):
+            return self._forward_train(images, normalize)
         with torch.no_grad():
             return self._forward_infer(images, normalize, return_stages)
+
+    # ------------------------------------------------------------------------------------------ training path
+    def _forward_train(self, images: torch.Tensor, normalize: bool) -> torch.Tensor:
+        """Differentiable forward of the finetune step (ref:scripts/finetune.py:211-227 with a swinv2 backbone, which is what every
+        shipped configuration uses).  Every Linear, LayerNorm and GELU runs on this library's kernels with kernel backwards
+        (cs_vit/autograd.py: TF32 tensor cores in the 16-bit modes, exact fp32 in the validation mode); the residual stream, the
+        window gather / scatter and stochastic depth are torch index / elementwise ops.  The scaled-cosine attention CORE
+        (normalise q and k, logit scale, continuous position bias, softmax, P V; V2:421-487) is plain differentiable torch code
+        here - batched matmuls on cuBLAS: the 256-token windows of this family are beyond the window-attention backward kernel
+        (64 keys), and a tcgen05 forward / backward pair for them is not built.  Matches HF's autograd on the gradient golden
+        (tests/test_swinv2_gpu.py); it is the functional path, not a tuned one."""
+        from .. import autograd as ag
+        cfg = self.config
+        n, _, S, _ = images.shape
+        impl = ops.GEMM_SIMT if self._fp32 else ops.GEMM_TC
+        eps = cfg.layer_norm_eps
+        dev = images.device
+        cols = ops.patch_im2col(images.float().contiguous(), out_dtype=torch.float32, normalize=normalize)
+        pe = self.embeddings.patch_embeddings.projection
+        x = ag.linear(cols, pe.weight.reshape(pe.weight.shape[0], -1), pe.bias, impl=impl)
+        x = ag.LayerNormFn.apply(x, self.embeddings.norm.weight, self.embeddings.norm.bias, eps)
+        total_blocks = sum(cfg.depths)
+        rates = torch.linspace(0, cfg.drop_path_rate, total_blocks).tolist() if self.training and cfg.drop_path_rate > 0 else [0.0] * total_blocks
+        k = -1
+
+        def drop_path(branch: torch.Tensor, rate: float, tokens: int) -> torch.Tensor:      # V2: both residual branches (V2:706, 710)
+            if rate <= 0.0:
+                return branch
+            keep = 1.0 - rate
+            u = self._drop_path_rand.pop(0).to(dev, torch.float32) if self._drop_path_rand else torch.rand(n, device=dev)
+            scale = torch.floor(keep + u) / keep
+            return (branch.view(n, tokens, -1) * scale[:, None, None]).view(-1, branch.shape[-1])
+
+        for s, stage in enumerate(self.encoder.layers):
+            heads = cfg.num_heads[s]
+            H, ws, stage_shift = cfg.stage_geometry(s)
+            N, L, nW = H * H, ws * ws, (H // ws) ** 2
+            C = x.shape[1]
+            rel_index = self._w(f"relidx{ws}", [], lambda: ops.rel_pos_index(ws, device=dev).long().reshape(-1))
+            coords = self._w(f"coords{ws}_{cfg.pretrained_window_sizes[s]}", [], lambda: relative_coords_table(ws, cfg.pretrained_window_sizes[s]).to(dev))
+            for i, blk in enumerate(stage.blocks):
+                k += 1
+                shift = stage_shift if i % 2 == 1 else 0
+                idx = self._w(f"widx{H}_{ws}_{shift}", [], lambda: ops.window_index_map(H, H, ws, shift, device=dev).long())
+                inv = self._w(f"winv{H}_{ws}_{shift}", [], lambda: torch.argsort(ops.window_index_map(H, H, ws, shift, device=dev).long()))
+                sa = blk.attention.self
+                xw = x.view(n, N, C)[:, idx].reshape(n * N, C)                     # roll(-s) + window_partition as one gather
+                q = ag.linear(xw, sa.query.weight, sa.query.bias, impl=impl)
+                kk = ag.linear(xw, sa.key.weight, None, impl=impl)
+                v = ag.linear(xw, sa.value.weight, sa.value.bias, impl=impl)
+                qh, kh, vh = (t.view(n * nW, L, heads, C // heads).transpose(1, 2) for t in (q, kk, v))
+                scores = torch.nn.functional.normalize(qh, dim=-1) @ torch.nn.functional.normalize(kh, dim=-1).transpose(-1, -2)
+                scores = scores * torch.clamp(sa.logit_scale, max=math.log(1.0 / 0.01)).exp()                         # V2:450-453
+                table = sa.continuous_position_bias_mlp(coords)                                                      # [(2ws-1)^2, heads]
+                bias = 16.0 * torch.sigmoid(table[rel_index].view(L, L, heads).permute(2, 0, 1))                     # V2:455-460
+                scores = scores + bias[None]
+                if shift > 0:      # HF adds the shift mask twice (V2:462-468)
+                    mask = self._w(f"mask{H}_{ws}_{shift}", [], lambda: ops.shift_mask(H, H, ws, shift, device=dev))
+                    scores = (scores.view(n, nW, heads, L, L) + 2.0 * mask[None, :, None]).view(n * nW, heads, L, L)
+                ctx = (scores.softmax(dim=-1) @ vh).transpose(1, 2).reshape(n * N, C)
+                proj = blk.attention.output.dense
+                ya = ag.linear(ctx.contiguous(), proj.weight, proj.bias, impl=impl)
+                ya = ya.view(n, N, C)[:, inv].reshape(n * N, C)                    # window_reverse + roll(+s)
+                ya = ag.LayerNormFn.apply(ya.contiguous(), blk.layernorm_before.weight, blk.layernorm_before.bias, eps)
+                x = x + drop_path(ya, rates[k], N)                                                                   # res-post-norm, V2:705-706
+                fc1, fc2 = blk.intermediate.dense, blk.output.dense
+                hid = ag.gelu(ag.linear(x, fc1.weight, fc1.bias, impl=impl))
+                z = ag.linear(hid, fc2.weight, fc2.bias, impl=impl)
+                z = ag.LayerNormFn.apply(z, blk.layernorm_after.weight, blk.layernorm_after.bias, eps)
+                x = x + drop_path(z, rates[k], N)                                                                    # V2:708-710
+            if hasattr(stage, "downsample"):
+                ds = stage.downsample
+                g4 = x.view(n, H, H, C)
+                cat = torch.cat([g4[:, 0::2, 0::2], g4[:, 1::2, 0::2], g4[:, 0::2, 1::2], g4[:, 1::2, 1::2]], dim=-1).reshape(-1, 4 * C)
+                x = ag.linear(cat.contiguous(), ds.reduction.weight, None, impl=impl)                                # V2: reduction, then norm
+                x = ag.LayerNormFn.apply(x, ds.norm.weight, ds.norm.bias, eps)
+        Hl = cfg.stage_geometry(len(cfg.depths) - 1)[0]
+        out = ag.LayerNormFn.apply(x, self.layernorm.weight, self.layernorm.bias, eps)
+        return out.view(n, Hl * Hl, cfg.hidden_size)
 
     def _forward_infer(self, images: torch.Tensor, normalize: bool, return_stages: bool):
         cfg = self.config

@@ -409,38 +409,41 @@ int launch_layernorm_bwd(const float* x, const void* dy, int dy_dtype, long long
 }
 
 // ----------------------------------------------------------------------------------------------------
-// Attention backward (<= 64 keys, head_dim 32)
+// Attention backward (<= 64 keys with a bias gradient: window attention; <= 128 keys without: the heads; head_dim 32)
 // ----------------------------------------------------------------------------------------------------
-constexpr int AB_MAX = 64;
+constexpr int AB_MAX = 128;       // longest sequence (MAXL = 128 instantiation: no bias-gradient accumulator, it would not fit)
 constexpr int AB_HD = 32;
 constexpr int AB_LD = 36;         // padded fp32 row of a 32-wide operand: 16-byte aligned rows, conflict-free LDS.128
-constexpr int AB_LDP = AB_MAX + 4;
 constexpr int AB_THREADS = 256;
-constexpr size_t AB_SMEM = sizeof(float) * (4 * AB_MAX * AB_LD + 2 * AB_MAX * AB_LDP + AB_MAX * AB_MAX + 2 * AB_MAX) + sizeof(int) * AB_MAX;
+template <int MAXL>
+constexpr size_t ab_smem() {
+  return sizeof(float) * (4 * MAXL * AB_LD + 2 * MAXL * (MAXL + 4) + (MAXL <= 64 ? MAXL * MAXL : 0) + 2 * MAXL) + sizeof(int) * MAXL;
+}
 
 // Forward (attention_simt_kernel): s_ij = scale q_i.k_j + bias[h,i,j] + mask_ij, p = softmax_j(s), o_i = sum_j p_ij v_j.
 // Backward: dp_ij = do_i.v_j, D_i = sum_j p_ij dp_ij, ds_ij = p_ij (dp_ij - D_i),
 //           dq_i = scale sum_j ds_ij k_j,  dk_j = scale sum_i ds_ij q_i,  dv_j = sum_i p_ij do_i,  dbias[h,i,j] += ds_ij.
 // CTA b works on head (b % heads) only, so the bias gradient accumulates in shared memory and reaches HBM once per CTA.
-template <typename T>
+template <typename T, int MAXL>
 __global__ void __launch_bounds__(AB_THREADS)
 attention_bwd_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __restrict__ v, const T* __restrict__ dout,
                      T* __restrict__ dq, T* __restrict__ dk, T* __restrict__ dv, long long ldq, long long ldk, long long ldv,
                      long long ldo, long long lddq, long long lddk, long long lddv, int n_seq, int Lq, int S, int heads, float scale,
                      const float* __restrict__ bias, float* __restrict__ dbias, WinGeom g, int nW) {
+  constexpr int AB_LDP = MAXL + 4, NH = MAXL / 32;
   extern __shared__ __align__(16) float sm[];
-  float* Qs = sm;                          // [AB_MAX][AB_LD]
-  float* Ks = Qs + AB_MAX * AB_LD;
-  float* Vs = Ks + AB_MAX * AB_LD;
-  float* Os = Vs + AB_MAX * AB_LD;         // dO
-  float* Ps = Os + AB_MAX * AB_LD;         // [AB_MAX][AB_LDP]
-  float* Ds = Ps + AB_MAX * AB_LDP;        // dS
-  float* Bacc = Ds + AB_MAX * AB_LDP;      // [Lq][S] bias-gradient accumulator
-  int* region = reinterpret_cast<int*>(Bacc + AB_MAX * AB_MAX);
+  float* Qs = sm;                          // [MAXL][AB_LD]
+  float* Ks = Qs + MAXL * AB_LD;
+  float* Vs = Ks + MAXL * AB_LD;
+  float* Os = Vs + MAXL * AB_LD;           // dO
+  float* Ps = Os + MAXL * AB_LD;           // [MAXL][AB_LDP]
+  float* Ds = Ps + MAXL * AB_LDP;          // dS
+  float* Bacc = Ds + MAXL * AB_LDP;        // [Lq][S] bias-gradient accumulator (MAXL <= 64 only)
+  int* region = reinterpret_cast<int*>(Bacc + (MAXL <= 64 ? MAXL * MAXL : 0));
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int h = blockIdx.x % heads;
   const int seq0 = blockIdx.x / heads, seq_step = gridDim.x / heads;
-  if (dbias) for (int i = tid; i < Lq * S; i += AB_THREADS) Bacc[i] = 0.f;
+  if (MAXL <= 64 && dbias) for (int i = tid; i < Lq * S; i += AB_THREADS) Bacc[i] = 0.f;
   for (int seq = seq0; seq < n_seq; seq += seq_step) {
     __syncthreads();
     for (int idx = tid; idx < S * (AB_HD / 4); idx += AB_THREADS) {
@@ -453,13 +456,13 @@ attention_bwd_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* 
       *reinterpret_cast<float4*>(Qs + r * AB_LD + d4) = ld4<T>(q + (static_cast<long long>(seq) * Lq + r) * ldq + h * AB_HD + d4);
       *reinterpret_cast<float4*>(Os + r * AB_LD + d4) = ld4<T>(dout + (static_cast<long long>(seq) * Lq + r) * ldo + h * AB_HD + d4);
     }
-    if (tid < AB_MAX) region[tid] = (g.shift > 0 && tid < S) ? win_region(g, seq % nW, tid) : 0;
+    if (tid < MAXL) region[tid] = (g.shift > 0 && tid < S) ? win_region(g, seq % nW, tid) : 0;
     __syncthreads();
-    // phase 1: one warp per query row, lane = key (two keys per lane)
+    // phase 1: one warp per query row, lane = key (NH keys per lane)
     for (int i = warp; i < Lq; i += AB_THREADS / 32) {
-      float sc[2], dp[2];
+      float sc[NH], dp[NH];
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
+      for (int half = 0; half < NH; ++half) {
         const int j = lane + 32 * half;
         float a = -INFINITY, b = 0.f;
         if (j < S) {
@@ -479,18 +482,24 @@ attention_bwd_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* 
         }
         sc[half] = a; dp[half] = b;
       }
-      const float mx = warp_max(fmaxf(sc[0], sc[1]));
-      const float e0 = lane < S ? expf(sc[0] - mx) : 0.f;
-      const float e1 = lane + 32 < S ? expf(sc[1] - mx) : 0.f;
-      const float inv = 1.0f / warp_sum(e0 + e1);
-      const float p0 = e0 * inv, p1 = e1 * inv;
-      const float D = warp_sum(p0 * dp[0] + p1 * dp[1]);
-      const float ds0 = p0 * (dp[0] - D), ds1 = p1 * (dp[1] - D);
-      Ps[i * AB_LDP + lane] = p0; Ps[i * AB_LDP + lane + 32] = p1;
-      Ds[i * AB_LDP + lane] = ds0; Ds[i * AB_LDP + lane + 32] = ds1;
-      if (dbias) {
-        if (lane < S) Bacc[i * S + lane] += ds0;
-        if (lane + 32 < S) Bacc[i * S + lane + 32] += ds1;
+      float mloc = sc[0];
+#pragma unroll
+      for (int half = 1; half < NH; ++half) mloc = fmaxf(mloc, sc[half]);
+      const float mx = warp_max(mloc);
+      float e[NH], esum = 0.f;
+#pragma unroll
+      for (int half = 0; half < NH; ++half) { e[half] = lane + 32 * half < S ? expf(sc[half] - mx) : 0.f; esum += e[half]; }
+      const float inv = 1.0f / warp_sum(esum);
+      float dloc = 0.f;
+#pragma unroll
+      for (int half = 0; half < NH; ++half) { e[half] *= inv; dloc = fmaf(e[half], dp[half], dloc); }
+      const float D = warp_sum(dloc);
+#pragma unroll
+      for (int half = 0; half < NH; ++half) {
+        const float ds = e[half] * (dp[half] - D);
+        Ps[i * AB_LDP + lane + 32 * half] = e[half];
+        Ds[i * AB_LDP + lane + 32 * half] = ds;
+        if (MAXL <= 64 && dbias && lane + 32 * half < S) Bacc[i * S + lane + 32 * half] += ds;
       }
     }
     __syncthreads();
@@ -522,16 +531,17 @@ attention_bwd_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* 
     }
   }
   __syncthreads();
-  if (dbias)
+  if (MAXL <= 64 && dbias)
     for (int i = tid; i < Lq * S; i += AB_THREADS) atomicAdd(dbias + static_cast<long long>(h) * Lq * S + i, Bacc[i]);
 }
 
-template <typename T>
+template <typename T, int MAXL>
 static int launch_ab_t(const void* q, const void* k, const void* v, const void* dout, void* dq, void* dk, void* dv, long long ldq,
                        long long ldk, long long ldv, long long ldo, long long lddq, long long lddk, long long lddv, int n_seq, int Lq,
                        int S, int heads, float scale, const float* bias, float* dbias, const WinGeom& g, int nW, cudaStream_t stream) {
   static DeviceOnce once;
-  auto kern = attention_bwd_kernel<T>;
+  auto kern = attention_bwd_kernel<T, MAXL>;
+  constexpr size_t AB_SMEM = ab_smem<MAXL>();
   if (once.first()) {
     CSVIT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(AB_SMEM)));
   }
@@ -555,11 +565,13 @@ int launch_attention_bwd(const void* q, const void* k, const void* v, const void
   WinGeom g = make_geom(mH > 0 ? mH : 1, mW > 0 ? mW : 1, mws > 0 ? mws : 1, mshift);
   const int nW = mshift > 0 ? (mH / mws) * (mW / mws) : 1;
   if (mshift > 0) CSVIT_REQUIRE(S == mws * mws && Lq == S, "attention_bwd: window mask needs Lq == S == ws^2");
-  if (dtype == DT_BF16)
-    return launch_ab_t<__nv_bfloat16>(q, k, v, dout, dq, dk, dv, ldq, ldk, ldv, ldo, lddq, lddk, lddv, n_seq, Lq, S, heads, scale, bias, dbias, g, nW, stream);
-  if (dtype == DT_F16)
-    return launch_ab_t<__half>(q, k, v, dout, dq, dk, dv, ldq, ldk, ldv, ldo, lddq, lddk, lddv, n_seq, Lq, S, heads, scale, bias, dbias, g, nW, stream);
-  return launch_ab_t<float>(q, k, v, dout, dq, dk, dv, ldq, ldk, ldv, ldo, lddq, lddk, lddv, n_seq, Lq, S, heads, scale, bias, dbias, g, nW, stream);
+  const bool wide = S > 64 || Lq > 64;
+  CSVIT_REQUIRE(!wide || dbias == nullptr, "attention_bwd: a bias gradient is built for sequences of <= 64 keys only (%d, %d)", Lq, S);
+#define CSVIT_AB_ARGS q, k, v, dout, dq, dk, dv, ldq, ldk, ldv, ldo, lddq, lddk, lddv, n_seq, Lq, S, heads, scale, bias, dbias, g, nW, stream
+  if (dtype == DT_BF16) return wide ? launch_ab_t<__nv_bfloat16, 128>(CSVIT_AB_ARGS) : launch_ab_t<__nv_bfloat16, 64>(CSVIT_AB_ARGS);
+  if (dtype == DT_F16) return wide ? launch_ab_t<__half, 128>(CSVIT_AB_ARGS) : launch_ab_t<__half, 64>(CSVIT_AB_ARGS);
+  return wide ? launch_ab_t<float, 128>(CSVIT_AB_ARGS) : launch_ab_t<float, 64>(CSVIT_AB_ARGS);
+#undef CSVIT_AB_ARGS
 }
 
 }  // namespace csvit

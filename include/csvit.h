@@ -285,7 +285,8 @@ CSVIT_API int csvit_layernorm_bwd(const float* x, const void* dy, int dy_dtype, 
 
 /* Backward of csvit_attention and of csvit_window_attention (pass q = qkv, k = qkv + C, v = qkv + 2C, pitches 3C,
  * n_seq = B*nW, Lq = S = ws*ws, scale = 1/sqrt(32), bias = csvit_expand_rel_bias table, mask_* = the window geometry;
- * mask_shift = 0 disables the shift mask).  Lq, S <= 64, head_dim 32, exact fp32 math, I/O in `dtype`.
+ * mask_shift = 0 disables the shift mask).  Lq, S <= 64 (<= 128 when dbias is NULL: the head attention over 3 + 64 tokens of a
+ * 256x256 SwinV2 input), head_dim 32, exact fp32 math, I/O in `dtype`.
  * dbias [heads, Lq, S] fp32 is accumulated (caller zeroes it); bias / dbias may be NULL. */
 CSVIT_API int csvit_attention_bwd(const void* q, const void* k, const void* v, const void* dout, void* dq, void* dk, void* dv,
                                   int dtype, long long ldq, long long ldk, long long ldv, long long ldo, long long lddq,

@@ -187,7 +187,7 @@ def _attn_ref(q, k, v, n, L, S, h, scale, bias=None, mask=None):
     return (torch.softmax(s, -1) @ vh).transpose(1, 2).reshape(n * L, h * 32)
 
 
-@pytest.mark.parametrize("L,S,heads,n", [(52, 52, 24, 5), (3, 49, 32, 7), (1, 8, 24, 33), (3, 3, 24, 4)])
+@pytest.mark.parametrize("L,S,heads,n", [(52, 52, 24, 5), (3, 49, 32, 7), (1, 8, 24, 33), (3, 3, 24, 4), (67, 67, 8, 3), (3, 128, 4, 2), (100, 65, 2, 2)])
 def test_attention_bwd_dense(ops, L, S, heads, n):
     g = torch.Generator(device="cuda").manual_seed(L * S)
     D = heads * 32

@@ -45,7 +45,7 @@ def test_swinv2_restatement_matches_hf_goldens(name):
 @pytest.mark.parametrize("name", sorted(V2_GRAD_CASES))
 def test_swinv2_restatement_autograd_matches_hf_gradient_goldens(name):
     """Gradients of <features, R> w.r.t. every Swinv2Model parameter, produced by HF's autograd, against torch autograd through
-    the restatement: the pin for the SwinV2 backward path (not built yet; the product raises for trainable swinv2 backbones)."""
+    the restatement: the pin for the SwinV2 backward path (GPU side: test_swinv2_gpu.py::test_swinv2_backward_matches_hf_gradient_golden)."""
     from cs_vit.synthetic import SWINV2_VARIANTS
     from oracle import swinv2_restated as v2
     from oracle.make_train_goldens import projections

@@ -21,6 +21,7 @@ Works with any ``torch.distributed`` backend: NCCL on the B200 box, gloo in the 
 from __future__ import annotations
 
 import math
+import os
 from typing import Dict, Iterable, List, Optional
 
 import torch
@@ -44,6 +45,7 @@ class GradReducer:
         if comm not in ("auto", "symm", "nccl"):
             raise ValueError(f"comm must be auto / symm / nccl, got {comm!r}")
         self.comm = comm
+        self.comm_ctas = int(os.environ.get("CSVIT_AR_CTAS", "0"))      # grid of the allreduce kernel (0 = library default), same on all ranks
         self.poison: Optional[torch.Tensor] = None   # device scalar (0 or NaN) folded into the first bucket flushed this step
         self._symm = None                     # {"buf", "handle", "ptrs", "mc", "flag_off"} once the symmetric buffer exists
         self._comm_stream = None
@@ -93,7 +95,8 @@ class GradReducer:
                     sy = self._symm
                     off = bucket["offset"] * 4
                     ops.allreduce_f32([q + off for q in sy["ptrs"]], [q + sy["flag_off"] for q in sy["ptrs"]],
-                                      sy["mc"] + off if sy["mc"] else 0, bucket["padded"], sy["rank"], self.world, 1.0 / self.world)
+                                      sy["mc"] + off if sy["mc"] else 0, bucket["padded"], sy["rank"], self.world, 1.0 / self.world,
+                                      ctas=self.comm_ctas)
                     done = torch.cuda.Event()
                     done.record()
                 self._events.append(done)

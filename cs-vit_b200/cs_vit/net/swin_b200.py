@@ -108,6 +108,7 @@ class SwinBackboneB200(nn.Module):
         self.config = config
         self.precision = precision
         self.fuse_attn = True  # csvit_swin_attn_fused for C in {128, 256}: LN + QKV + window attention in one tcgen05 kernel
+        self.fuse_attn_widths = ops.ATTN_FUSED_WIDTHS   # (ablation: restrict the fused kernel to a subset of its widths)
         self._drop_path_rand: List[torch.Tensor] = []   # test hook: the [B] uniform draws of the next stochastic-depth calls, in call order
         self.fuse_mlp = True   # csvit_mlp_fused for C in {128, 256}: hidden activations never leave the SM
         # Inference runs the batch through the whole backbone in chunks of this many images (0 = all at once).  Images are
@@ -207,7 +208,7 @@ class SwinBackboneB200(nn.Module):
             if ws != 7 or C != 32 * heads:
                 raise NotImplementedError(f"the tcgen05 window-attention kernels are built for 7x7 windows and head_dim 32 "
                                           f"(got window {ws}, C={C}, heads={heads}); use precision='fp32'")
-            if self.fuse_attn and C in ops.ATTN_FUSED_WIDTHS:
+            if self.fuse_attn and C in self.fuse_attn_widths:
                 # narrow stages: layernorm_before + shift/partition + Q/K/V + window attention + reverse/un-shift in ONE tcgen05
                 # kernel (csrc/attn_fused.cu); xn, qkv, logits and probabilities stay on the SM.  Out-proj on plain rows.
                 src = qkv_src + bqkv_src + [sa.relative_position_bias_table, ln1.weight, ln1.bias]

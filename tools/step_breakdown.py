@@ -18,6 +18,8 @@ inp = {k: v.cuda() for k, v in make_inputs(B, 1, S, seed=3).items()}
 def step():
     with torch.no_grad():
         return m.predict_batch(inp["patches"], inp["square_bboxes"], inp["timestamp"], inp["focal"], inp["princpt"])
+if os.environ.get("FUSE_WIDTHS") is not None:
+    m.backbone.fuse_attn_widths = tuple(int(v) for v in os.environ["FUSE_WIDTHS"].split(",") if v)
 if os.environ.get("FUSE_ATTN") is not None:
     m.backbone.fuse_attn = os.environ["FUSE_ATTN"] == "1"
 for _ in range(3): step()

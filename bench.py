@@ -207,14 +207,14 @@ def peaks():
         return 1400.0, 6650.0, "fallback"
 
 
-def gemm_traffic(a):
-    """DRAM bytes per GEMM launch from the committed ncu capture of this exact workload (profiles/r1_gemm_dram_traffic.json);
-    None for any other workload / variant / batch."""
+def kernel_traffic(a, key):
+    """DRAM bytes per launch of a kernel group ("gemm", "attn_core", "attn_fused") from the committed ncu capture of this exact workload
+    (profiles/r2_dram_traffic.json, tools/dram_traffic.py); None for any other workload / variant / batch."""
     if a.variant != "swin_b" or a.workload != "spatial" or a.batch != BATCH:
         return None
     try:
-        with open(os.path.join(ROOT, "profiles", "r1_gemm_dram_traffic.json")) as f:
-            return json.load(f)["traffic_bytes_per_launch"]
+        with open(os.path.join(ROOT, "profiles", "r2_dram_traffic.json")) as f:
+            return json.load(f)[key]["traffic_bytes_per_launch"]
     except Exception:
         return None
 
@@ -337,20 +337,21 @@ def run_ours(a):
             ach = prof["flops"] / (prof["ms"] / 1e3) / 1e12
             out["roofline"] = {"bound": "tensor", "kernel": "csvit_linear = gemm_pair_kernel (cta_group::2, most launches) / gemm_tc_kernel: every Linear of backbone and head",
                                "achieved": round(ach, 1), "peak": peak_tf, "unit": "TFLOP/s", "frac": round(ach / peak_tf, 4),
-                               "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peak_kind})", "traffic": gemm_traffic(a),
+                               "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peak_kind})", "traffic": kernel_traffic(a, "gemm"),
                                "launches_per_step": prof["launches"] // a.steps,
                                "share_of_step": round(prof["ms"] / a.steps / (ms_total / a.steps), 3),
                                "avg_launch_us": round(1e3 * prof["ms"] / prof["launches"], 2)}
         # ---- the tcgen05 window-attention kernels (HBM-bound), same instrumented pass -------------------------------
-        for key, entry, kern, bpt in (("roofline_attention", "csvit_swin_attn_core", "swin_attn_core_kernel: q/k/v tiles by TMA, QK^T and PV on tcgen05/TMEM (stages 2-3)", "8C"),
-                                     ("roofline_attention_fused", "csvit_swin_attn_fused", "swin_attn_fused_kernel: LN + QKV + attention in one tcgen05 kernel (stages 0-1)", "6C")):
+        for key, entry, kern, bpt, tkey in (
+                ("roofline_attention", "csvit_swin_attn_core", "swin_attn_core_kernel: q/k/v tiles by TMA, QK^T and PV on tcgen05/TMEM (stages 2-3)", "8C", "attn_core"),
+                ("roofline_attention_fused", "csvit_swin_attn_fused", "swin_attn_fused_kernel: LN + QKV + attention in one tcgen05 kernel (stages 0-1)", "6C", "attn_fused")):
             ops.begin_profile(entry)
             timed_loop(a.steps, eager_step)
             prof = ops.end_profile()
             if prof["launches"]:
                 gbs = prof["bytes"] / (prof["ms"] / 1e3) / 1e9
                 out[key] = {"bound": "hbm", "kernel": kern, "achieved": round(gbs, 1), "peak": peak_gbs, "unit": "GB/s",
-                            "frac": round(gbs / peak_gbs, 4), "algorithmic_bytes_per_token": bpt, "traffic": None,
+                            "frac": round(gbs / peak_gbs, 4), "algorithmic_bytes_per_token": bpt, "traffic": kernel_traffic(a, tkey),
                             "tflops": round(prof["flops"] / (prof["ms"] / 1e3) / 1e12, 1),
                             "launches_per_step": prof["launches"] // a.steps,
                             "share_of_step": round(prof["ms"] / a.steps / (ms_total / a.steps), 3),

@@ -41,6 +41,7 @@ SIGNATURES = {
     "csvit_rot6d_to_axis_angle": [c_void_p, c_void_p, c_longlong, c_void_p],
     "csvit_mano_fk": [c_void_p] * 10 + [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p],
     "csvit_allreduce_f32": [c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_int, c_float, c_int, c_void_p],
+    "csvit_last_gemm_kernel": [],
     "csvit_set_gemm_tuning": [c_int, c_int, c_int, c_int],
     "csvit_window_attention": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p],
     "csvit_attention": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_longlong, c_longlong, c_longlong, c_longlong,

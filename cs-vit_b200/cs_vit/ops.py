@@ -44,7 +44,7 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
-_profile = None  # {"name": entry point, "events": [(start, stop, flops, bytes)]} while bench.py instruments a kernel
+_profile = None  # {"name": entry point, "events": [(start, stop, flops, bytes, gemm kernel id)]} while bench.py instruments a kernel
 
 
 def begin_profile(name: str) -> None:
@@ -58,8 +58,12 @@ def end_profile() -> dict:
     prof, _profile = _profile, None
     torch.cuda.synchronize()
     ev = prof["events"]
-    return {"launches": len(ev), "ms": sum(a.elapsed_time(b) for a, b, _, _ in ev),
-            "flops": float(sum(f for _, _, f, _ in ev)), "bytes": float(sum(b for _, _, _, b in ev))}
+    out = {"launches": len(ev), "ms": sum(e[0].elapsed_time(e[1]) for e in ev),
+           "flops": float(sum(e[2] for e in ev)), "bytes": float(sum(e[3] for e in ev))}
+    for kind in sorted({e[4] for e in ev if e[4]}):      # csvit_linear: the same split per kernel the C side chose
+        sel = [e for e in ev if e[4] == kind]
+        out[f"kind{kind}"] = {"launches": len(sel), "ms": sum(e[0].elapsed_time(e[1]) for e in sel), "flops": float(sum(e[2] for e in sel))}
+    return out
 
 
 def _call(name: str, *args, flops: float = 0.0, nbytes: float = 0.0) -> None:
@@ -70,7 +74,8 @@ def _call(name: str, *args, flops: float = 0.0, nbytes: float = 0.0) -> None:
         e0.record()
         _lib.check(getattr(_lib.load(), name)(*args))
         e1.record()
-        _profile["events"].append((e0, e1, flops, nbytes))
+        kind = _lib.load().csvit_last_gemm_kernel() if name == "csvit_linear" else 0
+        _profile["events"].append((e0, e1, flops, nbytes, kind))
         return
     _lib.check(getattr(_lib.load(), name)(*args))
 

@@ -151,6 +151,8 @@ int csvit_mlp_fused(const void* xn, long long ldxn, const void* W1, long long ld
   return launch_mlp_fused(xn, ldxn, W1, ldw1, b1, W2, ldw2, b2, x, ldx, dtype, M, C, S(stream));
 }
 
+int csvit_last_gemm_kernel(void) { return last_gemm_kernel(); }
+
 int csvit_set_gemm_tuning(int cluster, int tma_store, int max_ctas, int pair) {
   g_tune.pair = pair;
   CSVIT_REQUIRE(cluster == 0 || cluster == 1 || cluster == 2 || cluster == 4, "gemm tuning: cluster %d not in {0,1,2,4}", cluster);

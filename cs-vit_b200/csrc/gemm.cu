@@ -309,8 +309,12 @@ static int launch_tc_cs(int cs, const CUtensorMap& a, const CUtensorMap& b, cons
   return launch_tc<BN, FMT, 1>(a, b, c, r, K, ep, max_ctas, st);
 }
 
+static thread_local int g_last_gemm_kernel = 0;      // which kernel the last launch_gemm() of this thread chose (bench.py labels its roofline by it)
+int last_gemm_kernel() { return g_last_gemm_kernel; }
+
 int launch_gemm(const void* A, long long lda, const void* W, long long ldw, int in_dtype, int M, int N, int K,
                 const EpiParams& ep_in, int impl, const GemmTuning& tune, cudaStream_t stream) {
+  g_last_gemm_kernel = 0;
   if (M <= 0 || N <= 0 || K <= 0) return 0;
   EpiParams ep = ep_in;
   ep.M = M; ep.N = N;
@@ -324,6 +328,7 @@ int launch_gemm(const void* A, long long lda, const void* W, long long ldw, int 
     dim3 grid((N + 63) / 64, (M + 63) / 64);
     gemm_simt_f32_kernel<<<grid, 256, 0, stream>>>(static_cast<const float*>(A), lda, static_cast<const float*>(W), ldw, K, ep);
     CSVIT_CUDA(cudaGetLastError());
+    g_last_gemm_kernel = 3;
     return 0;
   }
   // Tile width: 256 halves the per-MMA shared-memory operand traffic; narrower tiles only where N is small
@@ -349,7 +354,11 @@ int launch_gemm(const void* A, long long lda, const void* W, long long ldw, int 
   // CTA pairs (cta_group::2): 256x256 tiles with the weight tile split across the two SMs - a third less
   // shared-memory ingest per MMA than the single-CTA kernel, which is what bounds the large-K GEMMs.
   const bool pair_ok = in_dtype != DT_F32 && N % 256 == 0 && num_m * (N / 256) >= 2 * num_sms();
-  if (pair_ok && tune.pair != 0) return launch_gemm_pair(A, lda, W, ldw, in_dtype, M, N, K, ep, tune, stream);
+  if (pair_ok && tune.pair != 0) {
+    g_last_gemm_kernel = 1;
+    return launch_gemm_pair(A, lda, W, ldw, in_dtype, M, N, K, ep, tune, stream);
+  }
+  g_last_gemm_kernel = 2;
   CUtensorMap tmA, tmB, tmC, tmR;
   if (int e = make_tmap(&tmA, A, lda, M, K, in_dtype, kBM, true)) return e;
   if (int e = make_tmap(&tmB, W, ldw, N, K, in_dtype, BN / cs, true)) return e;

@@ -414,6 +414,8 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& ep, const CUtenso
 // Host launchers (gemm.cu).  in_dtype: DT_BF16 / DT_F16 -> tcgen05 kind::f16 (W in the same format);
 // DT_F32 -> tcgen05 kind::tf32 when impl == GEMM_TC, exact fp32 FMA when impl == GEMM_SIMT.
 enum : int { GEMM_TC = 0, GEMM_SIMT = 1 };
+int last_gemm_kernel();      // 0 none, 1 gemm_pair_kernel, 2 gemm_tc_kernel, 3 gemm_simt_f32_kernel
+
 struct GemmTuning {
   int max_ctas;   // 0 = one per SM
   int cluster;    // 0 = auto, else 1 / 2 / 4 CTAs sharing the weight tile by TMA multicast

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define CSVIT_ABI_VERSION 9
+#define CSVIT_ABI_VERSION 10
 
 #if defined(__GNUC__)
 #define CSVIT_API __attribute__((visibility("default")))
@@ -115,6 +115,10 @@ CSVIT_API int csvit_linear(const void* A, long long lda, const void* W, long lon
  * second tcgen05 GEMM).  Replaces intermediate.dense + GELU + output.dense + residual add   (HF:510-531, 650). */
 CSVIT_API int csvit_mlp_fused(const void* xn, long long ldxn, const void* W1, long long ldw1, const float* b1, const void* W2,
                               long long ldw2, const float* b2, float* x, long long ldx, int dtype, int M, int C, void* stream);
+
+/* Which kernel the calling thread's last csvit_linear launched: 1 = gemm_pair_kernel (CTA pairs, cta_group::2), 2 = gemm_tc_kernel
+ * (single CTA), 3 = gemm_simt_f32_kernel (exact fp32), 0 = nothing.  Measurement aid: bench.py attributes launch times per kernel. */
+CSVIT_API int csvit_last_gemm_kernel(void);
 
 /* Process-wide tuning knobs of the GEMM engine (benchmarking / ablation; defaults are automatic):
  *   cluster   0 = auto, 1 / 2 / 4 = CTAs per cluster sharing the weight tile by TMA multicast

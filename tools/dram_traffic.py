@@ -16,7 +16,8 @@ ids = sorted(by_id)
 names = [by_id[i]["name"] for i in ids]
 # the capture is filtered to these kernels: a step starts with the patch-embedding GEMM (gemm_tc_kernel<128, 0, 1> / <128, 1, 1>) - find the
 # last repetition of the per-step launch pattern by its length
-groups = {"gemm": ("gemm_pair_kernel", "gemm_tc_kernel"), "attn_core": ("swin_attn_core_kernel",), "attn_fused": ("swin_attn_fused_kernel",)}
+groups = {"gemm": ("gemm_pair_kernel", "gemm_tc_kernel"), "gemm_pair": ("gemm_pair_kernel",), "attn_core": ("swin_attn_core_kernel",),
+          "attn_fused": ("swin_attn_fused_kernel",)}
 steps = int(sys.argv[3]) if len(sys.argv) > 3 else 2
 out = {"source": "ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:gemm_|swin_attn python bench.py "
                  "--steps 1 --warmup 1 --no-extras --no-cpu-baseline --no-graph (last step of the capture)", "workload": "swin_b spatial predict_batch, batch 256, fp16"}

@@ -24,11 +24,11 @@
 //           on the last window row / column), exp2, unnormalised P in 16 bit written over Q' (dead once S(h) has completed)
 //   PV(h)   O'[128 x 64] = P' V' (written over S' in TMEM): row r finds its window's output in columns 32 (r / 64) .. +31
 //   E(h)    O' / rowsum + bv -> 16 bit -> ctx rows in TOKEN order (window_reverse + un-shift folded into the store address)
-// Roles: warp 0 TMA producer, warp 1 MMA issuer (convergent, one elected lane issues), warps 2-3 L2 prefetch of the next tiles'
-// rows, warps 4-15 three softmax warpgroups, warps 16-23 LayerNorm producers (setmaxnreg moves registers to the softmax groups).  A head's chain G -> D -> S -> X -> PV -> E crosses the tensor pipe three times, so THREE
+// Roles: warp 0 TMA producer, warp 1 projection (G) issuer, warp 2 attention (S, PV) issuer (convergent warps, one elected lane
+// issues), warp 3 L2 prefetch of the next tiles' rows, warps 4-15 three softmax warpgroups, warps 16-23 LayerNorm producers (setmaxnreg moves registers to the softmax groups).  A head's chain G -> D -> S -> X -> PV -> E crosses the tensor pipe three times, so THREE
 // heads are in flight: global head gh uses slot gh % 3 (accumulator, Q'K'V' buffers, S'/O' columns) and warpgroup gh % 3,
-// continuously across tile boundaries.  The issuer's order per step s is PV(s-2), S(s), G(s+3) - the order in which their
-// operands become ready in steady state, the long projection last so that it never delays a softmax group.
+// continuously across tile boundaries.  Two issuer warps: the projections run ahead on their own, so a PV or S whose operands
+// are ready is never queued behind a projection's weight waits.
 // TMEM: 3 slots x (96 accumulator + 64 S'/O') = 480 columns.
 #include <type_traits>
 
@@ -162,6 +162,7 @@ swin_attn_fused_kernel(const __grid_constant__ CUtensorMap tmW, FaParams p) {
           const int h = (wq / KB) % HEADS, kb = wq % KB;
           mbar_arrive_expect_tx(&w_full[s], 96 * 128);
           tma_load_2d(smem + Cfg::RING_OFF + size_t(s) * FA_STAGE, &tmW, &w_full[s], kb * 64, h * 96);
+          if (wq < 128) FA_TR(15, 128 + wq);
           if (++s == FA_NST) { s = 0; ph ^= 1u; }
           ++wq; moved = true;
         }
@@ -174,17 +175,17 @@ swin_attn_fused_kernel(const __grid_constant__ CUtensorMap tmW, FaParams p) {
             ++bq; moved = true;
           }
         }
-        if (!moved) __nanosleep(64);
+        if (!moved) __nanosleep(256);      // (both rings run two heads ahead: a slower poll costs nothing and frees issue slots)
       }
     }
   } else if (warp == 1) {
-    // ---------------- MMA issuer: the whole warp runs the loop and waits, one elected lane issues.  Per step s: PV(s-2), S(s),
-    // G(s+3).  (An event-driven variant that polled the three queues with test_wait and issued whatever was ready, k-slab by
-    // k-slab, measured 6-30 % slower: the polling itself costs more than the head-of-line waits it removes.)
+    // ---------------- projection issuer: G(gh) for every head in order, as far ahead as the accumulator slots and the weight ring
+    // allow (the whole warp runs the loop and waits, one elected lane issues).  S and PV have an issuer warp of their own: with one
+    // in-order issuer for all three (round 2, first version) a ready PV waited ~2900 cycles behind the next head's S and a
+    // projection whose issue takes 1000-1700 cycles when the warp shares its scheduler with five busy warps (clock64 trace,
+    // profiles/r2_attn_fused_issuer_trace.txt) - and the softmax groups idled for exactly that long.
     {
       constexpr uint32_t idesc_g = make_idesc(uint32_t(FMT), 128, 96);
-      constexpr uint32_t idesc_s = make_idesc(uint32_t(FMT), 128, 64);
-      constexpr uint32_t idesc_o = make_idesc(uint32_t(FMT), 128, 64) | (1u << 16);                // V' is MN-major
       int s = 0; uint32_t ph = 0;
       uint32_t xn_addr = 0;
       // G(gh): projection of global head gh into its slot's accumulator
@@ -204,6 +205,7 @@ swin_attn_fused_kernel(const __grid_constant__ CUtensorMap tmW, FaParams p) {
         for (int kb = 0; kb < KB; ++kb) {
           mbar_wait(&w_full[s], ph);
           tc_fence_after();
+          if (lane == 0 && kb < 2 && gh < 64) FA_TR(15, 2 * gh + kb);
           if (fa_elect_one()) {
             const uint64_t adesc = make_sw128_kmajor_desc(xn_addr + uint32_t(kb) * FA_SLAB);
             const uint64_t bdesc = make_sw128_kmajor_desc(base + Cfg::RING_OFF + uint32_t(s) * FA_STAGE);
@@ -220,7 +222,13 @@ swin_attn_fused_kernel(const __grid_constant__ CUtensorMap tmW, FaParams p) {
         }
         if (lane == 0) FA_TR(1, gh);
       };
-      for (int gh = 0; gh < FA_NSLOT && gh < total; ++gh) issue_g(gh);
+      for (int gh = 0; gh < total; ++gh) issue_g(gh);
+    }
+  } else if (warp == 2) {
+    // ---------------- attention issuer: per step s PV(s-2), then S(s) - the order in which their operands become ready in steady state
+    {
+      constexpr uint32_t idesc_s = make_idesc(uint32_t(FMT), 128, 64);
+      constexpr uint32_t idesc_o = make_idesc(uint32_t(FMT), 128, 64) | (1u << 16);                // V' is MN-major
       for (int gs = 0; gs < total + 2; ++gs) {
         if (gs >= 2) {          // PV(gs - 2)
           const int gh = gs - 2, sl = gh % FA_NSLOT;
@@ -254,16 +262,15 @@ swin_attn_fused_kernel(const __grid_constant__ CUtensorMap tmW, FaParams p) {
           __syncwarp();
           if (lane == 0) FA_TR(4, gs);
         }
-        if (gs + FA_NSLOT < total) issue_g(gs + FA_NSLOT);
       }
     }
   } else {
-    // ---------------- spare warps 2-3: pull the rows of the tiles ahead into L2, at most three tiles ahead of the LayerNorm warps
-    const int pl = (warp - 2) * 32 + lane;
+    // ---------------- spare warp 3: pull the rows of the tiles ahead into L2, at most three tiles ahead of the LayerNorm warps
+    const int pl = lane;
     for (int ti = 1; ti < my_tiles; ++ti) {
-      while (*ln_done + 3 < ti) __nanosleep(128);
+      while (*ln_done + 3 < ti) __nanosleep(2000);      // (a tile takes ~6 us: polling faster only burns issue slots the softmax warps need)
       const int t = int(blockIdx.x) + ti * int(gridDim.x);
-      for (int q = pl; q < FA_ROWS; q += 64) {
+      for (int q = pl; q < FA_ROWS; q += 32) {
         const int wg = 2 * t + q / FA_L, i = q % FA_L;
         if (wg >= p.num_windows) continue;
         const int b = wg / p.nW, w = wg - b * p.nW;
@@ -290,19 +297,33 @@ swin_attn_fused_kernel(const __grid_constant__ CUtensorMap tmW, FaParams p) {
     uint32_t dm_lo = 0, dm_hi = 0;           // shift mask of this row: bit c set = key slot c lies in another region
     int cur_ti = -1;
     uint32_t n = 0;
+    const int slot_iy = (j < FA_L ? j : 0) / 7, slot_ix = (j < FA_L ? j : 0) % 7;       // position of this row's slot inside its 7 x 7 window
+    const int th = p.g.ws - p.g.shift, nWy = p.g.H / p.g.ws;
+    const unsigned long long rows_lo = (1ull << (7 * th)) - 1ull;                     // key slots with iy < th
+    const unsigned long long cols_lo = ((1ull << th) - 1ull) * 0x40810204081ull;      // key slots with ix < th
     for (int gh = g; gh < total; gh += FA_NSLOT, ++n) {
       const int ti = gh / HEADS, h = gh - ti * HEADS;
       const uint32_t ph = n & 1u;
       if (ti != cur_ti) {   // first head of a tile for this group: where the row goes, and its mask
+        // (at C = 128 nearly every head of a group starts a new tile: the slot's (iy, ix) are hoisted out of the loop and the window's
+        // (image, wy, wx) cost two divisions; win_row_to_token / fa_row_mask of common.cuh restated on those)
         cur_ti = ti;
         const int t = int(blockIdx.x) + ti * int(gridDim.x);
         const int wg = 2 * t + wdx;
         tok_off = -1; dm_lo = dm_hi = 0;
         if (j < FA_L && wg < p.num_windows) {
           const int b = wg / p.nW, w = wg - b * p.nW;
-          tok_off = (static_cast<long long>(b) * p.g.N + win_row_to_token(p.g, w * FA_L + j)) * C;
-          const unsigned long long dm = fa_row_mask(p.g, w, j);
-          dm_lo = uint32_t(dm); dm_hi = uint32_t(dm >> 32);
+          const int wy = w / p.g.nWx, wx = w - wy * p.g.nWx;
+          int y = wy * 7 + slot_iy + p.g.shift; if (y >= p.g.H) y -= p.g.H;
+          int x = wx * 7 + slot_ix + p.g.shift; if (x >= p.g.W) x -= p.g.W;
+          tok_off = (static_cast<long long>(b) * p.g.N + y * p.g.W + x) * C;
+          if (p.g.shift > 0) {
+            unsigned long long dm = 0;
+            if (wy == nWy - 1) dm |= (slot_iy < th) ? ~rows_lo : rows_lo;
+            if (wx == p.g.nWx - 1) dm |= (slot_ix < th) ? ~cols_lo : cols_lo;
+            dm &= (1ull << FA_L) - 1ull;
+            dm_lo = uint32_t(dm); dm_hi = uint32_t(dm >> 32);
+          }
         }
       }
       // ---- D(h): projection accumulator -> Q' / K' / V'

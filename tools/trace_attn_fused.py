@@ -22,6 +22,10 @@ names = ["Gwait", "Gdone", "PViss", "Siss", "Scmt", "Dwait", "Dbeg", "Dend", "Xb
 print("gh   " + " ".join(f"{n:>7s}" for n in names))
 for gh in range(lo, hi):
     print(f"{gh:3d}  " + " ".join(f"{int(t[k, gh] - t0):7d}" for k in range(11)))
+print("gh   Gwait  w_full(kb0) w_full(kb1)  Gdone   (issuer inside G)   TMA issued kb0 / kb1 (producer)")
+for gh in range(lo, min(hi, 63)):
+    print(f"{gh:3d} {int(t[0, gh] - t0):7d} {int(t[15, 2 * gh] - t0):9d} {int(t[15, 2 * gh + 1] - t0):9d} {int(t[1, gh] - t0):9d}      "
+          f"{int(t[15, 128 + 2 * gh] - t0):9d} {int(t[15, 128 + 2 * gh + 1] - t0):9d}")
 print("per-head period (G issue):", np.diff(t[0, lo:hi]).tolist())
 print("tile LNbeg  LNwaitE LNgotE  LNend")
 for ti in range(lo // heads, hi // heads + 1):

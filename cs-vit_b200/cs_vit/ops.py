@@ -369,6 +369,52 @@ def swinv2_window_attention(qkv: torch.Tensor, bias_tab: torch.Tensor, logit_sca
     return out
 
 
+def swinv2_qkv(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], qscale_log2: torch.Tensor) -> torch.Tensor:
+    """SwinV2 Q/K/V projection with both ``F.normalize`` and the logit scale folded into the epilogue (``csvit_swinv2_qkv``):
+    ``a [M, K]`` and ``w [3C, K]`` 16 bit, ``qscale_log2`` fp32 ``[heads]`` = log2(e) * exp(min(logit_scale, ln 100))."""
+    _dev(a, w, qscale_log2)
+    M, K, lda = _rows2d(a)
+    N, K2, ldw = _rows2d(w)
+    C = N // 3
+    if K2 != K or N != 3 * C or a.dtype != w.dtype or a.dtype not in (torch.float16, torch.bfloat16):
+        raise ValueError("swinv2_qkv: a [M, K] and w [3C, K] must share one 16-bit dtype")
+    if qscale_log2.dtype != torch.float32 or qscale_log2.numel() != C // 32 or not qscale_log2.is_contiguous():
+        raise ValueError("swinv2_qkv: qscale_log2 must be contiguous float32 [C / 32]")
+    if bias is not None and (bias.dtype != torch.float32 or bias.numel() != N or not bias.is_contiguous()):
+        raise ValueError("swinv2_qkv: bias must be contiguous float32 [3C]")
+    out = torch.empty(M, N, dtype=a.dtype, device=a.device)
+    _call("csvit_swinv2_qkv", a.data_ptr(), lda, w.data_ptr(), ldw, _code(a.dtype), M, C, K, bias.data_ptr() if bias is not None else None,
+          qscale_log2.data_ptr(), out.data_ptr(), N, _stream(), flops=2.0 * M * N * K,
+          nbytes=float(a.numel() + w.numel() + out.numel()) * a.element_size())
+    return out
+
+
+def swinv2_bias_log2(bias_tab: torch.Tensor) -> torch.Tensor:
+    """``[heads, 31 * 31]`` table of window 16 (16 sigmoid(cpb_mlp)) -> the padded log2-domain ``[heads, 31, 48]`` table of
+    ``csvit_swinv2_attn_tc``."""
+    heads = bias_tab.shape[0]
+    out = torch.zeros(heads, 31, 48, dtype=torch.float32, device=bias_tab.device)
+    out[:, :, :31] = bias_tab.float().view(heads, 31, 31) * 1.4426950408889634
+    return out.contiguous()
+
+
+def swinv2_attn_tc(qkv: torch.Tensor, bias_log2: torch.Tensor, B: int, H: int, W: int, heads: int, shift: int, mask_repeat: int = 2,
+                   token_order: bool = False) -> torch.Tensor:
+    """tcgen05 cosine window attention for 16 x 16 windows (``csvit_swinv2_attn_tc``) on the output of :func:`swinv2_qkv`."""
+    _dev(qkv, bias_log2)
+    rows, C3, ld = _rows2d(qkv)
+    C = C3 // 3
+    if rows != B * H * W or qkv.dtype not in (torch.float16, torch.bfloat16):
+        raise ValueError("swinv2_attn_tc: qkv must be 16-bit [B*H*W, 3C]")
+    if bias_log2.dtype != torch.float32 or tuple(bias_log2.shape) != (heads, 31, 48) or not bias_log2.is_contiguous():
+        raise ValueError(f"swinv2_attn_tc: bias table must be contiguous float32 [{heads}, 31, 48]")
+    out = torch.empty(rows, C, dtype=qkv.dtype, device=qkv.device)
+    _call("csvit_swinv2_attn_tc", qkv.data_ptr(), ld, bias_log2.data_ptr(), out.data_ptr(), _code(qkv.dtype), B, H, W, C, heads, shift,
+          mask_repeat, 1 if token_order else 0, _stream(), flops=4.0 * rows * 256 * C,
+          nbytes=float(qkv.numel() + out.numel()) * qkv.element_size())
+    return out
+
+
 def layernorm_post(y: torch.Tensor, resid: Optional[torch.Tensor], gamma: torch.Tensor, beta: torch.Tensor, eps: float, *,
                    out: Optional[torch.Tensor] = None, copy_mode: int = COPY_NONE, copy_dtype: torch.dtype = torch.bfloat16,
                    geom: Tuple[int, int, int, int] = (0, 0, 0, 0)) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:

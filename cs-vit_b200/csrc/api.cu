@@ -231,6 +231,28 @@ int csvit_swinv2_window_attention(const void* qkv, const float* bias_tab, const 
                                         out_token_order ? 1 : 0, S(stream));
 }
 
+int csvit_swinv2_qkv(const void* A, long long lda, const void* W, long long ldw, int dtype, int M, int C, int K, const float* bias,
+                     const float* qscale_log2, void* out, long long ldo, void* stream) {
+  CSVIT_REQUIRE(dtype == DT_BF16 || dtype == DT_F16, "swinv2_qkv: 16-bit operands only (the fp32 mode normalises inside its attention kernel)");
+  CSVIT_REQUIRE(A && W && out && qscale_log2, "swinv2_qkv: null operand");
+  CSVIT_REQUIRE(C > 0 && C % 32 == 0 && lda >= K && ldw >= K && ldo >= 3ll * C, "swinv2_qkv: C=%d must be a multiple of 32, pitches >= widths", C);
+  CSVIT_REQUIRE(ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 && (!bias || (reinterpret_cast<uintptr_t>(bias) & 15) == 0),
+                "swinv2_qkv: output rows and bias must be 16-byte aligned");
+  EpiParams ep{};
+  ep.bias = bias; ep.out = out; ep.ldo = ldo; ep.out_dtype = dtype; ep.act = ACT_NONE;
+  ep.map_mode = ROWMAP_IDENTITY;
+  ep.geom = make_geom(1, 1, 1, 0);
+  ep.cos_scale = qscale_log2; ep.cos_C = C;
+  return launch_gemm(A, lda, W, ldw, dtype, M, 3 * C, K, ep, GEMM_TC, g_tune, S(stream));
+}
+
+int csvit_swinv2_attn_tc(const void* qkv, long long ldq, const float* bias_log2, void* ctx, int dtype, int B, int H, int W, int C,
+                         int heads, int shift, int mask_repeat, int token_order, void* stream) {
+  CSVIT_REQUIRE(qkv && bias_log2 && ctx, "swinv2_attn_tc: null operand");
+  CSVIT_REQUIRE(mask_repeat >= 0 && mask_repeat <= 2, "swinv2_attn_tc: mask_repeat %d outside [0,2]", mask_repeat);
+  return launch_swinv2_attn_tc(qkv, ldq, bias_log2, ctx, dtype, B, H, W, C, heads, shift, mask_repeat, token_order, S(stream));
+}
+
 int csvit_layernorm_post(const float* y, long long ldy, const float* resid, const float* gamma, const float* beta, float eps, float* out,
                          void* copy, int copy_dtype, long long ldc, int copy_mode, int rows, int C, int H, int W, int ws, int shift,
                          void* stream) {

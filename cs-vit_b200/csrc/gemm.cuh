@@ -28,7 +28,23 @@ struct EpiParams {
   int tma_f32;    // 1: fp32 output on identity rows (+residual): residual chunks arrive by TMA, results leave by TMA
   int map_mode;
   WinGeom geom;
+  // SwinV2 Q/K/V projection (cos_C = C > 0, N = 3C): every head's 32 columns of q and k are L2-normalised per row before the 16-bit
+  // store (F.normalize of V2:452-455) and q is multiplied by cos_scale[head] (logit scale, log2 domain); v passes unchanged.
+  const float* cos_scale;
+  int cos_C;
 };
+
+// The cosine normalisation above on 32 consecutive columns of one row (= one head: col0 is a multiple of 32).
+__device__ __forceinline__ void epi_cosnorm32(const EpiParams& ep, int col0, float (&v)[32]) {
+  if (col0 >= 2 * ep.cos_C) return;
+  float ss0 = 0.f, ss1 = 0.f;
+#pragma unroll
+  for (int j = 0; j < 32; j += 2) { ss0 = fmaf(v[j], v[j], ss0); ss1 = fmaf(v[j + 1], v[j + 1], ss1); }
+  float inv = 1.0f / fmaxf(sqrtf(ss0 + ss1), 1e-12f);
+  if (col0 < ep.cos_C) inv *= __ldg(ep.cos_scale + (col0 >> 5));
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] *= inv;
+}
 
 __device__ __forceinline__ long long epi_out_row(const EpiParams& ep, int row) {
   if (ep.map_mode == ROWMAP_WINDOW) {
@@ -130,6 +146,7 @@ __device__ __forceinline__ void epi_bias_act32(const EpiParams& ep, int col0, fl
       v[4 * j + 0] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
     }
   }
+  if (ep.cos_C > 0) epi_cosnorm32(ep, col0, v);
   if (ep.act == ACT_GELU) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = gelu_fast(v[j]);

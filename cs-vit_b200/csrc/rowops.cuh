@@ -79,6 +79,10 @@ int launch_layernorm_post(const float* y, long long ldy, const float* resid, con
                           float* xo, void* copy, int copy_dtype, long long ldc, int copy_mode, int rows, int C, const WinGeom& g,
                           cudaStream_t stream);
 
+// swinv2_attn_tc.cu
+int launch_swinv2_attn_tc(const void* qkv, long long ldq, const float* bias_log2, void* ctx, int dtype, int B, int H, int W, int C,
+                          int heads, int shift, int mask_repeat, int token_order, cudaStream_t stream);
+
 // attention_bwd_mma.cu
 int launch_window_attention_bwd_mma(const void* qkv, const void* dout, void* dqkv, int dtype, const float* bias, float* dbias, int B,
                                     int H, int W, int C, int heads, int ws, int shift, cudaStream_t stream);

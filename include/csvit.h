@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define CSVIT_ABI_VERSION 10
+#define CSVIT_ABI_VERSION 11
 
 #if defined(__GNUC__)
 #define CSVIT_API __attribute__((visibility("default")))
@@ -212,6 +212,24 @@ CSVIT_API int csvit_allreduce_f32(const void* const* bufs, const void* const* fl
 CSVIT_API int csvit_swinv2_window_attention(const void* qkv, const float* bias_tab, const float* logit_scale, void* out,
                                             int dtype, int B, int H, int W, int C, int heads, int ws, int shift,
                                             int mask_repeat, int out_token_order, void* stream);
+
+/* SwinV2 Q/K/V projection with the cosine normalisation folded into the GEMM epilogue (16-bit operands):
+ *   out[M, 3C] = A[M, K] @ W[3C, K]^T + bias, then per row and head h (32 columns):
+ *   q_h <- q_h / max(|q_h|, 1e-12) * qscale_log2[h],   k_h <- k_h / max(|k_h|, 1e-12),   v_h unchanged,
+ * with qscale_log2[h] = log2(e) * exp(min(logit_scale[h], ln 100)): the product q_h . k_h is then the log2-domain cosine logit of
+ * V2:450-455 (both F.normalize and the logit scale), computed on the fp32 accumulator before the one 16-bit rounding. */
+CSVIT_API int csvit_swinv2_qkv(const void* A, long long lda, const void* W, long long ldw, int dtype, int M, int C, int K,
+                               const float* bias, const float* qscale_log2, void* out, long long ldo, void* stream);
+
+/* SwinV2 cosine window attention for 16 x 16 windows on tcgen05 / TMEM (swinv2_attn_tc.cu), on the output of csvit_swinv2_qkv:
+ *   ctx = softmax2( q_h k_h^T + bias_log2[h] + mask_repeat * log2(e) * shift_mask ) v_h     per window and head   (V2:450-487)
+ * Operand tiles by TMA ({64 columns, 256 rows} boxes), S = Q K^T [128 x 256] per query tile in TMEM, the 16-bit probabilities
+ * written back to TMEM and read from there as the A operand of P V (no shared-memory round trip).
+ *   bias_log2   fp32 [heads][31][48]: entry [dy + 15][dx + 15] = log2(e) * 16 sigmoid(cpb_mlp)[(dy + 15) * 31 + dx + 15], dy / dx =
+ *               query minus key row / column inside the window (columns 31..47 are padding: conflict-free shared-memory rows)
+ *   shift       0 or 8;  token_order as csvit_swinv2_window_attention's out_token_order */
+CSVIT_API int csvit_swinv2_attn_tc(const void* qkv, long long ldq, const float* bias_log2, void* ctx, int dtype, int B, int H, int W,
+                                   int C, int heads, int shift, int mask_repeat, int token_order, void* stream);
 
 /* Post-norm residual LayerNorm of SwinV2 (V2:707-712, 387, 282) with the next GEMM's operand copy folded in:
  *   out[r, :] = (resid ? resid[r, :] : 0) + LayerNorm(y[r, :]) * gamma + beta        fp32, rows in token order;

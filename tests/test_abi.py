@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/csvit.h but not exported"
     assert set(_lib.SIGNATURES) | {"csvit_last_error"} == set(names), "ctypes table out of sync with the header"
-    assert lib.csvit_abi_version() == 10
+    assert lib.csvit_abi_version() == 11
 
 
 def test_errors_are_reported_not_thrown():

@@ -61,6 +61,47 @@ def test_swinv2_window_attention(ops, H, ws, heads, shift, dtype):
         assert rel(out1, ref) > tol
 
 
+@pytest.mark.parametrize("H,heads,shift,B", [(32, 4, 0, 2), (32, 4, 8, 2), (64, 1, 8, 1), (16, 16, 0, 3), (16, 3, 0, 2), (48, 2, 8, 1),
+                                             (32, 8, 8, 5)])
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_swinv2_qkv_and_tcgen05_attention(ops, H, heads, shift, B, dtype):
+    """csvit_swinv2_qkv (cosine normalisation in the GEMM epilogue) + csvit_swinv2_attn_tc (tcgen05, P as a TMEM operand) against
+    fp32 torch math of V2:450-487 on the same 16-bit-rounded activations and weights."""
+    g = torch.Generator(device="cuda").manual_seed(7 * H + heads + shift)
+    ws, W, C, L = 16, H, heads * 32, 256
+    nW = (H // ws) * (W // ws)
+    xw = torch.randn(B * H * W, C, device="cuda", generator=g).to(dtype)
+    wqkv = (torch.randn(3 * C, C, device="cuda", generator=g) / math.sqrt(C)).to(dtype)
+    bqkv = 0.3 * torch.randn(3 * C, device="cuda", generator=g)
+    bqkv[C:2 * C] = 0                                                   # V2: the key projection has no bias
+    tab = _bias_table(ws, heads, g)
+    scale = (math.log(10.0) + 0.8 * torch.randn(heads, device="cuda", generator=g)).clamp(max=math.log(100.0)).exp().contiguous()
+    qkv_n = ops.swinv2_qkv(xw, wqkv, bqkv, (scale * 1.4426950408889634).contiguous())
+    raw = xw.float() @ wqkv.float().T + bqkv
+    q, k, v = raw.view(B * nW, L, 3, heads, 32).permute(2, 0, 3, 1, 4)
+    qn, kn = torch.nn.functional.normalize(q, dim=-1), torch.nn.functional.normalize(k, dim=-1)
+    # the epilogue: q_hat * log2(e) * scale | k_hat | v, rounded once
+    want_n = torch.stack([qn * (scale * 1.4426950408889634).view(1, heads, 1, 1), kn, v], 0).permute(1, 3, 0, 2, 4).reshape(B * H * W, 3 * C)
+    assert rel(qkv_n, want_n) < (4e-3 if dtype == torch.bfloat16 else 5e-4)
+    out = ops.swinv2_attn_tc(qkv_n, ops.swinv2_bias_log2(tab), B, H, W, heads, shift)
+    idx = ops.rel_pos_index(ws).long().reshape(-1)
+    s = (qn @ kn.transpose(-1, -2)) * scale.view(1, heads, 1, 1) + tab[:, idx].view(1, heads, L, L)
+    if shift:
+        m = ops.shift_mask(H, W, ws, shift)
+        s = (s.view(B, nW, heads, L, L) + 2 * m[None, :, None]).view(B * nW, heads, L, L)
+    ref = (s.softmax(-1) @ v).transpose(1, 2).reshape(B * H * W, C)
+    tol = 2e-2 if dtype == torch.bfloat16 else 3e-3
+    assert rel(out, ref) < tol, rel(out, ref)
+    out_tok = ops.swinv2_attn_tc(qkv_n, ops.swinv2_bias_log2(tab), B, H, W, heads, shift, token_order=True)
+    widx = ops.window_index_map(H, W, ws, shift).long()
+    want_tok = torch.empty_like(out).view(B, H * W, C)
+    want_tok[:, widx] = out.view(B, H * W, C)
+    assert torch.equal(out_tok.view(B, H * W, C), want_tok)
+    if shift:
+        out0 = ops.swinv2_attn_tc(qkv_n, ops.swinv2_bias_log2(tab), B, H, W, heads, shift, mask_repeat=0)
+        assert rel(out0, ref) > tol
+
+
 def test_swinv2_window_attention_rejects_unbuilt_windows(ops):
     qkv = torch.zeros(36, 96, device="cuda", dtype=torch.bfloat16)
     with pytest.raises(RuntimeError, match="not built"):

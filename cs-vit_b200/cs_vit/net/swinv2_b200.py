@@ -120,6 +120,8 @@ class Swinv2BackboneB200(nn.Module):
         super().__init__()
         self.config = config
         self.precision = precision
+        # 16-bit inference on 16 x 16 windows: the tcgen05 attention kernel (CSVIT_V2_ATTN=mma selects round 1's mma.sync kernel: ablation)
+        self._v2_tcgen05 = os.environ.get("CSVIT_V2_ATTN", "tcgen05") != "mma"
         c0, eps = config.embed_dim, config.layer_norm_eps
         self.embeddings = _holder(
             patch_embeddings=_holder(projection=nn.Conv2d(3, c0, kernel_size=4, stride=4)),
@@ -343,9 +345,17 @@ class Swinv2BackboneB200(nn.Module):
                 bqkv = self._w(key + "bqkv", bqkv_src, lambda: torch.cat(
                     [sa.query.bias.detach().float(), torch.zeros_like(sa.query.bias, dtype=torch.float32), sa.value.bias.detach().float()], 0).contiguous())
                 bias_tab, lscale = self._attn_tables(sa, key, ws, cfg.pretrained_window_sizes[s])
-                qkv = ops.linear(xw, wqkv, bqkv, out_dtype=act, impl=impl)
-                # the attention kernel un-partitions / un-shifts on its store: the out-proj runs on plain token rows
-                ctx = ops.swinv2_window_attention(qkv, bias_tab, lscale, n, H, H, heads, ws, shift, token_order=True)
+                # the attention kernels un-partition / un-shift on their store: the out-proj runs on plain token rows
+                if ws == 16 and not self._fp32 and self._v2_tcgen05:
+                    # 256-token windows, 16-bit operands: both F.normalize and the logit scale in the Q/K/V GEMM epilogue, attention
+                    # on tcgen05 with the probabilities kept in TMEM (csvit_swinv2_qkv + csvit_swinv2_attn_tc)
+                    qs = self._pack.get(f"fp32/{key}qscale2", [sa.logit_scale], lambda: (lscale * 1.4426950408889634).contiguous())
+                    bl2 = self._pack.get(f"fp32/{key}cpb{ws}log2", [bias_tab], lambda: ops.swinv2_bias_log2(bias_tab))
+                    qkv = ops.swinv2_qkv(xw, wqkv, bqkv, qs)
+                    ctx = ops.swinv2_attn_tc(qkv, bl2, n, H, H, heads, shift, token_order=True)
+                else:
+                    qkv = ops.linear(xw, wqkv, bqkv, out_dtype=act, impl=impl)
+                    ctx = ops.swinv2_window_attention(qkv, bias_tab, lscale, n, H, H, heads, ws, shift, token_order=True)
                 proj = blk.attention.output.dense
                 ya = ops.linear(ctx, self._weight(key + "wproj", proj.weight), self._f32(key + "bproj", proj.bias), out_dtype=torch.float32,
                                 impl=impl)

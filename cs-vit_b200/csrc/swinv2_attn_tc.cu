@@ -20,7 +20,10 @@
 // Roles: warp 0 TMA producer (2-stage ring), warp 1 MMA issuer, warps 4-19 = two softmax sets (one per TMEM slot / query tile of the
 // head) of two warpgroups (key halves): both query tiles of a head are in flight, so the tensor pipe, the MUFU / LDS work and the
 // loads overlap.  The kernel is bound by the per-logit work of X1 / X2 (about 5 issue slots per logit), not by bytes or MMAs.
+#include <cstdio>
+#include <cstdlib>
 #include <type_traits>
+#include <vector>
 
 #include "attn_common.cuh"
 #include "errors.h"
@@ -37,7 +40,8 @@ constexpr uint32_t VT_BIAS_BYTES = 31 * VT_BROW * 4;
 constexpr uint32_t VT_STAGE_USED = 3 * VT_TILE + 2 * VT_BIAS_BYTES;
 constexpr uint32_t VT_STAGE = (VT_STAGE_USED + 1023u) & ~1023u;
 constexpr uint32_t VT_XCH_OFF = 2 * VT_STAGE;           // float xmax[2 sets][2 halves][128], xsum[2][2][128]
-constexpr uint32_t VT_BAR_OFF = VT_XCH_OFF + 4096;
+constexpr uint32_t VT_ONES_OFF = VT_XCH_OFF + 4096;      // 2 KB of 1.0 (16 bit): the B operand of the row-sum MMA, any layout
+constexpr uint32_t VT_BAR_OFF = VT_ONES_OFF + 2048;
 constexpr size_t VT_SMEM = 1024 + size_t(VT_BAR_OFF) + 256;
 
 struct VtParams {
@@ -49,7 +53,10 @@ struct VtParams {
   int token_order;
   float mask_add;        // log2(e) * (-100) * mask_repeat
   WinGeom g;
+  long long* trace;      // debugging (CSVIT_V2_TRACE): clock64 at the phase boundaries of CTA 0's first tiles, else null
 };
+constexpr int VT_TRACE_TILES = 24;
+#define VT_STAMP(k) do { if (tr) tr[k] = clock64(); } while (0)
 
 __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) {
   asm volatile(
@@ -81,6 +88,9 @@ __device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64
 __device__ __forceinline__ void named_bar_sync(int id, int threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
+__device__ __forceinline__ void named_bar_arrive(int id, int threads) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
 __device__ __forceinline__ uint32_t ex2_h2(uint32_t x) {
   uint32_t y;
   asm("ex2.approx.f16x2 %0, %1;" : "=r"(y) : "r"(x));
@@ -89,10 +99,8 @@ __device__ __forceinline__ uint32_t ex2_h2(uint32_t x) {
 
 // X1 on one 32-column chunk (keys 32 c4 .. 32 c4 + 31 of the thread's half): + bias [+ mask], running max, write back.
 template <bool MASKED>
-__device__ __forceinline__ void vt_pass1_chunk(uint32_t taddr, const float* bt, int c4, float madd_lo, float madd_hi, float& mx0, float& mx1) {
-  uint32_t v[32];
-  tmem_ld_32x32(taddr, v);
-  tmem_ld_wait();
+__device__ __forceinline__ void vt_pass1_chunk(uint32_t taddr, uint32_t (&v)[32], const float* bt, int c4, float madd_lo, float madd_hi,
+                                               float& mx0, float& mx1) {
 #pragma unroll
   for (int k = 0; k < 32; ++k) {
     const int c = 32 * c4 + k;                                   // key (8 hf + (c >> 4), c & 15)
@@ -108,8 +116,46 @@ __device__ __forceinline__ void vt_pass1_chunk(uint32_t taddr, const float* bt, 
   tmem_st_32x32(taddr, v);
 }
 
-// FMT: 0 = fp16, 1 = bf16.
-template <int FMT>
+// X1 over the thread's four chunks; chunk c + 1 is requested from TMEM before chunk c is processed.
+template <bool MASKED>
+__device__ __forceinline__ void vt_pass1(uint32_t ts, const float* bt, float madd_lo, float madd_hi, float& mx0, float& mx1) {
+  uint32_t a[32], b[32];
+  tmem_ld_32x32(ts, a);
+  tmem_ld_wait();
+  tmem_ld_32x32(ts + 32u, b);
+  vt_pass1_chunk<MASKED>(ts, a, bt, 0, madd_lo, madd_hi, mx0, mx1);
+  tmem_ld_wait();
+  tmem_ld_32x32(ts + 64u, a);
+  vt_pass1_chunk<MASKED>(ts + 32u, b, bt, 1, madd_lo, madd_hi, mx0, mx1);
+  tmem_ld_wait();
+  tmem_ld_32x32(ts + 96u, b);
+  vt_pass1_chunk<MASKED>(ts + 64u, a, bt, 2, madd_lo, madd_hi, mx0, mx1);
+  tmem_ld_wait();
+  vt_pass1_chunk<MASKED>(ts + 96u, b, bt, 3, madd_lo, madd_hi, mx0, mx1);
+}
+
+// X2 on one chunk: exp2(logit - max) -> 16 packed pairs; SUM: also accumulate the row sum in registers.
+template <int FMT, bool SUM>
+__device__ __forceinline__ void vt_pass2_chunk(const uint32_t (&v)[32], uint32_t (&pk)[16], float mx, float& sum0, float& sum1) {
+  if (FMT == 0) {       // fp16: the difference is rounded to fp16, the exponential comes out as the packed pair
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      pk[k] = ex2_h2(pack_f16x2(__uint_as_float(v[2 * k]) - mx, __uint_as_float(v[2 * k + 1]) - mx));
+      if (SUM) fa_add_h2(sum0, sum1, pk[k]);
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const float e0 = fa_exp2(__uint_as_float(v[2 * k]) - mx), e1 = fa_exp2(__uint_as_float(v[2 * k + 1]) - mx);
+      if (SUM) { sum0 += e0; sum1 += e1; }
+      pk[k] = pack_bf16x2(e0, e1);
+    }
+  }
+}
+
+// FMT: 0 = fp16, 1 = bf16.  VAR bit 0: P V with N = 32 (the head's own value columns only) instead of the pair's 64; bit 1: row sums
+// from the tensor core (P times a tile of ones) instead of the softmax threads' registers.
+template <int FMT, int VAR>
 __global__ void __launch_bounds__(VT_THREADS, 1)
 swinv2_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, VtParams p) {
   using T16 = typename std::conditional<FMT == 1, __nv_bfloat16, __half>::type;
@@ -132,6 +178,9 @@ swinv2_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, VtParams p) {
   const int u_begin = int(units * blockIdx.x / gridDim.x), u_end = int(units * (blockIdx.x + 1) / gridDim.x);
   const int total_units = u_end - u_begin;
 
+  constexpr bool N32 = (VAR & 1) != 0, ONES = (VAR & 2) != 0;
+  for (uint32_t k = threadIdx.x; k < 512; k += VT_THREADS)
+    reinterpret_cast<uint32_t*>(smem + VT_ONES_OFF)[k] = FMT == 1 ? 0x3F803F80u : 0x3C003C00u;
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmQ);
     for (int s = 0; s < 2; ++s) {
@@ -142,6 +191,7 @@ swinv2_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, VtParams p) {
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
+  fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -166,10 +216,13 @@ swinv2_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, VtParams p) {
                        VT_BIAS_BYTES, &st_full[st]);
         }
       }
-    } else if (warp == 1 && lane == 0) {
-      // ---------------- MMA issuer: query tile gq = 4 unit + 2 e + t uses TMEM slot t; S(gq), then PV(gq - 1)
+    } else if (warp == 1) {
+      // ---------------- MMA issuer: query tile gq = 4 unit + 2 e + t uses TMEM slot t; S(gq), then PV(gq - 1).  The whole warp walks
+      // the loop converged and one elected lane issues: in divergent code every tcgen05.mma costs a six-instruction loop with a branch.
       constexpr uint32_t idesc_s = make_idesc(uint32_t(FMT), 128, 256);
-      constexpr uint32_t idesc_o = make_idesc(uint32_t(FMT), 128, 64) | (1u << 16);       // V' is MN-major
+      constexpr uint32_t idesc_o = make_idesc(uint32_t(FMT), 128, N32 ? 32 : 64) | (1u << 16);       // V' is MN-major
+      constexpr uint32_t idesc_1 = make_idesc(uint32_t(FMT), 128, 16) | (1u << 16);
+      const uint64_t onesd = fa_mnmajor_desc(base + VT_ONES_OFF);
       const int QT = 4 * total_units;
       for (int gq = 0; gq <= QT; ++gq) {
         if (gq < QT) {
@@ -178,29 +231,42 @@ swinv2_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, VtParams p) {
           if ((gq & 3) == 0) mbar_wait(&st_full[gp & 1], (uint32_t(gp) >> 1) & 1u);
           mbar_wait(&o_empty[t], (n & 1u) ^ 1u);                     // E of the slot's previous tile has drained O'
           tc_fence_after();
-          const uint32_t sb = base + uint32_t(gp & 1) * VT_STAGE;
-          const uint64_t qd = make_sw128_kmajor_desc(sb + uint32_t(t) * 16384u) + uint64_t(4 * e);
-          const uint64_t kd = make_sw128_kmajor_desc(sb + VT_TILE) + uint64_t(4 * e);
+          if (fa_elect_one()) {
+            const uint32_t sb = base + uint32_t(gp & 1) * VT_STAGE;
+            const uint64_t qd = make_sw128_kmajor_desc(sb + uint32_t(t) * 16384u) + uint64_t(4 * e);
+            const uint64_t kd = make_sw128_kmajor_desc(sb + VT_TILE) + uint64_t(4 * e);
 #pragma unroll
-          for (int k = 0; k < 2; ++k)
-            umma_ss<false>(tmem_base + uint32_t(t) * 256u, qd + uint64_t(2 * k), kd + uint64_t(2 * k), idesc_s, k ? 1u : 0u);
-          umma_commit(&s_full[t]);
+            for (int k = 0; k < 2; ++k)
+              umma_ss<false>(tmem_base + uint32_t(t) * 256u, qd + uint64_t(2 * k), kd + uint64_t(2 * k), idesc_s, k ? 1u : 0u);
+            umma_commit(&s_full[t]);
+          }
+          __syncwarp();
         }
         if (gq >= 1) {
-          const int q = gq - 1, gp = q >> 2, t = q & 1;
+          const int q = gq - 1, gp = q >> 2, t = q & 1, e = (q >> 1) & 1;
           const uint32_t n = uint32_t(q) >> 1;
           mbar_wait(&p_full[t], n & 1u);
           tc_fence_after();
-          const uint32_t sb = base + uint32_t(gp & 1) * VT_STAGE;
-          const uint64_t vd = fa_mnmajor_desc(sb + 2 * VT_TILE);
-          const uint32_t slot = tmem_base + uint32_t(t) * 256u;
+          if (fa_elect_one()) {
+            const uint32_t sb = base + uint32_t(gp & 1) * VT_STAGE;
+            const uint64_t vd = fa_mnmajor_desc(sb + 2 * VT_TILE) + uint64_t(N32 ? 4 * e : 0);    // N32: head e's 32 columns, 64 bytes in
+            const uint32_t slot = tmem_base + uint32_t(t) * 256u;
 #pragma unroll
-          for (int hf = 0; hf < 2; ++hf)
+            for (int hf = 0; hf < 2; ++hf)
 #pragma unroll
-            for (int ks = 0; ks < 8; ++ks)     // 16 keys per step: 8 packed TMEM columns of P, 16 key rows (2048 B) of V'
-              umma_ts(slot + 64u, slot + uint32_t(128 * hf + 8 * ks), vd + uint64_t(128 * (8 * hf + ks)), idesc_o, (hf | ks) ? 1u : 0u);
-          umma_commit(&o_full[t]);
-          if ((q & 3) == 3) umma_commit(&st_empty[gp & 1]);      // the unit's last P V: its stage may be reloaded
+              for (int ks = 0; ks < 8; ++ks)     // 16 keys per step: 8 packed TMEM columns of P, 16 key rows (2048 B) of V'
+                umma_ts(slot + 64u, slot + uint32_t(128 * hf + 8 * ks), vd + uint64_t(128 * (8 * hf + ks)), idesc_o, (hf | ks) ? 1u : 0u);
+            if (ONES) {
+#pragma unroll
+              for (int hf = 0; hf < 2; ++hf)
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks)     // every column of this 16-column result = the row's sum of rounded probabilities
+                  umma_ts(slot + 64u + (N32 ? 32u : 64u), slot + uint32_t(128 * hf + 8 * ks), onesd, idesc_1, (hf | ks) ? 1u : 0u);
+            }
+            umma_commit(&o_full[t]);
+            if ((q & 3) == 3) umma_commit(&st_empty[gp & 1]);      // the unit's last P V: its stage may be reloaded
+          }
+          __syncwarp();
         }
       }
     }
@@ -225,6 +291,9 @@ swinv2_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, VtParams p) {
     bool masked = false;
     int cur_w = -1;
     const int total_tiles = 2 * total_units;
+    // X2 is MUFU-bound and the two sets share the SM's MUFU pipes: they take turns (set 0 first), so that one set's exponentials
+    // overlap the other's X1 / E / MMA round trips instead of both queueing on the same pipe and then idling together.
+    if (set == 1) named_bar_arrive(3, 512);
     for (int n = 0; n < total_tiles; ++n) {
       const int gp = n >> 1, e = n & 1;
       const int wg = (u_begin + gp) / PAIRS, hp = (u_begin + gp) - wg * PAIRS, h = 2 * hp + e;
@@ -243,63 +312,65 @@ swinv2_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, VtParams p) {
         madd_lo = (ydiff || (lastcol && xi >= 8)) ? p.mask_add : 0.0f;
         madd_hi = (ydiff || (lastcol && xi < 8)) ? p.mask_add : 0.0f;
       }
+      long long* tr = (p.trace && blockIdx.x == 0 && lane == 0 && quad == 0 && n < VT_TRACE_TILES)
+                          ? p.trace + ((set * 2 + hf) * VT_TRACE_TILES + n) * 8 : nullptr;
+      VT_STAMP(0);
       if (e == 0) mbar_wait(&st_full[gp & 1], (uint32_t(gp) >> 1) & 1u);      // the bias tables (async-proxy writes) are visible
       const float* bt = reinterpret_cast<const float*>(sb + 3 * VT_TILE + e * VT_BIAS_BYTES) + boff;
       // ---- X1: biased logits, row max
       mbar_wait(&s_full[set], ph);
       tc_fence_after();
+      VT_STAMP(1);
       float mx0 = -INFINITY, mx1 = -INFINITY;
-      if (masked) {
-#pragma unroll
-        for (int c4 = 0; c4 < 4; ++c4) vt_pass1_chunk<true>(ts + uint32_t(32 * c4), bt, c4, madd_lo, madd_hi, mx0, mx1);
-      } else {
-#pragma unroll
-        for (int c4 = 0; c4 < 4; ++c4) vt_pass1_chunk<false>(ts + uint32_t(32 * c4), bt, c4, 0.f, 0.f, mx0, mx1);
-      }
+      if (masked) vt_pass1<true>(ts, bt, madd_lo, madd_hi, mx0, mx1);
+      else vt_pass1<false>(ts, bt, 0.f, 0.f, mx0, mx1);
       tmem_st_wait();
       float mx = fmaxf(mx0, mx1);
       xmax[hf * 128 + r] = mx;
+      uint32_t va[32], vb[32], pk[16];
+      tmem_ld_32x32(ts, va);                       // X2's first chunk travels while the halves exchange their maxima
+      VT_STAMP(2);
       named_bar_sync(1 + set, 256);
+      VT_STAMP(3);
       mx = fmaxf(mx, xmax[(hf ^ 1) * 128 + r]);
       // ---- X2: unnormalised probabilities, 16 bit, into TMEM over the consumed logits (two keys per column)
       float sum0 = 0.f, sum1 = 0.f;
-#pragma unroll
-      for (int c4 = 0; c4 < 4; ++c4) {
-        uint32_t v[32], pk[16];
-        tmem_ld_32x32(ts + uint32_t(32 * c4), v);
-        tmem_ld_wait();
-        if (FMT == 0) {       // fp16: the difference is rounded to fp16 and one MUFU.EX2 gives the packed pair of probabilities
-#pragma unroll
-          for (int k = 0; k < 16; ++k) {
-            pk[k] = ex2_h2(pack_f16x2(__uint_as_float(v[2 * k]) - mx, __uint_as_float(v[2 * k + 1]) - mx));
-            fa_add_h2(sum0, sum1, pk[k]);
-          }
-        } else {
-#pragma unroll
-          for (int k = 0; k < 16; ++k) {
-            const float e0 = fa_exp2(__uint_as_float(v[2 * k]) - mx), e1 = fa_exp2(__uint_as_float(v[2 * k + 1]) - mx);
-            sum0 += e0; sum1 += e1;
-            pk[k] = pack16(bf, e0, e1);
-          }
-        }
-        tmem_st_32x16(ts + uint32_t(16 * c4), pk);
-      }
+      named_bar_sync(3 + set, 512);                // my turn on the MUFU pipes
+      tmem_ld_wait();
+      tmem_ld_32x32(ts + 32u, vb);
+      vt_pass2_chunk<FMT, !ONES>(va, pk, mx, sum0, sum1);
+      tmem_st_32x16(ts, pk);
+      tmem_ld_wait();
+      tmem_ld_32x32(ts + 64u, va);
+      vt_pass2_chunk<FMT, !ONES>(vb, pk, mx, sum0, sum1);
+      tmem_st_32x16(ts + 16u, pk);
+      tmem_ld_wait();
+      tmem_ld_32x32(ts + 96u, vb);
+      vt_pass2_chunk<FMT, !ONES>(va, pk, mx, sum0, sum1);
+      tmem_st_32x16(ts + 32u, pk);
+      tmem_ld_wait();
+      vt_pass2_chunk<FMT, !ONES>(vb, pk, mx, sum0, sum1);
+      tmem_st_32x16(ts + 48u, pk);
+      named_bar_arrive(4 - set, 512);              // the other set's turn
       tmem_st_wait();
-      xsum[hf * 128 + r] = sum0 + sum1;
+      if (!ONES) xsum[hf * 128 + r] = sum0 + sum1;
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[set]);
+      VT_STAMP(4);
       // ---- E: this half's 16 of the head's 32 output columns
       mbar_wait(&o_full[set], ph);
       tc_fence_after();
-      uint32_t o[16];
-      tmem_ld_32x16(tslot + 64u + uint32_t(32 * e + 16 * hf), o);
+      uint32_t o[16], rs1 = 0;
+      tmem_ld_32x16(tslot + 64u + uint32_t((N32 ? 0 : 32 * e) + 16 * hf), o);
+      if (ONES) tmem_ld_32x1(tslot + 64u + (N32 ? 32u : 64u), rs1);
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&o_empty[set]);
+      VT_STAMP(5);
       if (h < HEADS && wg < p.num_windows) {
-        const float inv = 1.0f / (xsum[r] + xsum[128 + r]);
+        const float inv = 1.0f / (ONES ? __uint_as_float(rs1) : xsum[r] + xsum[128 + r]);
         uint4* dst = reinterpret_cast<uint4*>(ctx + tok_off + h * 32 + 16 * hf);
 #pragma unroll
         for (int q = 0; q < 2; ++q)
@@ -311,14 +382,15 @@ swinv2_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, VtParams p) {
     }
   }
 
+  if (warp >= 4 && ((warp - 4) >> 3) == 0) named_bar_sync(3, 512);      // absorbs set 1's last hand-over
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
-template <int FMT>
+template <int FMT, int VAR>
 static int launch_vt(const CUtensorMap& tmQ, const VtParams& p, cudaStream_t stream) {
-  auto kern = swinv2_attn_tc_kernel<FMT>;
+  auto kern = swinv2_attn_tc_kernel<FMT, VAR>;
   CSVIT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(VT_SMEM)));
   const long long units = static_cast<long long>(p.num_windows) * ((p.heads + 1) / 2);
   const int ctas = units < num_sms() ? int(units) : num_sms();
@@ -343,6 +415,7 @@ int launch_swinv2_attn_tc(const void* qkv, long long ldq, const float* bias_log2
   if (windows <= 0) return 0;
   CSVIT_REQUIRE(windows * VT_L < (1ll << 31), "swinv2_attn_tc: too many rows");
   VtParams p{};
+  p.trace = nullptr;
   p.bias = bias_log2; p.ctx = ctx;
   p.num_windows = static_cast<int>(windows); p.nW = nW; p.C = C; p.heads = heads;
   p.token_order = token_order ? 1 : 0;
@@ -350,7 +423,34 @@ int launch_swinv2_attn_tc(const void* qkv, long long ldq, const float* bias_log2
   p.g = make_geom(H, W, ws, shift);
   CUtensorMap tmQ;
   if (int e = make_tmap(&tmQ, qkv, ldq, windows * VT_L, 3ll * C, dtype, VT_L, false)) return e;
-  return dtype == DT_BF16 ? launch_vt<1>(tmQ, p, stream) : launch_vt<0>(tmQ, p, stream);
+  // CSVIT_V2_VAR (ablation): bit 0 = P V on the head's own 32 value columns, bit 1 = row sums from the tensor core
+  static const char* trace_path = getenv("CSVIT_V2_TRACE");
+  const bool bf = dtype == DT_BF16;
+  if (trace_path) {      // debugging: one traced launch, timestamps written as text
+    const size_t nb = size_t(4) * VT_TRACE_TILES * 8 * sizeof(long long);
+    CSVIT_CUDA(cudaMalloc(&p.trace, nb));
+    CSVIT_CUDA(cudaMemsetAsync(p.trace, 0, nb, stream));
+    int e = bf ? launch_vt<1, 3>(tmQ, p, stream) : launch_vt<0, 3>(tmQ, p, stream);
+    if (e) return e;
+    CSVIT_CUDA(cudaStreamSynchronize(stream));
+    std::vector<long long> h(nb / sizeof(long long));
+    CSVIT_CUDA(cudaMemcpy(h.data(), p.trace, nb, cudaMemcpyDeviceToHost));
+    cudaFree(p.trace);
+    if (FILE* f = fopen(trace_path, "w")) {
+      long long t0 = 0;
+      for (long long v : h) if (v && (!t0 || v < t0)) t0 = v;
+      fprintf(f, "# clock64 relative to the first stamp; rows: set hf tile | loop top, S ready, X1 done, max exchanged, P published, O read\n");
+      for (int w = 0; w < 4; ++w)
+        for (int n = 0; n < VT_TRACE_TILES; ++n) {
+          fprintf(f, "%d %d %2d |", w >> 1, w & 1, n);
+          for (int k = 0; k < 6; ++k) fprintf(f, " %8lld", h[(w * VT_TRACE_TILES + n) * 8 + k] ? h[(w * VT_TRACE_TILES + n) * 8 + k] - t0 : -1);
+          fprintf(f, "\n");
+        }
+      fclose(f);
+    }
+    return 0;
+  }
+  return bf ? launch_vt<1, 3>(tmQ, p, stream) : launch_vt<0, 3>(tmQ, p, stream);
 }
 
 }  // namespace csvit

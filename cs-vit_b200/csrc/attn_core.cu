@@ -140,8 +140,9 @@ swin_attn_core_kernel(const __grid_constant__ CUtensorMap tmQ, AcParams p) {
         fa_bulk_load(smem + AC_BIAS_OFF + uint32_t(bs) * FA_BIAS_STAGE, static_cast<const char*>(p.bias) + size_t(h) * FA_BIAS_BYTES,
                      FA_BIAS_BYTES, &b_full[bs]);
       }
-    } else if (warp == 1 && lane == 0) {
-      // ---------------- MMA issuer: per step S(gp) for both heads, then PV(gp - 1) for both heads
+    } else if (warp == 1) {
+      // ---------------- MMA issuer: per step S(gp) for both heads, then PV(gp - 1) for both heads (converged warp, one elected lane
+      // issues: see fa_elect_one)
       constexpr uint32_t idesc_s = make_idesc(uint32_t(FMT), 128, 128);
       constexpr uint32_t idesc_o = make_idesc(uint32_t(FMT), 128, 128) | (1u << 16);      // V' is MN-major
       for (int gp = 0; gp <= total_pairs; ++gp) {
@@ -154,35 +155,41 @@ swin_attn_core_kernel(const __grid_constant__ CUtensorMap tmQ, AcParams p) {
             mbar_wait(&o_empty[gh & 3u], ((gh >> 2) & 1u) ^ 1u);       // E(gh - 4) has drained this slot's columns
           }
           tc_fence_after();
-          const uint32_t sb = base + uint32_t(st) * AC_STAGE;
-          const uint64_t qdesc = make_sw128_kmajor_desc(sb), kdesc = make_sw128_kmajor_desc(sb + AC_TILE);
+          if (fa_elect_one()) {
+            const uint32_t sb = base + uint32_t(st) * AC_STAGE;
+            const uint64_t qdesc = make_sw128_kmajor_desc(sb), kdesc = make_sw128_kmajor_desc(sb + AC_TILE);
 #pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const uint32_t d_tmem = tmem_base + (uint32_t(2 * gp + e) & 3u) * 128u;
+            for (int e = 0; e < 2; ++e) {
+              const uint32_t d_tmem = tmem_base + (uint32_t(2 * gp + e) & 3u) * 128u;
 #pragma unroll
-            for (int k = 0; k < 2; ++k)
-              umma_ss<false>(d_tmem, qdesc + uint64_t(2 * (2 * e + k)), kdesc + uint64_t(2 * (2 * e + k)), idesc_s, k ? 1u : 0u);
+              for (int k = 0; k < 2; ++k)
+                umma_ss<false>(d_tmem, qdesc + uint64_t(2 * (2 * e + k)), kdesc + uint64_t(2 * (2 * e + k)), idesc_s, k ? 1u : 0u);
+            }
+            // both arrive once BOTH products are complete: the probabilities overwrite the Q and K tiles
+            umma_commit(&s_full[uint32_t(2 * gp) & 3u]);
+            umma_commit(&s_full[uint32_t(2 * gp + 1) & 3u]);
           }
-          // both arrive once BOTH products are complete: the probabilities overwrite the Q and K tiles
-          umma_commit(&s_full[uint32_t(2 * gp) & 3u]);
-          umma_commit(&s_full[uint32_t(2 * gp + 1) & 3u]);
+          __syncwarp();
         }
         if (gp >= 1) {
           const int q = gp - 1, st = q % AC_NST;
           const uint32_t sb = base + uint32_t(st) * AC_STAGE;
-          const uint64_t vdesc = ac_mnmajor_desc(sb + 2 * AC_TILE);
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
             const uint32_t gh = uint32_t(2 * q + e), sl = gh & 3u;
             mbar_wait(&p_full[sl], (gh >> 2) & 1u);
             tc_fence_after();
-            const uint64_t pdesc = make_sw128_kmajor_desc(sb + uint32_t(e) * AC_TILE);
+            if (fa_elect_one()) {
+              const uint64_t vdesc = ac_mnmajor_desc(sb + 2 * AC_TILE);
+              const uint64_t pdesc = make_sw128_kmajor_desc(sb + uint32_t(e) * AC_TILE);
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_ss<false>(tmem_base + sl * 128u, pdesc + uint64_t(2 * k), vdesc + uint64_t(128 * k), idesc_o, k ? 1u : 0u);
-            umma_commit(&o_full[sl]);
+              for (int k = 0; k < 4; ++k)
+                umma_ss<false>(tmem_base + sl * 128u, pdesc + uint64_t(2 * k), vdesc + uint64_t(128 * k), idesc_o, k ? 1u : 0u);
+              umma_commit(&o_full[sl]);
+              if (e == 1) umma_commit(&st_empty[st]);         // the pair's stage may be reloaded once both P V products are complete
+            }
+            __syncwarp();
           }
-          umma_commit(&st_empty[st]);         // the pair's stage may be reloaded once both P V products are complete
         }
       }
     }

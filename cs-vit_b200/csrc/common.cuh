@@ -217,6 +217,14 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
+// One lane of a CONVERGED warp.  The MMA issuers walk their loops with the whole warp and issue under this predicate: ptxas then emits
+// back-to-back UTCHMMA, whereas under `lane == 0` (divergent code) every tcgen05.mma becomes a six-instruction loop with a branch.
+__device__ __forceinline__ bool fa_elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 

@@ -119,8 +119,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else if (warp == 1) {
-    // ---------------- MMA issuer ----------------
-    if (lane == 0) {
+    // ---------------- MMA issuer (converged warp, one elected lane issues: see fa_elect_one) ----------------
+    {
       constexpr uint32_t idesc = make_idesc(uint32_t(FMT), kBM, BN);
       int s = 0; uint32_t ph = 0;
       int as = 0; uint32_t aph = 0;
@@ -131,15 +131,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full[s], ph);
           tc_fence_after();
-          const uint32_t sa = base + uint32_t(s) * Cfg::STAGE_BYTES;
-          const uint64_t adesc = make_sw128_kmajor_desc(sa);
-          const uint64_t bdesc = make_sw128_kmajor_desc(sa + Cfg::A_BYTES);
+          if (fa_elect_one()) {
+            const uint32_t sa = base + uint32_t(s) * Cfg::STAGE_BYTES;
+            const uint64_t adesc = make_sw128_kmajor_desc(sa);
+            const uint64_t bdesc = make_sw128_kmajor_desc(sa + Cfg::A_BYTES);
 #pragma unroll
-          for (int k = 0; k < 4; ++k)  // 4 x 32-byte K slices per 128-byte row; +32 B = +2 in the >>4 field
-            umma_ss<TF32>(d_tmem, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), idesc, (kb | k) ? 1u : 0u);
-          if constexpr (CS == 1) umma_commit(&empty[s]);
-          else umma_commit_mc(&empty[s], kMask);   // release the slot in every CTA that multicasts into it
-          if (kb == num_kb - 1) umma_commit(&tfull[as]);
+            for (int k = 0; k < 4; ++k)  // 4 x 32-byte K slices per 128-byte row; +32 B = +2 in the >>4 field
+              umma_ss<TF32>(d_tmem, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), idesc, (kb | k) ? 1u : 0u);
+            if constexpr (CS == 1) umma_commit(&empty[s]);
+            else umma_commit_mc(&empty[s], kMask);   // release the slot in every CTA that multicasts into it
+            if (kb == num_kb - 1) umma_commit(&tfull[as]);
+          }
+          __syncwarp();
           if (++s == STAGES) { s = 0; ph ^= 1u; }
         }
         if (++as == 2) { as = 0; aph ^= 1u; }

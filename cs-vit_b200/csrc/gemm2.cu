@@ -90,7 +90,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else if (warp == 1) {
     // ---------------- MMA issuer (leader CTA only) ----------------
-    if (lane == 0 && rank == 0) {
+    if (rank == 0) {      // converged warp, one elected lane issues (see fa_elect_one)
       constexpr uint32_t idesc = make_idesc(uint32_t(FMT), 2 * kBM, BN);
       int s = 0; uint32_t ph = 0;
       int as = 0; uint32_t aph = 0;
@@ -101,14 +101,17 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full[s], ph);
           tc_fence_after();
-          const uint32_t sa = base + uint32_t(s) * kPairStageBytes;
-          const uint64_t adesc = make_sw128_kmajor_desc(sa);
-          const uint64_t bdesc = make_sw128_kmajor_desc(sa + kPairABytes);
+          if (fa_elect_one()) {
+            const uint32_t sa = base + uint32_t(s) * kPairStageBytes;
+            const uint64_t adesc = make_sw128_kmajor_desc(sa);
+            const uint64_t bdesc = make_sw128_kmajor_desc(sa + kPairABytes);
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_ss_pair(d_tmem, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), idesc, (kb | k) ? 1u : 0u);
-          umma_commit_pair(&empty[s], 3);
-          if (kb == num_kb - 1) umma_commit_pair(&tfull[as], 3);
+            for (int k = 0; k < 4; ++k)
+              umma_ss_pair(d_tmem, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), idesc, (kb | k) ? 1u : 0u);
+            umma_commit_pair(&empty[s], 3);
+            if (kb == num_kb - 1) umma_commit_pair(&tfull[as], 3);
+          }
+          __syncwarp();
           if (++s == STAGES) { s = 0; ph ^= 1u; }
         }
         if (++as == 2) { as = 0; aph ^= 1u; }

@@ -115,19 +115,22 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       }
     }
   } else if (warp == 1) {
-    // ---------------- MMA issuer ----------------
-    if (lane == 0) {
+    // ---------------- MMA issuer (converged warp, one elected lane issues: see fa_elect_one) ----------------
+    {
       constexpr uint32_t idesc = make_idesc(uint32_t(FMT), kBM, 128);
       int s = 0; uint32_t ph = 0;
       auto mma_unit = [&](uint32_t a_addr, uint32_t d_tmem, bool first) {
         mbar_wait(&w_full[s], ph);
         tc_fence_after();
-        const uint64_t adesc = make_sw128_kmajor_desc(a_addr);
-        const uint64_t bdesc = make_sw128_kmajor_desc(base + w_off + uint32_t(s) * kUnit);
+        if (fa_elect_one()) {
+          const uint64_t adesc = make_sw128_kmajor_desc(a_addr);
+          const uint64_t bdesc = make_sw128_kmajor_desc(base + w_off + uint32_t(s) * kUnit);
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_ss<false>(d_tmem, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), idesc, (first && k == 0) ? 0u : 1u);
-        umma_commit(&w_empty[s]);
+          for (int k = 0; k < 4; ++k)
+            umma_ss<false>(d_tmem, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), idesc, (first && k == 0) ? 0u : 1u);
+          umma_commit(&w_empty[s]);
+        }
+        __syncwarp();
         if (++s == WS) { s = 0; ph ^= 1u; }
       };
       uint32_t it = 0;
@@ -137,7 +140,8 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         mbar_wait(&acc1_empty[b], (use[b] & 1u) ^ 1u);
         tc_fence_after();
         for (int kb = 0; kb < KB1; ++kb) mma_unit(base + a1_off + uint32_t(kb) * kUnit, tmem_base + uint32_t(b * 128), kb == 0);
-        umma_commit(&acc1_full[b]);
+        if (fa_elect_one()) umma_commit(&acc1_full[b]);
+        __syncwarp();
       };
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
         mbar_wait(a1_full, it & 1u);
@@ -147,7 +151,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           const int b = j & 1;
           if (j + 1 < NCH) {
             gemm1(j + 1);
-            if (j + 2 == NCH) umma_commit(a1_empty);   // last GEMM1 of the tile issued: xn tile free once it completes
+            if (j + 2 == NCH) { if (fa_elect_one()) umma_commit(a1_empty); __syncwarp(); }   // last GEMM1 of the tile issued: xn tile free once it completes
           }
           mbar_wait(&a2_full[b], use[b] & 1u);
           tc_fence_after();
@@ -155,8 +159,11 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           for (int kb2 = 0; kb2 < 2; ++kb2)
             for (int n2 = 0; n2 < N2; ++n2)
               mma_unit(base + a2_off + uint32_t(b * 2 + kb2) * kUnit, tm_acc2 + uint32_t(n2 * 128), j == 0 && kb2 == 0);
-          umma_commit(&a2_empty[b]);
-          if (j == NCH - 1) umma_commit(acc2_full);
+          if (fa_elect_one()) {
+            umma_commit(&a2_empty[b]);
+            if (j == NCH - 1) umma_commit(acc2_full);
+          }
+          __syncwarp();
           ++use[b];
         }
       }

@@ -102,11 +102,12 @@ template <bool MASKED>
 __device__ __forceinline__ void vt_pass1_chunk(uint32_t taddr, uint32_t (&v)[32], const float* bt, int c4, float madd_lo, float madd_hi,
                                                float& mx0, float& mx1) {
 #pragma unroll
-  for (int k = 0; k < 32; ++k) {
+  for (int k = 0; k < 32; k += 2) {                              // two logits per packed f32x2 add
     const int c = 32 * c4 + k;                                   // key (8 hf + (c >> 4), c & 15)
-    float f = __uint_as_float(v[k]) + bt[-((c >> 4) * VT_BROW + (c & 15))];
-    if (MASKED) f += ((c & 15) < 8) ? madd_lo : madd_hi;
-    v[k] = __float_as_uint(f);
+    float2 f = __fadd2_rn(make_float2(__uint_as_float(v[k]), __uint_as_float(v[k + 1])),
+                          make_float2(bt[-((c >> 4) * VT_BROW + (c & 15))], bt[-((c >> 4) * VT_BROW + (c & 15) + 1)]));
+    if (MASKED) f = __fadd2_rn(f, ((c & 15) < 8) ? make_float2(madd_lo, madd_lo) : make_float2(madd_hi, madd_hi));
+    v[k] = __float_as_uint(f.x); v[k + 1] = __float_as_uint(f.y);
   }
 #pragma unroll
   for (int k = 0; k < 32; k += 4) {
@@ -140,22 +141,26 @@ __device__ __forceinline__ void vt_pass2_chunk(const uint32_t (&v)[32], uint32_t
   if (FMT == 0) {       // fp16: the difference is rounded to fp16, the exponential comes out as the packed pair
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
-      pk[k] = ex2_h2(pack_f16x2(__uint_as_float(v[2 * k]) - mx, __uint_as_float(v[2 * k + 1]) - mx));
+      const float2 d = __fadd2_rn(make_float2(__uint_as_float(v[2 * k]), __uint_as_float(v[2 * k + 1])), make_float2(-mx, -mx));
+      pk[k] = ex2_h2(pack_f16x2(d.x, d.y));
       if (SUM) fa_add_h2(sum0, sum1, pk[k]);
     }
   } else {
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
-      const float e0 = fa_exp2(__uint_as_float(v[2 * k]) - mx), e1 = fa_exp2(__uint_as_float(v[2 * k + 1]) - mx);
+      const float2 d = __fadd2_rn(make_float2(__uint_as_float(v[2 * k]), __uint_as_float(v[2 * k + 1])), make_float2(-mx, -mx));
+      const float e0 = fa_exp2(d.x), e1 = fa_exp2(d.y);
       if (SUM) { sum0 += e0; sum1 += e1; }
       pk[k] = pack_bf16x2(e0, e1);
     }
   }
 }
 
-// FMT: 0 = fp16, 1 = bf16.  VAR bit 0: P V with N = 32 (the head's own value columns only) instead of the pair's 64; bit 1: row sums
-// from the tensor core (P times a tile of ones) instead of the softmax threads' registers.
-template <int FMT, int VAR>
+// FMT: 0 = fp16, 1 = bf16.  (POLY is unused: exponentials on the FMA pipes for one or two of the four X2 chunks - a degree-4
+// polynomial, FA4's MUFU relief - measured SLOWER, 28.3 -> 29.8 / 30.6 ns: the kernel is bound by issued instructions, not by MUFU.)
+// (P V runs on the head's own 32 value columns - the B descriptor starts 64 e bytes into the pair's 128-byte rows - and the row sums
+// come from the tensor core: P times a tile of ones.  Both were measured against the alternatives: 38 -> 32 ns per (window, head).)
+template <int FMT, int POLY>
 __global__ void __launch_bounds__(VT_THREADS, 1)
 swinv2_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, VtParams p) {
   using T16 = typename std::conditional<FMT == 1, __nv_bfloat16, __half>::type;
@@ -178,7 +183,7 @@ swinv2_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, VtParams p) {
   const int u_begin = int(units * blockIdx.x / gridDim.x), u_end = int(units * (blockIdx.x + 1) / gridDim.x);
   const int total_units = u_end - u_begin;
 
-  constexpr bool N32 = (VAR & 1) != 0, ONES = (VAR & 2) != 0;
+  constexpr bool N32 = true, ONES = true;
   for (uint32_t k = threadIdx.x; k < 512; k += VT_THREADS)
     reinterpret_cast<uint32_t*>(smem + VT_ONES_OFF)[k] = FMT == 1 ? 0x3F803F80u : 0x3C003C00u;
   if (threadIdx.x == 0) {
@@ -291,12 +296,13 @@ swinv2_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, VtParams p) {
     bool masked = false;
     int cur_w = -1;
     const int total_tiles = 2 * total_units;
+    int wg = u_begin / PAIRS, hp = u_begin - wg * PAIRS;      // (window, head pair) of the current unit, advanced without divisions
     // X2 is MUFU-bound and the two sets share the SM's MUFU pipes: they take turns (set 0 first), so that one set's exponentials
     // overlap the other's X1 / E / MMA round trips instead of both queueing on the same pipe and then idling together.
     if (set == 1) named_bar_arrive(3, 512);
     for (int n = 0; n < total_tiles; ++n) {
       const int gp = n >> 1, e = n & 1;
-      const int wg = (u_begin + gp) / PAIRS, hp = (u_begin + gp) - wg * PAIRS, h = 2 * hp + e;
+      const int h = 2 * hp + e;
       const uint32_t ph = uint32_t(n) & 1u;
       const uint8_t* sb = smem + size_t(gp & 1) * VT_STAGE;
       if (wg != cur_w) {      // where the row goes, and its shift-mask addends for the key columns x < 8 / x >= 8
@@ -351,7 +357,7 @@ swinv2_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, VtParams p) {
       tmem_ld_wait();
       vt_pass2_chunk<FMT, !ONES>(vb, pk, mx, sum0, sum1);
       tmem_st_32x16(ts + 48u, pk);
-      named_bar_arrive(4 - set, 512);              // the other set's turn
+      named_bar_arrive(4 - set, 512);              // the other set's turn (handing over a chunk earlier is slower: 36 vs 29 ns)
       tmem_st_wait();
       if (!ONES) xsum[hf * 128 + r] = sum0 + sum1;
       tc_fence_before();
@@ -379,6 +385,7 @@ swinv2_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, VtParams p) {
                               pack16(bf, __uint_as_float(o[8 * q + 4]) * inv, __uint_as_float(o[8 * q + 5]) * inv),
                               pack16(bf, __uint_as_float(o[8 * q + 6]) * inv, __uint_as_float(o[8 * q + 7]) * inv));
       }
+      if (e == 1 && ++hp == PAIRS) { hp = 0; ++wg; }
     }
   }
 
@@ -388,9 +395,9 @@ swinv2_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, VtParams p) {
   if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
-template <int FMT, int VAR>
+template <int FMT, int POLY>
 static int launch_vt(const CUtensorMap& tmQ, const VtParams& p, cudaStream_t stream) {
-  auto kern = swinv2_attn_tc_kernel<FMT, VAR>;
+  auto kern = swinv2_attn_tc_kernel<FMT, POLY>;
   CSVIT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(VT_SMEM)));
   const long long units = static_cast<long long>(p.num_windows) * ((p.heads + 1) / 2);
   const int ctas = units < num_sms() ? int(units) : num_sms();
@@ -430,7 +437,7 @@ int launch_swinv2_attn_tc(const void* qkv, long long ldq, const float* bias_log2
     const size_t nb = size_t(4) * VT_TRACE_TILES * 8 * sizeof(long long);
     CSVIT_CUDA(cudaMalloc(&p.trace, nb));
     CSVIT_CUDA(cudaMemsetAsync(p.trace, 0, nb, stream));
-    int e = bf ? launch_vt<1, 3>(tmQ, p, stream) : launch_vt<0, 3>(tmQ, p, stream);
+    int e = bf ? launch_vt<1, 0>(tmQ, p, stream) : launch_vt<0, 0>(tmQ, p, stream);
     if (e) return e;
     CSVIT_CUDA(cudaStreamSynchronize(stream));
     std::vector<long long> h(nb / sizeof(long long));
@@ -450,7 +457,7 @@ int launch_swinv2_attn_tc(const void* qkv, long long ldq, const float* bias_log2
     }
     return 0;
   }
-  return bf ? launch_vt<1, 3>(tmQ, p, stream) : launch_vt<0, 3>(tmQ, p, stream);
+  return bf ? launch_vt<1, 0>(tmQ, p, stream) : launch_vt<0, 0>(tmQ, p, stream);
 }
 
 }  // namespace csvit

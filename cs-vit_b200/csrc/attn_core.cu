@@ -108,6 +108,8 @@ swin_attn_core_kernel(const __grid_constant__ CUtensorMap tmQ, AcParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  griddep_launch();      // PDL: the next kernel's prologue may overlap this kernel's tail ...
+  griddep_wait();        // ... and this kernel touches global memory only after its predecessors have completed
 
   if (warp < 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
@@ -336,8 +338,7 @@ static int launch_ac(const CUtensorMap& tmQ, const AcParams& p, cudaStream_t str
   CSVIT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(AC_SMEM)));
   const long long units = static_cast<long long>((p.num_windows + 1) / 2) * ((p.heads + 1) / 2);
   const int ctas = units < num_sms() ? int(units) : num_sms();
-  kern<<<ctas, AC_THREADS, AC_SMEM, stream>>>(tmQ, p);
-  CSVIT_CUDA(cudaGetLastError());
+  CSVIT_CUDA(launch_pdl(kern, dim3(ctas), dim3(AC_THREADS), AC_SMEM, stream, tmQ, p));
   return 0;
 }
 

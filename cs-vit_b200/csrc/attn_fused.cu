@@ -147,6 +147,8 @@ swin_attn_fused_kernel(const __grid_constant__ CUtensorMap tmW, FaParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  griddep_launch();      // PDL: the next kernel's prologue may overlap this kernel's tail ...
+  griddep_wait();        // ... and this kernel touches global memory only after its predecessors have completed
 
   if (warp < FA_SM_WARP0) {
   asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
@@ -611,8 +613,7 @@ static int launch_fa(const CUtensorMap& tmW, const FaParams& p, cudaStream_t str
   CSVIT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(Cfg::SMEM)));
   const int tiles = (p.num_windows + 1) / 2;
   const int ctas = tiles < num_sms() ? tiles : num_sms();
-  kern<<<ctas, FA_THREADS, Cfg::SMEM, stream>>>(tmW, p);
-  CSVIT_CUDA(cudaGetLastError());
+  CSVIT_CUDA(launch_pdl(kern, dim3(ctas), dim3(FA_THREADS), Cfg::SMEM, stream, tmW, p));
   return 0;
 }
 

@@ -217,6 +217,11 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
+// Programmatic dependent launch (errors.h::launch_pdl): let the next kernel of the stream be scheduled / wait until every kernel
+// before this one has completed and its writes are visible.  No-ops for kernels launched without the attribute.
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // One lane of a CONVERGED warp.  The MMA issuers walk their loops with the whole warp and issue under this predicate: ptxas then emits
 // back-to-back UTCHMMA, whereas under `lane == 0` (divergent code) every tcgen05.mma becomes a six-instruction loop with a branch.
 __device__ __forceinline__ bool fa_elect_one() {

@@ -23,6 +23,24 @@ struct DeviceOnce {
   }
 };
 
+// Programmatic dependent launch (PDL): kernels launched through launch_pdl() may be scheduled while the previous kernel of the
+// stream is still draining - their prologue (barrier init, TMEM allocation, tensor-map prefetch) overlaps its tail - and call
+// griddep_wait() (common.cuh) before they touch global memory; every such kernel also calls griddep_launch() at its top so that
+// ITS successor may be scheduled early.  Only kernels that contain the wait are launched this way.  Opt-in (CSVIT_PDL=1): with the CUDA-graph replay of the step it measured
+// 2-3 % SLOWER than plain stream order on this pool (profiles/r2_pdl_experiment.txt), so the default launch carries no attribute.
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 }  // namespace csvit
 
 #define CSVIT_CUDA(expr)                                                                              \

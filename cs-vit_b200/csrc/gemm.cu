@@ -95,6 +95,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if constexpr (CS > 1) cluster_sync_all();  // peers' barriers are initialised before any remote arrive / multicast
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  griddep_launch();      // PDL: the next kernel's prologue may overlap this kernel's tail ...
+  griddep_wait();        // ... and this kernel touches global memory only after its predecessors have completed
 
   if (warp == 0) {
     // ---------------- TMA producer ----------------
@@ -293,13 +295,15 @@ static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUten
   cfg.blockDim = dim3(kGemmThreads);
   cfg.dynamicSmemBytes = Cfg::SMEM;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CS;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;      // PDL, see errors.h::launch_pdl
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
   CSVIT_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, tmR, K, ep));
   return 0;
 }

@@ -69,6 +69,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  griddep_launch();      // PDL: the next kernel's prologue may overlap this kernel's tail ...
+  griddep_wait();        // ... and this kernel touches global memory only after its predecessors have completed
 
   if (warp == 0) {
     // ---------------- TMA producer (both CTAs) ----------------
@@ -161,8 +163,7 @@ static int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   int pairs = (max_ctas > 0 ? max_ctas : num_sms()) / 2;
   if (pairs > num_mp * num_n) pairs = num_mp * num_n;
   if (pairs < 1) pairs = 1;
-  kern<<<pairs * 2, kGemmThreads, kPairSmem, stream>>>(tmA, tmB, tmC, tmR, K, ep);
-  CSVIT_CUDA(cudaGetLastError());
+  CSVIT_CUDA(launch_pdl(kern, dim3(pairs * 2), dim3(kGemmThreads), kPairSmem, stream, tmA, tmB, tmC, tmR, K, ep));
   return 0;
 }
 

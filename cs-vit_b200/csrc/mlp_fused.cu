@@ -88,6 +88,8 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  griddep_launch();      // PDL: the next kernel's prologue may overlap this kernel's tail ...
+  griddep_wait();        // ... and this kernel touches global memory only after its predecessors have completed
   const uint32_t tm_acc2 = tmem_base + 256;
 
   if (warp == 0) {
@@ -234,8 +236,7 @@ static int launch_mlp(const CUtensorMap& tmX, const CUtensorMap& tmW1, const CUt
   }
   const int tiles = (mp.M + kBM - 1) / kBM;
   const int ctas = tiles < num_sms() ? tiles : num_sms();
-  kern<<<ctas, kGemmThreads, Cfg::SMEM, stream>>>(tmX, tmW1, tmW2, tmR, mp, ep);
-  CSVIT_CUDA(cudaGetLastError());
+  CSVIT_CUDA(launch_pdl(kern, dim3(ctas), dim3(kGemmThreads), Cfg::SMEM, stream, tmX, tmW1, tmW2, tmR, mp, ep));
   return 0;
 }
 

@@ -36,6 +36,8 @@ template <int MAXJ, int R, typename OutT>
 __global__ void __launch_bounds__(256)
 ln_rows_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                OutT* __restrict__ out, long long ldo, int rows, int C, int mode, WinGeom g, int scatter_min_c) {
+  griddep_launch();
+  griddep_wait();
   const int lane = threadIdx.x & 31;
   const int Cout = mode == LN_MERGE2X2 ? 4 * C : C;
   const int n4 = Cout >> 2;
@@ -130,6 +132,8 @@ template <int LPR, int J, int PASSES, typename OutT>
 __global__ void __launch_bounds__(256)
 ln_rows_sub_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                    OutT* __restrict__ out, long long ldo, int rows, int mode, WinGeom g) {
+  griddep_launch();
+  griddep_wait();
   constexpr int C = LPR * J * 4;
   constexpr int RPW = 32 / LPR;                      // rows per warp per pass
   const int lane = threadIdx.x & 31;
@@ -197,7 +201,7 @@ static void launch_ln_sub(const float* x, const float* gamma, const float* beta,
   constexpr int PASSES = 2;
   const int rows_per_warp = (32 / LPR) * PASSES;
   const int warps = (rows + rows_per_warp - 1) / rows_per_warp;
-  ln_rows_sub_kernel<LPR, J, PASSES, OutT><<<(warps + 7) / 8, 256, 0, stream>>>(x, gamma, beta, eps, out, ldo, rows, mode, g);
+  (void)launch_pdl(ln_rows_sub_kernel<LPR, J, PASSES, OutT>, dim3((warps + 7) / 8), dim3(256), 0, stream, x, gamma, beta, eps, out, ldo, rows, mode, g);
 }
 
 template <int MAXJ, int R, typename OutT>
@@ -212,7 +216,7 @@ static void launch_ln_cfg(const float* x, const float* gamma, const float* beta,
   // gathered instead, but scattering measured faster down to C = 128 (tools/bench_ln.py: 221 vs 242 us at stage 0)
   static int scatter_min = -1;
   if (scatter_min < 0) { const char* e = getenv("CSVIT_LN_SCATTER_MIN_C"); scatter_min = e ? atoi(e) : 128; }
-  ln_rows_kernel<MAXJ, R, OutT><<<blocks, 256, 0, stream>>>(x, gamma, beta, eps, out, ldo, rows, C, mode, g, scatter_min);
+  (void)launch_pdl(ln_rows_kernel<MAXJ, R, OutT>, dim3(blocks), dim3(256), 0, stream, x, gamma, beta, eps, out, ldo, rows, C, mode, g, scatter_min);
 }
 
 template <typename OutT>

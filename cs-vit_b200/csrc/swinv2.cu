@@ -425,6 +425,8 @@ __global__ void __launch_bounds__(256)
 ln_post_kernel(const float* y, long long ldy, const float* resid, const float* __restrict__ gamma,
                const float* __restrict__ beta, float eps, float* xo, CopyT* __restrict__ copy, long long ldc, int copy_mode,
                int rows, int C, WinGeom g) {
+  griddep_launch();
+  griddep_wait();
   const int lane = threadIdx.x & 31;
   const int n4 = C >> 2;
   const int warps_total = (gridDim.x * blockDim.x) >> 5;
@@ -504,8 +506,8 @@ static void launch_lnp_cfg(const float* y, long long ldy, const float* resid, co
                            cudaStream_t stream) {
   const int warps = (rows + R - 1) / R;
   const int blocks = (warps + 7) / 8;
-  ln_post_kernel<MAXJ, R, CopyT><<<blocks, 256, 0, stream>>>(y, ldy, resid, gamma, beta, eps, xo, static_cast<CopyT*>(copy), ldc,
-                                                             copy_mode, rows, C, g);
+  (void)launch_pdl(ln_post_kernel<MAXJ, R, CopyT>, dim3(blocks), dim3(256), 0, stream, y, ldy, resid, gamma, beta, eps, xo,
+                   static_cast<CopyT*>(copy), ldc, copy_mode, rows, C, g);
 }
 
 template <typename CopyT>

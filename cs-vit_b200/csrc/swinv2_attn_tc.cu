@@ -201,6 +201,8 @@ swinv2_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, VtParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  griddep_launch();      // PDL: the next kernel's prologue may overlap this kernel's tail ...
+  griddep_wait();        // ... and this kernel touches global memory only after its predecessors have completed
 
   if (warp < 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
@@ -401,8 +403,7 @@ static int launch_vt(const CUtensorMap& tmQ, const VtParams& p, cudaStream_t str
   CSVIT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(VT_SMEM)));
   const long long units = static_cast<long long>(p.num_windows) * ((p.heads + 1) / 2);
   const int ctas = units < num_sms() ? int(units) : num_sms();
-  kern<<<ctas, VT_THREADS, VT_SMEM, stream>>>(tmQ, p);
-  CSVIT_CUDA(cudaGetLastError());
+  CSVIT_CUDA(launch_pdl(kern, dim3(ctas), dim3(VT_THREADS), VT_SMEM, stream, tmQ, p));
   return 0;
 }
 

@@ -138,21 +138,13 @@ __device__ __forceinline__ void vt_pass1(uint32_t ts, const float* bt, float mad
 // X2 on one chunk: exp2(logit - max) -> 16 packed pairs; SUM: also accumulate the row sum in registers.
 template <int FMT, bool SUM>
 __device__ __forceinline__ void vt_pass2_chunk(const uint32_t (&v)[32], uint32_t (&pk)[16], float mx, float& sum0, float& sum1) {
-  if (FMT == 0) {       // fp16: the difference is rounded to fp16, the exponential comes out as the packed pair
+  // fp32 MUFU.EX2 for both formats: ex2.approx.f16x2 is two MUFU.EX2.F16 plus a PRMT, one instruction more per pair
 #pragma unroll
-    for (int k = 0; k < 16; ++k) {
-      const float2 d = __fadd2_rn(make_float2(__uint_as_float(v[2 * k]), __uint_as_float(v[2 * k + 1])), make_float2(-mx, -mx));
-      pk[k] = ex2_h2(pack_f16x2(d.x, d.y));
-      if (SUM) fa_add_h2(sum0, sum1, pk[k]);
-    }
-  } else {
-#pragma unroll
-    for (int k = 0; k < 16; ++k) {
-      const float2 d = __fadd2_rn(make_float2(__uint_as_float(v[2 * k]), __uint_as_float(v[2 * k + 1])), make_float2(-mx, -mx));
-      const float e0 = fa_exp2(d.x), e1 = fa_exp2(d.y);
-      if (SUM) { sum0 += e0; sum1 += e1; }
-      pk[k] = pack_bf16x2(e0, e1);
-    }
+  for (int k = 0; k < 16; ++k) {
+    const float2 d = __fadd2_rn(make_float2(__uint_as_float(v[2 * k]), __uint_as_float(v[2 * k + 1])), make_float2(-mx, -mx));
+    const float e0 = fa_exp2(d.x), e1 = fa_exp2(d.y);
+    if (SUM) { sum0 += e0; sum1 += e1; }
+    pk[k] = FMT == 1 ? pack_bf16x2(e0, e1) : pack_f16x2(e0, e1);
   }
 }
 

@@ -235,7 +235,9 @@ static int launch_mlp(const CUtensorMap& tmX, const CUtensorMap& tmW1, const CUt
     CSVIT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(Cfg::SMEM)));
   }
   const int tiles = (mp.M + kBM - 1) / kBM;
-  const int ctas = tiles < num_sms() ? tiles : num_sms();
+  static const int cap = [] { const char* e = getenv("CSVIT_MLP_CTAS"); return e ? atoi(e) : 0; }();      // ablation: fewer CTAs than SMs
+  int ctas = tiles < num_sms() ? tiles : num_sms();
+  if (cap > 0 && cap < ctas) ctas = cap;
   CSVIT_CUDA(launch_pdl(kern, dim3(ctas), dim3(kGemmThreads), Cfg::SMEM, stream, tmX, tmW1, tmW2, tmR, mp, ep));
   return 0;
 }

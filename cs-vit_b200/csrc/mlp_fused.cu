@@ -13,6 +13,7 @@
 //   warps 2-9  chunk epilogue (TMEM -> +b1 -> GELU -> 16 bit -> smem) and, after the last chunk, the fp32
 //              residual epilogue of the tile (same coalesced path as the GEMM engine)
 // TMEM: two 128-column GEMM1 accumulators + one C-column GEMM2 accumulator (<= 512 columns).
+#include <cstdio>
 #include <cstdlib>
 #include <type_traits>
 
@@ -41,13 +42,27 @@ struct MlpCfg {
 struct MlpParams {
   const float* b1;
   int M;
+  long long* trace;      // debugging (CSVIT_MLP_TRACE): clock64 stamps of CTA 0's first tiles, else null
 };
+constexpr int kMlpTraceTiles = 8;
+#ifdef CSVIT_MLP_TRACE_BUILD      // make EXTRA=-DCSVIT_MLP_TRACE_BUILD: clock64 stamps (they cost registers and a few per cent)
+#define MLP_STAMP(k) do { if (tr) tr[k] = clock64(); } while (0)
+#else
+#define MLP_STAMP(k) do { } while (0)
+#endif
 
-template <int FMT, int C>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+// SPLIT (C = 128): the chunk epilogue (GELU) and the tile's residual epilogue run on DIFFERENT warps and the GEMM2 accumulator is
+// double-buffered in TMEM (2 x 128 + 2 x 128 columns), so tile t's residual epilogue (~3500 cycles, mostly TMA waits) and the wait for
+// its last GEMM2 (~1100) overlap the GELU chunks of tile t + 1 instead of preceding them on the same eight warps
+// (profiles/r2_mlp_fused_trace.txt: 4 x 2000 + 1100 + 3500 cycles per tile in series).
+// Warp roles with SPLIT (warpgroup-aligned for setmaxnreg): 0 TMA, 1 MMA, 2-3 idle, 4-11 chunk epilogue, 12-19 residual epilogue.
+constexpr int kMlpThreadsSplit = 640;
+template <int FMT, int C, bool SPLIT>
+__global__ void __launch_bounds__(SPLIT ? kMlpThreadsSplit : kGemmThreads, 1)
 mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
                  const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmR, MlpParams mp, EpiParams ep) {
   using Cfg = MlpCfg<C>;
+  static_assert(!SPLIT || C == 128, "the second GEMM2 accumulator fits TMEM at C = 128 only");
   constexpr int KB1 = Cfg::KB1, N2 = Cfg::N2, NCH = Cfg::NCH, WS = Cfg::WSTAGES;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -62,9 +77,9 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   uint64_t* a2_empty = acc1_full + 6;         // [2]
   uint64_t* a1_full = acc1_full + 8;
   uint64_t* a1_empty = acc1_full + 9;
-  uint64_t* acc2_full = acc1_full + 10;
-  uint64_t* acc2_empty = acc1_full + 11;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc1_full + 12);
+  uint64_t* acc2_full = acc1_full + 10;       // [2] (SPLIT: one per GEMM2 accumulator; else only [0])
+  uint64_t* acc2_empty = acc1_full + 12;      // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc1_full + 14);
   uint64_t* rbar = bars + 32;                 // [kEpiWarps][2] residual-chunk arrivals (tma_f32 epilogue, C = 128)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -80,7 +95,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       mbar_init(&a2_full[b], kEpiWarps); mbar_init(&a2_empty[b], 1);
     }
     mbar_init(a1_full, 1); mbar_init(a1_empty, 1);
-    mbar_init(acc2_full, 1); mbar_init(acc2_empty, kEpiWarps);
+    for (int b = 0; b < 2; ++b) { mbar_init(&acc2_full[b], 1); mbar_init(&acc2_empty[b], kEpiWarps); }
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -91,7 +106,11 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   griddep_launch();      // PDL: the next kernel's prologue may overlap this kernel's tail ...
   griddep_wait();        // ... and this kernel touches global memory only after its predecessors have completed
   const uint32_t tm_acc2 = tmem_base + 256;
-
+  constexpr int EW0 = SPLIT ? 4 : 2;         // first chunk-epilogue warp
+  // SPLIT: the register pool is the launch allocation (640 x 96): warps 0-3 hand back 128 x 32 and the residual-epilogue warps 256 x 16 for
+  // 256 x 32 more in the GELU warps; every setmaxnreg sits at the top of its role's branch so that ptxas allocates that branch against the new limit
+  if (warp < EW0) {
+  if (SPLIT) asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");      // (40 made the issuer spill)
   if (warp == 0) {
     // ---------------- TMA producer ----------------
     if (lane == 0) {
@@ -103,14 +122,26 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         if (++s == WS) { s = 0; ph ^= 1u; }
       };
       uint32_t it = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
-        mbar_wait(a1_empty, (it & 1u) ^ 1u);
+      auto load_a1 = [&](int t, uint32_t i) {       // the xn tile of the CTA's i-th tile (single buffer: free once the previous tile's last GEMM1 completes)
+        mbar_wait(a1_empty, (i & 1u) ^ 1u);
         mbar_arrive_expect_tx(a1_full, Cfg::A1_BYTES);
         for (int kb = 0; kb < KB1; ++kb) tma_load_2d(smem + a1_off + size_t(kb) * kUnit, &tmX, a1_full, kb * 64, t * kBM);
-        for (int kb = 0; kb < KB1; ++kb) load_w(&tmW1, kb * 64, 0);                       // G1(0)
+      };
+      bool pre = false;      // the next tile's xn and GEMM1(0) weights were requested ahead (same order as the issuer's, below)
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+        if (!pre) {
+          load_a1(t, it);
+          for (int kb = 0; kb < KB1; ++kb) load_w(&tmW1, kb * 64, 0);                     // G1(0)
+        }
+        pre = false;
         for (int j = 0; j < NCH; ++j) {
-          if (j + 1 < NCH)
+          if (j + 1 < NCH) {
             for (int kb = 0; kb < KB1; ++kb) load_w(&tmW1, kb * 64, (j + 1) * 128);       // G1(j+1)
+          } else if (SPLIT && t + int(gridDim.x) < num_tiles) {
+            load_a1(t + int(gridDim.x), it + 1);                                          // next tile: xn, then G1(0)
+            for (int kb = 0; kb < KB1; ++kb) load_w(&tmW1, kb * 64, 0);
+            pre = true;
+          }
           for (int kb2 = 0; kb2 < 2; ++kb2)
             for (int n2 = 0; n2 < N2; ++n2) load_w(&tmW2, j * 128 + kb2 * 64, n2 * 128);   // G2(j)
         }
@@ -145,34 +176,97 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         if (fa_elect_one()) umma_commit(&acc1_full[b]);
         __syncwarp();
       };
+      bool pre = false;      // GEMM1(0) of this tile was issued during the previous tile's last chunk
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
-        mbar_wait(a1_full, it & 1u);
-        tc_fence_after();
-        gemm1(0);
+        if (!pre) {
+          mbar_wait(a1_full, it & 1u);
+          tc_fence_after();
+          gemm1(0);
+        }
+        pre = false;
         for (int j = 0; j < NCH; ++j) {
           const int b = j & 1;
           if (j + 1 < NCH) {
             gemm1(j + 1);
             if (j + 2 == NCH) { if (fa_elect_one()) umma_commit(a1_empty); __syncwarp(); }   // last GEMM1 of the tile issued: xn tile free once it completes
+          } else if (SPLIT && t + int(gridDim.x) < num_tiles) {
+            // "G1(j+1) before G2(j)" across the tile boundary (SPLIT only: with one set of epilogue warps the next tile's weight units
+            // would only delay this tile's last GEMM2 and its residual epilogue): the next tile's first GEMM1 goes ahead of this tile's last GEMM2, which
+            // waits for the last GELU chunk - otherwise the GELU warps idle ~1500 cycles at every tile start (clock64 trace)
+            mbar_wait(a1_full, (it + 1) & 1u);
+            tc_fence_after();
+            gemm1(0);
+            pre = true;
           }
           mbar_wait(&a2_full[b], use[b] & 1u);
           tc_fence_after();
-          if (j == 0) { mbar_wait(acc2_empty, (it & 1u) ^ 1u); tc_fence_after(); }
+          const uint32_t ab = SPLIT ? (it & 1u) : 0u;             // GEMM2 accumulator of this tile
+          if (j == 0) { mbar_wait(&acc2_empty[ab], ((SPLIT ? it >> 1 : it) & 1u) ^ 1u); tc_fence_after(); }
           for (int kb2 = 0; kb2 < 2; ++kb2)
             for (int n2 = 0; n2 < N2; ++n2)
-              mma_unit(base + a2_off + uint32_t(b * 2 + kb2) * kUnit, tm_acc2 + uint32_t(n2 * 128), j == 0 && kb2 == 0);
+              mma_unit(base + a2_off + uint32_t(b * 2 + kb2) * kUnit, tm_acc2 + ab * 128u + uint32_t(n2 * 128), j == 0 && kb2 == 0);
           if (fa_elect_one()) {
             umma_commit(&a2_empty[b]);
-            if (j == NCH - 1) umma_commit(acc2_full);
+            if (j == NCH - 1) umma_commit(&acc2_full[ab]);
           }
           __syncwarp();
           ++use[b];
         }
       }
     }
+  }
+  } else if (SPLIT && warp >= 12) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
+    // ---------------- residual epilogue of tile `it` from GEMM2 accumulator it & 1, while the GELU warps work on tile it + 1 ----------------
+    const int e = warp - 12;
+    const int quad = warp & 3;
+    const int half = e >> 2;
+    uint8_t* stg = smem + stg_off + e * Cfg::STG_BUFS * kStageBufBytes;
+    uint32_t it = 0, rph = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+      // the tma_f32 form of gemm.cuh::epilogue_tile for this kernel's one case (C = 128: two 32 x 32 fp32 chunks per warp, both
+      // residual chunks requested at tile start) - written out here so that this branch compiles against 96 registers without spills
+      const uint32_t ab = it & 1u;
+      const int row0 = t * kBM + quad * 32, colbase = half * 64;
+      tma_f32_prefetch<C>(ep, &tmR, stg, rbar + 2 * e, t, 0, quad, half, lane);
+      mbar_wait(&acc2_full[ab], (it >> 1) & 1u);
+      tc_fence_after();
+      const uint32_t t_addr = tm_acc2 + ab * 128u + (uint32_t(quad * 32) << 16) + uint32_t(colbase);
+#pragma unroll 1
+      for (int ci = 0; ci < 2; ++ci) {
+        uint8_t* buf = stg + ci * kStageBufBytes;
+        uint32_t rr[32];
+        tmem_ld_32x32(t_addr + uint32_t(32 * ci), rr);
+        tmem_ld_wait();
+        if (row0 < ep.M) {
+          mbar_wait(&rbar[2 * e + ci], (rph >> ci) & 1u);
+          rph ^= (1u << ci);
+        }
+        const float4* b4 = reinterpret_cast<const float4*>(ep.bias + colbase + 32 * ci);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          float4* pp = reinterpret_cast<float4*>(buf + lane * 128 + ((k ^ (lane & 7)) << 4));
+          const float4 bb = __ldg(b4 + k);
+          float4 x0 = *pp;
+          x0.x += __uint_as_float(rr[4 * k]) + bb.x; x0.y += __uint_as_float(rr[4 * k + 1]) + bb.y;
+          x0.z += __uint_as_float(rr[4 * k + 2]) + bb.z; x0.w += __uint_as_float(rr[4 * k + 3]) + bb.w;
+          *pp = x0;
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0 && row0 < ep.M) {
+          tma_store_2d(&tmR, buf, colbase + 32 * ci, row0);
+          tma_store_commit();
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc2_empty[ab]);
+    }
   } else {
+    if (SPLIT) asm volatile("setmaxnreg.inc.sync.aligned.u32 128;");
     // ---------------- epilogues ----------------
-    const int e = warp - 2;
+    const int e = warp - EW0;
     const int quad = warp & 3;
     const int half = e >> 2;
     const int r = quad * 32 + lane;           // row of the tile owned by this thread
@@ -182,26 +276,35 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     uint32_t use[2] = {0, 0};
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
       // residual chunks of this tile requested now: they land while the hidden chunks are being processed
-      if (ep.tma_f32) tma_f32_prefetch<C>(ep, &tmR, stg, rbar + 2 * e, t, 0, quad, half, lane);
-      else prefetch_resid_tile<C>(ep, t, 0, quad, half, lane);   // C = 256 (no room for a second staging buffer): at least pull the lines into L2
+      if (!SPLIT) {
+        if (ep.tma_f32) tma_f32_prefetch<C>(ep, &tmR, stg, rbar + 2 * e, t, 0, quad, half, lane);
+        else prefetch_resid_tile<C>(ep, t, 0, quad, half, lane);   // C = 256 (no room for a second staging buffer): at least pull the lines into L2
+      }
+#ifdef CSVIT_MLP_TRACE_BUILD
+      long long* tr = (mp.trace && blockIdx.x == 0 && e == 0 && lane == 0 && it < kMlpTraceTiles) ? mp.trace + it * 64 : nullptr;
+#endif
       for (int j = 0; j < NCH; ++j) {
         const int b = j & 1;
+        MLP_STAMP(4 * j);
         mbar_wait(&acc1_full[b], use[b] & 1u);
         tc_fence_after();
-        uint32_t pk[32];                      // this thread's 64 hidden columns, packed to 16 bit
-        {   // both 32-column TMEM loads are in flight before the single wait (the chunk epilogue is latency-bound, not issue-bound)
-          uint32_t rr0[32], rr1[32];
+        MLP_STAMP(4 * j + 1);
+        uint32_t rr0[32], rr1[32];             // both 32-column TMEM loads are in flight before the single wait
+        {
           const uint32_t ta = tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(b * 128 + half * 64);
           tmem_ld_32x32(ta, rr0);
           tmem_ld_32x32(ta + 32u, rr1);
           tmem_ld_wait();
-          epi_bias_gelu_pack32(mp.b1, bf, j * 128 + half * 64, rr0, pk);
-          epi_bias_gelu_pack32(mp.b1, bf, j * 128 + half * 64 + 32, rr1, pk + 16);
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&acc1_empty[b]);            // accumulator drained: GEMM1(j+2) may overwrite it
+        if (lane == 0) mbar_arrive(&acc1_empty[b]);            // the accumulator is in registers: GEMM1(j+2) may overwrite it
+        uint32_t pk[32];                      // this thread's 64 hidden columns, packed to 16 bit
+        epi_bias_gelu_pack32(mp.b1, bf, j * 128 + half * 64, rr0, pk);
+        epi_bias_gelu_pack32(mp.b1, bf, j * 128 + half * 64 + 32, rr1, pk + 16);
+        MLP_STAMP(4 * j + 2);
         mbar_wait(&a2_empty[b], (use[b] & 1u) ^ 1u);           // GEMM2(j-2) has finished reading this A2 buffer
+        MLP_STAMP(4 * j + 3);
         uint8_t* dst = smem + a2_off + uint32_t(b * 2 + half) * kUnit + r * 128;
 #pragma unroll
         for (int ci = 0; ci < 8; ++ci)
@@ -211,26 +314,35 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         if (lane == 0) mbar_arrive(&a2_full[b]);
         ++use[b];
       }
-      // tile epilogue: acc2 (+ b2) + residual -> x, coalesced fp32 path of the GEMM engine (waits on acc2_full itself)
-      epilogue_tile<C>(ep, &tmR, stg, tm_acc2, acc2_full, it & 1u, t, 0, quad, half, lane, 1, nullptr, &tmR, rbar + 2 * e, &rph, true);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(acc2_empty);
+      MLP_STAMP(4 * NCH);
+      if (!SPLIT) {
+#ifdef CSVIT_MLP_TRACE_BUILD
+        if (tr) { mbar_wait(&acc2_full[0], it & 1u); tr[4 * NCH + 1] = clock64(); }
+#endif
+        // tile epilogue: acc2 (+ b2) + residual -> x, coalesced fp32 path of the GEMM engine (waits on acc2_full itself)
+        epilogue_tile<C>(ep, &tmR, stg, tm_acc2, &acc2_full[0], it & 1u, t, 0, quad, half, lane, 1, nullptr, &tmR, rbar + 2 * e, &rph, true);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc2_empty[0]);
+      } else {
+        MLP_STAMP(4 * NCH + 1);
+      }
+      MLP_STAMP(4 * NCH + 2);
     }
   }
 
-  if (ep.tma_f32 && warp >= 2 && lane == 0) tma_store_wait_all();
+  if (ep.tma_f32 && warp >= (SPLIT ? 12 : 2) && lane == 0) tma_store_wait_all();
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
-template <int FMT, int C>
-static int launch_mlp(const CUtensorMap& tmX, const CUtensorMap& tmW1, const CUtensorMap& tmW2, const CUtensorMap& tmR,
+template <int FMT, int C, bool SPLIT>
+static int launch_mlp_s(const CUtensorMap& tmX, const CUtensorMap& tmW1, const CUtensorMap& tmW2, const CUtensorMap& tmR,
                       const MlpParams& mp, const EpiParams& ep, cudaStream_t stream) {
   using Cfg = MlpCfg<C>;
   static DeviceOnce once;
-  auto kern = mlp_fused_kernel<FMT, C>;
+  auto kern = mlp_fused_kernel<FMT, C, SPLIT>;
   if (once.first()) {
     CSVIT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(Cfg::SMEM)));
   }
@@ -238,8 +350,17 @@ static int launch_mlp(const CUtensorMap& tmX, const CUtensorMap& tmW1, const CUt
   static const int cap = [] { const char* e = getenv("CSVIT_MLP_CTAS"); return e ? atoi(e) : 0; }();      // ablation: fewer CTAs than SMs
   int ctas = tiles < num_sms() ? tiles : num_sms();
   if (cap > 0 && cap < ctas) ctas = cap;
-  CSVIT_CUDA(launch_pdl(kern, dim3(ctas), dim3(kGemmThreads), Cfg::SMEM, stream, tmX, tmW1, tmW2, tmR, mp, ep));
+  CSVIT_CUDA(launch_pdl(kern, dim3(ctas), dim3(SPLIT ? kMlpThreadsSplit : kGemmThreads), Cfg::SMEM, stream, tmX, tmW1, tmW2, tmR, mp, ep));
   return 0;
+}
+template <int FMT, int C>
+static int launch_mlp(const CUtensorMap& tmX, const CUtensorMap& tmW1, const CUtensorMap& tmW2, const CUtensorMap& tmR,
+                      const MlpParams& mp, const EpiParams& ep, cudaStream_t stream) {
+  if constexpr (C == 128) {      // CSVIT_MLP_SPLIT=0: chunk and residual epilogue on the same eight warps (ablation)
+    static const bool split = [] { const char* e = getenv("CSVIT_MLP_SPLIT"); return !(e && e[0] == '0'); }();
+    if (split && ep.tma_f32 && ep.resid && ep.bias) return launch_mlp_s<FMT, C, true>(tmX, tmW1, tmW2, tmR, mp, ep, stream);
+  }
+  return launch_mlp_s<FMT, C, false>(tmX, tmW1, tmW2, tmR, mp, ep, stream);
 }
 
 int launch_mlp_fused(const void* xn, long long ldxn, const void* W1, long long ldw1, const float* b1, const void* W2,
@@ -252,7 +373,9 @@ int launch_mlp_fused(const void* xn, long long ldxn, const void* W1, long long l
   ep.bias = b2; ep.resid = x; ep.out = x; ep.ldo = ldx; ep.ldr = ldx; ep.out_dtype = DT_F32; ep.act = ACT_NONE;
   ep.M = M; ep.N = C; ep.vec_ok = 1; ep.tma_store = 0; ep.coalesced = 1;
   ep.map_mode = ROWMAP_IDENTITY; ep.geom = make_geom(1, 1, 1, 0);
-  MlpParams mp{b1, M};
+  MlpParams mp{b1, M, nullptr};
+  static const char* trace_path = getenv("CSVIT_MLP_TRACE");
+  if (trace_path) { CSVIT_CUDA(cudaMalloc(&mp.trace, kMlpTraceTiles * 64 * sizeof(long long))); CSVIT_CUDA(cudaMemsetAsync(mp.trace, 0, kMlpTraceTiles * 64 * sizeof(long long), stream)); }
   CUtensorMap tmX, tmW1, tmW2;
   if (int e = make_tmap(&tmX, xn, ldxn, M, C, dtype, kBM, true)) return e;
   if (int e = make_tmap(&tmW1, W1, ldw1, 4ll * C, C, dtype, 128, true)) return e;
@@ -265,6 +388,31 @@ int launch_mlp_fused(const void* xn, long long ldxn, const void* W1, long long l
     if (int e = make_tmap(&tmR, x, ldx, M, C, DT_F32, 32, false)) return e;
   }
   const bool bf = dtype == DT_BF16;
+  if (trace_path) {      // debugging: one traced launch, stamps written as text (cycles relative to the first stamp)
+    int e = C == 128 ? (bf ? launch_mlp<1, 128>(tmX, tmW1, tmW2, tmR, mp, ep, stream) : launch_mlp<0, 128>(tmX, tmW1, tmW2, tmR, mp, ep, stream))
+                     : (bf ? launch_mlp<1, 256>(tmX, tmW1, tmW2, tmR, mp, ep, stream) : launch_mlp<0, 256>(tmX, tmW1, tmW2, tmR, mp, ep, stream));
+    if (e) return e;
+    CSVIT_CUDA(cudaStreamSynchronize(stream));
+    long long h[kMlpTraceTiles * 64];
+    CSVIT_CUDA(cudaMemcpy(h, mp.trace, sizeof(h), cudaMemcpyDeviceToHost));
+    cudaFree(mp.trace);
+    if (FILE* f = fopen(trace_path, "a")) {
+      const int nch = 4 * C / 128;
+      fprintf(f, "# mlp_fused C=%d: epilogue warp 0 of CTA 0; per chunk: wait acc1 | TMEM load + GELU | wait A2 buffer | store; then wait acc2 | residual epilogue\n", C);
+      for (int t = 0; t < kMlpTraceTiles; ++t) {
+        const long long* r = h + t * 64;
+        if (!r[0]) continue;
+        fprintf(f, "tile %d start %8lld:", t, r[0] - h[0]);
+        for (int j = 0; j < nch; ++j) {
+          const long long nxt = j + 1 < nch ? r[4 * j + 4] : r[4 * nch];
+          fprintf(f, "  [%lld %lld %lld %lld]", r[4 * j + 1] - r[4 * j], r[4 * j + 2] - r[4 * j + 1], r[4 * j + 3] - r[4 * j + 2], nxt - r[4 * j + 3]);
+        }
+        fprintf(f, "  acc2 wait %lld, epilogue %lld, total %lld\n", r[4 * nch + 1] - r[4 * nch], r[4 * nch + 2] - r[4 * nch + 1], r[4 * nch + 2] - r[0]);
+      }
+      fclose(f);
+    }
+    return 0;
+  }
   if (C == 128) return bf ? launch_mlp<1, 128>(tmX, tmW1, tmW2, tmR, mp, ep, stream) : launch_mlp<0, 128>(tmX, tmW1, tmW2, tmR, mp, ep, stream);
   return bf ? launch_mlp<1, 256>(tmX, tmW1, tmW2, tmR, mp, ep, stream) : launch_mlp<0, 256>(tmX, tmW1, tmW2, tmR, mp, ep, stream);
 }

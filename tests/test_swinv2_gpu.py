@@ -62,7 +62,7 @@ def test_swinv2_window_attention(ops, H, ws, heads, shift, dtype):
 
 
 @pytest.mark.parametrize("H,heads,shift,B", [(32, 4, 0, 2), (32, 4, 8, 2), (64, 1, 8, 1), (16, 16, 0, 3), (16, 3, 0, 2), (48, 2, 8, 1),
-                                             (32, 8, 8, 5)])
+                                             (32, 8, 8, 5), (32, 8, 8, 13)])      # the last case is large enough for the CTA-pair GEMM
 @pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
 def test_swinv2_qkv_and_tcgen05_attention(ops, H, heads, shift, B, dtype):
     """csvit_swinv2_qkv (cosine normalisation in the GEMM epilogue) + csvit_swinv2_attn_tc (tcgen05, P as a TMEM operand) against

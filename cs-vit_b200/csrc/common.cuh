@@ -219,7 +219,11 @@ __device__ __forceinline__ void cluster_sync_all() {
 
 // Programmatic dependent launch (errors.h::launch_pdl): let the next kernel of the stream be scheduled / wait until every kernel
 // before this one has completed and its writes are visible.  No-ops for kernels launched without the attribute.
+#ifdef CSVIT_PDL_NO_TRIGGER      // experiment: no early trigger - the dependent kernel is released as this kernel's CTAs exit
+__device__ __forceinline__ void griddep_launch() {}
+#else
 __device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
 __device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // One lane of a CONVERGED warp.  The MMA issuers walk their loops with the whole warp and issue under this predicate: ptxas then emits

@@ -20,7 +20,10 @@
 // warps 4-19 four softmax warpgroups: global head gh uses TMEM slot gh % 4 (128 columns) and warpgroup gh % 4, continuously
 // across tile boundaries, so four heads are in flight and the tensor pipe, the MUFU/ALU work and the loads overlap.
 // Per token the kernel reads 6C bytes and writes 2C: it is HBM-bound (8C B/token) from C = 128 to 1024.
+#include <cstdio>
+#include <cstdlib>
 #include <type_traits>
+#include <vector>
 
 #include "attn_common.cuh"
 #include "errors.h"
@@ -48,7 +51,14 @@ struct AcParams {
   int token_order;       // 1: ctx rows in token order (window_reverse + roll(+s) folded in); 0: window order like qkv
   float qscale;          // log2(e) / sqrt(32), or 1 when the Q/K/V GEMM already applied it to q
   WinGeom g;
+  long long* trace;      // debugging (build with -DCSVIT_AC_TRACE_BUILD, run with CSVIT_AC_TRACE=<file>): clock64 stamps of CTA 0
 };
+constexpr int AC_TRACE_HEADS = 24;
+#ifdef CSVIT_AC_TRACE_BUILD
+#define AC_STAMP(k) do { if (tr) tr[k] = clock64(); } while (0)
+#else
+#define AC_STAMP(k) do { } while (0)
+#endif
 
 __device__ __forceinline__ uint64_t ac_mnmajor_desc(uint32_t smem_addr) {
   // MN-major SWIZZLE_128B operand, N = 128 = two 128-byte chunks: LBO = chunk stride (64 key rows), SBO = 8 key rows
@@ -216,6 +226,10 @@ swin_attn_core_kernel(const __grid_constant__ CUtensorMap tmQ, AcParams p) {
       const int ti = (u_begin + gp) / PAIRS, hp = (u_begin + gp) - ti * PAIRS, h = 2 * hp + e;
       const uint32_t ph = n & 1u;
       uint8_t* sb = smem + size_t(gp % AC_NST) * AC_STAGE;
+#ifdef CSVIT_AC_TRACE_BUILD
+      long long* tr = (p.trace && blockIdx.x == 0 && quad == 0 && lane == 0 && n < AC_TRACE_HEADS) ? p.trace + (g * AC_TRACE_HEADS + n) * 8 : nullptr;
+#endif
+      AC_STAMP(0);
       if (ti != cur_ti) {   // first head of a tile for this group: where the row goes, and its mask
         cur_ti = ti;
         const int wg = 2 * ti + wdx;
@@ -234,6 +248,7 @@ swin_attn_core_kernel(const __grid_constant__ CUtensorMap tmQ, AcParams p) {
       {
         mbar_wait(&s_full[g], ph);
         tc_fence_after();
+        AC_STAMP(1);
         uint32_t s0[32], s1[16], s2;
         tmem_ld_32x32(ts, s0);
         tmem_ld_32x16(ts + 32u, s1);
@@ -248,7 +263,9 @@ swin_attn_core_kernel(const __grid_constant__ CUtensorMap tmQ, AcParams p) {
         sv[48] = __uint_as_float(s2);
         sv[49] = 0.0f;
         {   // + relative-position bias of this query slot (padding rows read a real row, their output is dropped)
+          AC_STAMP(2);
           mbar_wait(&b_full[g], ph);
+          AC_STAMP(3);
           const uint4* brow = reinterpret_cast<const uint4*>(smem + AC_BIAS_OFF + uint32_t(g) * FA_BIAS_STAGE + (j < FA_L ? j : 0) * 112);
 #pragma unroll
           for (int c = 0; c < 7; ++c) {
@@ -302,11 +319,13 @@ swin_attn_core_kernel(const __grid_constant__ CUtensorMap tmQ, AcParams p) {
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_full[g]);
+        AC_STAMP(4);
       }
       // ---- E: O' / rowsum -> context row
       {
         mbar_wait(&o_full[g], ph);
         tc_fence_after();
+        AC_STAMP(5);
         uint32_t o[32];
         tmem_ld_32x32(ts + uint32_t(e) * 32u, o);
         tmem_ld_wait();
@@ -324,6 +343,7 @@ swin_attn_core_kernel(const __grid_constant__ CUtensorMap tmQ, AcParams p) {
                                 pack16(bf, __uint_as_float(o[8 * q + 6]) * inv, __uint_as_float(o[8 * q + 7]) * inv));
         }
       }
+      AC_STAMP(6);
     }
   }
 
@@ -355,6 +375,7 @@ int launch_swin_attn_core(const void* qkv, long long ldq, const void* bias_log2,
   if (windows <= 0) return 0;
   CSVIT_REQUIRE(windows * FA_L < (1ll << 31), "swin_attn_core: too many rows");
   AcParams p{};
+  p.trace = nullptr;
   p.bias = bias_log2; p.ctx = ctx;
   p.num_windows = static_cast<int>(windows); p.nW = nW; p.C = C; p.heads = heads;
   p.token_order = token_order ? 1 : 0;
@@ -363,6 +384,32 @@ int launch_swin_attn_core(const void* qkv, long long ldq, const void* bias_log2,
   CUtensorMap tmQ;
   if (int e = make_tmap(&tmQ, qkv, ldq, windows * FA_L, 3ll * C, dtype, FA_L, false)) return e;
   const bool bf = dtype == DT_BF16;
+#ifdef CSVIT_AC_TRACE_BUILD
+  if (const char* path = getenv("CSVIT_AC_TRACE")) {
+    const size_t nb = size_t(AC_NSLOT) * AC_TRACE_HEADS * 8 * sizeof(long long);
+    CSVIT_CUDA(cudaMalloc(&p.trace, nb));
+    CSVIT_CUDA(cudaMemsetAsync(p.trace, 0, nb, stream));
+    if (int e = bf ? launch_ac<1, false>(tmQ, p, stream) : launch_ac<0, false>(tmQ, p, stream)) return e;
+    CSVIT_CUDA(cudaStreamSynchronize(stream));
+    std::vector<long long> h(nb / sizeof(long long));
+    CSVIT_CUDA(cudaMemcpy(h.data(), p.trace, nb, cudaMemcpyDeviceToHost));
+    cudaFree(p.trace);
+    if (FILE* f = fopen(path, "w")) {
+      long long t0 = 0;
+      for (long long v : h) if (v && (!t0 || v < t0)) t0 = v;
+      fprintf(f, "# swin_attn_core, CTA 0, one warp per softmax group; per head: loop top | S wait | ld + prep | bias wait | softmax + P store | PV wait | E\n");
+      for (int g = 0; g < AC_NSLOT; ++g)
+        for (int n = 0; n < AC_TRACE_HEADS; ++n) {
+          const long long* r = h.data() + (g * AC_TRACE_HEADS + n) * 8;
+          if (!r[0]) continue;
+          fprintf(f, "g%d n%2d start %8lld | %6lld %6lld %6lld %6lld %6lld %6lld | total %6lld\n", g, n, r[0] - t0, r[1] - r[0], r[2] - r[1], r[3] - r[2],
+                  r[4] - r[3], r[5] - r[4], r[6] - r[5], r[6] - r[0]);
+        }
+      fclose(f);
+    }
+    return 0;
+  }
+#endif
   if (q_prescaled) return bf ? launch_ac<1, false>(tmQ, p, stream) : launch_ac<0, false>(tmQ, p, stream);
   return bf ? launch_ac<1, true>(tmQ, p, stream) : launch_ac<0, true>(tmQ, p, stream);
 }

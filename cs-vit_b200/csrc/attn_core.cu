@@ -53,8 +53,8 @@ struct AcParams {
   WinGeom g;
   long long* trace;      // debugging (build with -DCSVIT_AC_TRACE_BUILD, run with CSVIT_AC_TRACE=<file>): clock64 stamps of CTA 0
 };
-constexpr int AC_TRACE_HEADS = 24;
 #ifdef CSVIT_AC_TRACE_BUILD
+constexpr int AC_TRACE_HEADS = 24;
 #define AC_STAMP(k) do { if (tr) tr[k] = clock64(); } while (0)
 #else
 #define AC_STAMP(k) do { } while (0)
@@ -221,9 +221,12 @@ swin_attn_core_kernel(const __grid_constant__ CUtensorMap tmQ, AcParams p) {
     int cur_ti = -1;
     const int total_heads = 2 * total_pairs;
     uint32_t n = 0;
+    // (tile, head pair) of this group's current head, advanced without divisions: the group's heads are AC_NSLOT = 4 apart = 2 pairs
+    int ti = (u_begin + (g >> 1)) / PAIRS, hp = (u_begin + (g >> 1)) - ti * PAIRS;
+    const int ti_step = 2 / PAIRS, hp_step = 2 % PAIRS;
     for (int gh = g; gh < total_heads; gh += AC_NSLOT, ++n) {
       const int gp = gh >> 1, e = gh & 1;
-      const int ti = (u_begin + gp) / PAIRS, hp = (u_begin + gp) - ti * PAIRS, h = 2 * hp + e;
+      const int h = 2 * hp + e;
       const uint32_t ph = n & 1u;
       uint8_t* sb = smem + size_t(gp % AC_NST) * AC_STAGE;
 #ifdef CSVIT_AC_TRACE_BUILD
@@ -344,6 +347,8 @@ swin_attn_core_kernel(const __grid_constant__ CUtensorMap tmQ, AcParams p) {
         }
       }
       AC_STAMP(6);
+      ti += ti_step; hp += hp_step;
+      if (hp >= PAIRS) { hp -= PAIRS; ++ti; }
     }
   }
 

@@ -14,12 +14,18 @@
 //   X1       thread (row, key half): + bias (one LDS per logit, conflict-free: the table is padded to 48-float rows) [+ mask], row
 //            max, logits written back to TMEM in place; the two halves of a row meet in shared memory for the max
 //   X2       exp2(logit - max) -> 16-bit P written to TMEM over the consumed logits (tcgen05.st, two keys per column)
-//   PV       O'[128 x 64] = P[128 x 256] V'[256 x 64] with P read FROM TMEM as the A operand (16 MMAs, K = 16), V' MN-major
-//   E        O'[:, 32 e ..] / rowsum -> 16 bit -> ctx row (token order: window_reverse + un-shift folded into the address)
+//   PV       O'[128 x 32] = P[128 x 256] V_e[256 x 32] with P read FROM TMEM as the A operand (16 MMAs, K = 16); V' is MN-major and the B
+//            descriptor starts 64 e bytes into the pair's 128-byte rows, so only the head's own value columns are multiplied;
+//            16 more MMAs of P against a 2 KB tile of ones put the row sums of the ROUNDED probabilities next to O' (N = 16)
+//   E        O' / rowsum -> 16 bit -> ctx row (token order: window_reverse + un-shift folded into the address)
 // P never touches shared memory: the softmax thread that owns a row writes it where the tensor core reads it.
-// Roles: warp 0 TMA producer (2-stage ring), warp 1 MMA issuer, warps 4-19 = two softmax sets (one per TMEM slot / query tile of the
-// head) of two warpgroups (key halves): both query tiles of a head are in flight, so the tensor pipe, the MUFU / LDS work and the
-// loads overlap.  The kernel is bound by the per-logit work of X1 / X2 (about 5 issue slots per logit), not by bytes or MMAs.
+// TMEM slot (256 columns): S in 0-255; P of key half hf in 128 hf .. 128 hf + 63 (over logits already consumed); O' in 64-95 and the row
+// sums in 96-111 (both written only after every logit of the tile has been read).
+// Roles: warp 0 TMA producer (2-stage ring), warp 1 MMA issuer (whole warp converged, one elected lane issues), warps 4-19 = two
+// softmax sets (one per TMEM slot / query tile of the head) of two warpgroups (key halves).  X2 is MUFU-heavy and the sets share the
+// SM's MUFU pipes: they take turns on X2 (named-barrier ping-pong), so that one set's exponentials hide the other's X1, E and MMA round
+// trips - left alone, both sets run X2 together and then idle together (clock64 trace, profiles/r2_swinv2_attn_tc_trace.txt).
+// The kernel is bound by the instructions of X1 / X2 (about 4.5 issue slots per logit), not by bytes, MMAs or MUFU throughput.
 #include <cstdio>
 #include <cstdlib>
 #include <type_traits>

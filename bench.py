@@ -459,9 +459,10 @@ def finetune_measure(a, world, rank, local, dev, steps, warmup, comm="auto", spl
 
     B = a.batch if a.batch != BATCH else 32
     tmp = tempfile.mkdtemp(prefix=f"csvit_bench_ft_{rank}_")
-    bdir = make_random_backbone_dir(os.path.join(tmp, a.variant), a.variant, seed=0)
+    S = image_side(a.variant)
+    bdir = make_random_backbone_dir(os.path.join(tmp, a.variant), a.variant, seed=0, image_size=S)
     torch.manual_seed(0)
-    model = Poser(bdir, image_size=224, mano_layer=SyntheticMANO(), spatial_layer_type="encoder", persp_decorate="patch",
+    model = Poser(bdir, image_size=S, mano_layer=SyntheticMANO(), spatial_layer_type="encoder", persp_decorate="patch",
                   precision=a.precision, num_latent_layer=a.latent_layers or None)
     randomize_head_(model)
     model.phase(Poser.TrainingPhase.SPATIAL)          # train mode: batch-statistics BatchNorm, trainable spatial modules
@@ -471,7 +472,7 @@ def finetune_measure(a, world, rank, local, dev, steps, warmup, comm="auto", spl
     reducer = GradReducer(trainable, comm=comm)
     graphed = not a.no_graph
     opt = torch.optim.AdamW(trainable, lr=scaled_lr(1e-5, world, B), fused=True, capturable=graphed)
-    batch = {k: v.to(dev) for k, v in make_inputs(B, 1, 224, seed=100 + rank, labels=True).items()}
+    batch = {k: v.to(dev) for k, v in make_inputs(B, 1, S, seed=100 + rank, labels=True).items()}
 
     def barrier():
         if world > 1:
@@ -509,12 +510,13 @@ def finetune_measure(a, world, rank, local, dev, steps, warmup, comm="auto", spl
     value = world * B * steps / (ms.item() / 1e3)
     peak_tf, _, _ = peaks()
     res = {
-        "metric": "images/sec Swin-B spatial finetune step (fwd+bwd+AdamW) bs32/GPU", "value": round(value, 1), "unit": "images/s",
+        "metric": ("images/sec Swin-B" if a.variant == "swin_b" else f"images/sec {a.variant}") + f" spatial finetune step (fwd+bwd+AdamW) bs{B}/GPU",
+        "value": round(value, 1), "unit": "images/s",
         "n_gpus": world, "steps": steps, "warmup": max(warmup, 2), "ms_per_step": round(ms.item() / steps, 3),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": a.precision, "data": "synthetic",
         "config": {"launch": "one CUDA graph per step (cs_vit.train.GraphedFinetuneStep)" if graphed else "eager",
                    "workload": f"{a.variant} spatial model finetune step (Poser.forward loss, backward, grad clip 5.0, fused AdamW), "
-                               f"batch {B}/GPU, 224x224, train-mode BatchNorm"
+                               f"batch {B}/GPU, {S}x{S}, train-mode BatchNorm"
                                + (f", latent consistency branch with {a.latent_layers} layers ('ti' configuration)" if a.latent_layers else ""),
                    "global_batch": B * world, "parallelism": f"dp{world}",
                    "allreduce": f"{nparams * 4 / 1e6:.1f} MB fp32 gradients in {len(reducer.bucket_summary())} flat buckets, reduced from "

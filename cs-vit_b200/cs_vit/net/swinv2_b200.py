@@ -122,6 +122,8 @@ class Swinv2BackboneB200(nn.Module):
         self.precision = precision
         # 16-bit inference on 16 x 16 windows: the tcgen05 attention kernel (CSVIT_V2_ATTN=mma selects round 1's mma.sync kernel: ablation)
         self._v2_tcgen05 = os.environ.get("CSVIT_V2_ATTN", "tcgen05") != "mma"
+        # differentiable path, 16-bit modes: fused library attention for the cosine-attention core (CSVIT_V2_TRAIN_ATTN=math: materialised scores)
+        self._v2_train_sdpa = os.environ.get("CSVIT_V2_TRAIN_ATTN", "sdpa") != "math"
         c0, eps = config.embed_dim, config.layer_norm_eps
         self.embeddings = _holder(
             patch_embeddings=_holder(projection=nn.Conv2d(3, c0, kernel_size=4, stride=4)),
@@ -287,15 +289,32 @@ class Swinv2BackboneB200(nn.Module):
                 kk = ag.linear(xw, sa.key.weight, None, impl=impl)
                 v = ag.linear(xw, sa.value.weight, sa.value.bias, impl=impl)
                 qh, kh, vh = (t.view(n * nW, L, heads, C // heads).transpose(1, 2) for t in (q, kk, v))
-                scores = torch.nn.functional.normalize(qh, dim=-1) @ torch.nn.functional.normalize(kh, dim=-1).transpose(-1, -2)
-                scores = scores * torch.clamp(sa.logit_scale, max=math.log(1.0 / 0.01)).exp()                         # V2:450-453
+                lscale = torch.clamp(sa.logit_scale, max=math.log(1.0 / 0.01)).exp()                                 # V2:450-453
                 table = sa.continuous_position_bias_mlp(coords)                                                      # [(2ws-1)^2, heads]
                 bias = 16.0 * torch.sigmoid(table[rel_index].view(L, L, heads).permute(2, 0, 1))                     # V2:455-460
-                scores = scores + bias[None]
-                if shift > 0:      # HF adds the shift mask twice (V2:462-468)
-                    mask = self._w(f"mask{H}_{ws}_{shift}", [], lambda: ops.shift_mask(H, H, ws, shift, device=dev))
-                    scores = (scores.view(n, nW, heads, L, L) + 2.0 * mask[None, :, None]).view(n * nW, heads, L, L)
-                ctx = (scores.softmax(dim=-1) @ vh).transpose(1, 2).reshape(n * N, C)
+                mask = self._w(f"mask{H}_{ws}_{shift}", [], lambda: ops.shift_mask(H, H, ws, shift, device=dev)) if shift > 0 else None
+                if self._v2_train_sdpa and not self._fp32:
+                    # 16-bit modes: the core as ONE fused library attention (torch SDPA, memory-efficient backend) instead of materialised
+                    # [windows, heads, L, L] fp32 scores forward and backward.  q is normalised and scaled, k normalised, in fp32 before the
+                    # 16-bit cast; (window, head) is folded into SDPA's head dimension so that the additive term bias (+ 2 * shift mask,
+                    # HF adds the mask twice: V2:462-468) broadcasts over the images and receives its gradient.
+                    act = self._act_dtype
+                    d = C // heads
+                    qn = torch.nn.functional.normalize(qh, dim=-1) * lscale.view(1, heads, 1, 1)
+                    kn = torch.nn.functional.normalize(kh, dim=-1)
+                    add = bias[None].expand(nW, heads, L, L) if mask is None else bias[None] + 2.0 * mask[:, None]
+                    add = add.reshape(1, nW * heads, L, L).to(act)
+                    q4, k4, v4 = (t.reshape(n, nW * heads, L, d).to(act) for t in (qn, kn, vh))
+                    from torch.nn.attention import SDPBackend, sdpa_kernel
+                    with sdpa_kernel([SDPBackend.EFFICIENT_ATTENTION, SDPBackend.MATH]):     # (the automatic choice takes the math path here)
+                        ctx = torch.nn.functional.scaled_dot_product_attention(q4.contiguous(), k4.contiguous(), v4.contiguous(), attn_mask=add, scale=1.0)
+                    ctx = ctx.reshape(n * nW, heads, L, d).transpose(1, 2).reshape(n * N, C).float()
+                else:
+                    scores = torch.nn.functional.normalize(qh, dim=-1) @ torch.nn.functional.normalize(kh, dim=-1).transpose(-1, -2)
+                    scores = scores * lscale + bias[None]
+                    if mask is not None:
+                        scores = (scores.view(n, nW, heads, L, L) + 2.0 * mask[None, :, None]).view(n * nW, heads, L, L)
+                    ctx = (scores.softmax(dim=-1) @ vh).transpose(1, 2).reshape(n * N, C)
                 proj = blk.attention.output.dense
                 ya = ag.linear(ctx.contiguous(), proj.weight, proj.bias, impl=impl)
                 ya = ya.view(n, N, C)[:, inv].reshape(n * N, C)                    # window_reverse + roll(+s)

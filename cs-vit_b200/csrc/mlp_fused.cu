@@ -374,7 +374,11 @@ int launch_mlp_fused(const void* xn, long long ldxn, const void* W1, long long l
   ep.M = M; ep.N = C; ep.vec_ok = 1; ep.tma_store = 0; ep.coalesced = 1;
   ep.map_mode = ROWMAP_IDENTITY; ep.geom = make_geom(1, 1, 1, 0);
   MlpParams mp{b1, M, nullptr};
+#ifdef CSVIT_MLP_TRACE_BUILD
   static const char* trace_path = getenv("CSVIT_MLP_TRACE");
+#else
+  static const char* trace_path = nullptr;      // the stamps are compiled out: nothing to record
+#endif
   if (trace_path) { CSVIT_CUDA(cudaMalloc(&mp.trace, kMlpTraceTiles * 64 * sizeof(long long))); CSVIT_CUDA(cudaMemsetAsync(mp.trace, 0, kMlpTraceTiles * 64 * sizeof(long long), stream)); }
   CUtensorMap tmX, tmW1, tmW2;
   if (int e = make_tmap(&tmX, xn, ldxn, M, C, dtype, kBM, true)) return e;

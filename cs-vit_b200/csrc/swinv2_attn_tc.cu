@@ -437,7 +437,7 @@ int launch_swinv2_attn_tc(const void* qkv, long long ldq, const float* bias_log2
     CSVIT_CUDA(cudaMalloc(&p.trace, nb));
     CSVIT_CUDA(cudaMemsetAsync(p.trace, 0, nb, stream));
     int e = bf ? launch_vt<1, 0>(tmQ, p, stream) : launch_vt<0, 0>(tmQ, p, stream);
-    if (e) return e;
+    if (e) { cudaFree(p.trace); return e; }
     CSVIT_CUDA(cudaStreamSynchronize(stream));
     std::vector<long long> h(nb / sizeof(long long));
     CSVIT_CUDA(cudaMemcpy(h.data(), p.trace, nb, cudaMemcpyDeviceToHost));

@@ -205,6 +205,38 @@ def linear(a: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], *, act: 
     return _LinearFn.apply(a, w, b, resid, act, impl)
 
 
+class _Linear16Fn(Function):
+    """``a @ w.T + b`` on 16-bit tensor-core operands with fp32 accumulation, output and gradients (the operand policy of SwinBlockFn for
+    code that is not written as one Function per block): the 16-bit copies of the activation and the weight are what is saved, and the
+    backward GEMMs read them and the 16-bit copy of the incoming gradient AS STORED (MN-major operands of ``csvit_gemm_ex``) - no fp32
+    transposes, twice the MMA rate of the TF32 path that ``linear`` takes on fp32 tensors."""
+
+    @staticmethod
+    def forward(ctx, a, w, b, act_dtype):
+        a16 = a if a.dtype == act_dtype else a.to(act_dtype)
+        w16 = w.detach().to(act_dtype)
+        y = ops.linear(a16, w16, b, out_dtype=torch.float32)
+        ctx.save_for_backward(a16, w16)
+        ctx.has_b, ctx.act_dtype = b is not None, act_dtype
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        a16, w16 = ctx.saved_tensors
+        g = _c(g)
+        g16 = g.to(ctx.act_dtype)
+        da = ops.gemm_ex(g16, False, w16, True, out_dtype=torch.float32) if ctx.needs_input_grad[0] else None
+        dw = ops.gemm_ex(g16, True, a16, True, out_dtype=torch.float32) if ctx.needs_input_grad[1] else None
+        db = ops.col_reduce(g)[0] if ctx.has_b and ctx.needs_input_grad[2] else None
+        return da, dw, db, None
+
+
+def linear16(a: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], act_dtype: torch.dtype) -> torch.Tensor:
+    """fp32 ``a @ w.T + b`` computed on ``act_dtype`` (fp16 / bf16) tensor-core operands, kernel backward on the same operands."""
+    return _Linear16Fn.apply(a, w, b, act_dtype)
+
+
 class _GeluFn(Function):
     @staticmethod
     def forward(ctx, x):

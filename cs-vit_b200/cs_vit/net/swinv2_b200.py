@@ -257,6 +257,10 @@ class Swinv2BackboneB200(nn.Module):
         dev = images.device
         cols = ops.patch_im2col(images.float().contiguous(), out_dtype=torch.float32, normalize=normalize)
         pe = self.embeddings.patch_embeddings.projection
+        if self._fp32 or os.environ.get("CSVIT_V2_TRAIN_LINEAR", "16") == "tf32":
+            lin = lambda a_, w_, b_: ag.linear(a_, w_, b_, impl=impl)                 # noqa: E731  (exact fp32 / TF32 on fp32 tensors)
+        else:
+            lin = lambda a_, w_, b_: ag.linear16(a_, w_, b_, self._act_dtype)          # noqa: E731  (16-bit operands, fp32 everything else)
         x = ag.linear(cols, pe.weight.reshape(pe.weight.shape[0], -1), pe.bias, impl=impl)
         x = ag.LayerNormFn.apply(x, self.embeddings.norm.weight, self.embeddings.norm.bias, eps)
         total_blocks = sum(cfg.depths)
@@ -285,9 +289,9 @@ class Swinv2BackboneB200(nn.Module):
                 inv = self._w(f"winv{H}_{ws}_{shift}", [], lambda: torch.argsort(ops.window_index_map(H, H, ws, shift, device=dev).long()))
                 sa = blk.attention.self
                 xw = x.view(n, N, C)[:, idx].reshape(n * N, C)                     # roll(-s) + window_partition as one gather
-                q = ag.linear(xw, sa.query.weight, sa.query.bias, impl=impl)
-                kk = ag.linear(xw, sa.key.weight, None, impl=impl)
-                v = ag.linear(xw, sa.value.weight, sa.value.bias, impl=impl)
+                q = lin(xw, sa.query.weight, sa.query.bias)
+                kk = lin(xw, sa.key.weight, None)
+                v = lin(xw, sa.value.weight, sa.value.bias)
                 qh, kh, vh = (t.view(n * nW, L, heads, C // heads).transpose(1, 2) for t in (q, kk, v))
                 lscale = torch.clamp(sa.logit_scale, max=math.log(1.0 / 0.01)).exp()                                 # V2:450-453
                 table = sa.continuous_position_bias_mlp(coords)                                                      # [(2ws-1)^2, heads]
@@ -316,20 +320,20 @@ class Swinv2BackboneB200(nn.Module):
                         scores = (scores.view(n, nW, heads, L, L) + 2.0 * mask[None, :, None]).view(n * nW, heads, L, L)
                     ctx = (scores.softmax(dim=-1) @ vh).transpose(1, 2).reshape(n * N, C)
                 proj = blk.attention.output.dense
-                ya = ag.linear(ctx.contiguous(), proj.weight, proj.bias, impl=impl)
+                ya = lin(ctx.contiguous(), proj.weight, proj.bias)
                 ya = ya.view(n, N, C)[:, inv].reshape(n * N, C)                    # window_reverse + roll(+s)
                 ya = ag.LayerNormFn.apply(ya.contiguous(), blk.layernorm_before.weight, blk.layernorm_before.bias, eps)
                 x = x + drop_path(ya, rates[k], N)                                                                   # res-post-norm, V2:705-706
                 fc1, fc2 = blk.intermediate.dense, blk.output.dense
-                hid = ag.gelu(ag.linear(x, fc1.weight, fc1.bias, impl=impl))
-                z = ag.linear(hid, fc2.weight, fc2.bias, impl=impl)
+                hid = ag.gelu(lin(x, fc1.weight, fc1.bias))
+                z = lin(hid, fc2.weight, fc2.bias)
                 z = ag.LayerNormFn.apply(z, blk.layernorm_after.weight, blk.layernorm_after.bias, eps)
                 x = x + drop_path(z, rates[k], N)                                                                    # V2:708-710
             if hasattr(stage, "downsample"):
                 ds = stage.downsample
                 g4 = x.view(n, H, H, C)
                 cat = torch.cat([g4[:, 0::2, 0::2], g4[:, 1::2, 0::2], g4[:, 0::2, 1::2], g4[:, 1::2, 1::2]], dim=-1).reshape(-1, 4 * C)
-                x = ag.linear(cat.contiguous(), ds.reduction.weight, None, impl=impl)                                # V2: reduction, then norm
+                x = lin(cat.contiguous(), ds.reduction.weight, None)                                # V2: reduction, then norm
                 x = ag.LayerNormFn.apply(x, ds.norm.weight, ds.norm.bias, eps)
         Hl = cfg.stage_geometry(len(cfg.depths) - 1)[0]
         out = ag.LayerNormFn.apply(x, self.layernorm.weight, self.layernorm.bias, eps)

@@ -307,7 +307,7 @@ class Swinv2BackboneB200(nn.Module):
                     qn = torch.nn.functional.normalize(qh, dim=-1) * lscale.view(1, heads, 1, 1)
                     kn = torch.nn.functional.normalize(kh, dim=-1)
                     add = bias[None].expand(nW, heads, L, L) if mask is None else bias[None] + 2.0 * mask[:, None]
-                    add = add.reshape(1, nW * heads, L, L).to(act)
+                    add = add.reshape(1, nW * heads, L, L).to(act).contiguous()      # (a permuted-stride bias sends SDPA down its math path)
                     q4, k4, v4 = (t.reshape(n, nW * heads, L, d).to(act) for t in (qn, kn, vh))
                     from torch.nn.attention import SDPBackend, sdpa_kernel
                     with sdpa_kernel([SDPBackend.EFFICIENT_ATTENTION, SDPBackend.MATH]):     # (the automatic choice takes the math path here)

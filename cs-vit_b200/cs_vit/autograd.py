@@ -212,10 +212,10 @@ class _Linear16Fn(Function):
     transposes, twice the MMA rate of the TF32 path that ``linear`` takes on fp32 tensors."""
 
     @staticmethod
-    def forward(ctx, a, w, b, act_dtype):
+    def forward(ctx, a, w, b, act_dtype, out16):
         a16 = a if a.dtype == act_dtype else a.to(act_dtype)
         w16 = w.detach().to(act_dtype)
-        y = ops.linear(a16, w16, b, out_dtype=torch.float32)
+        y = ops.linear(a16, w16, b, out_dtype=act_dtype if out16 else torch.float32)
         ctx.save_for_backward(a16, w16)
         ctx.has_b, ctx.act_dtype = b is not None, act_dtype
         return y
@@ -225,16 +225,46 @@ class _Linear16Fn(Function):
     def backward(ctx, g):
         a16, w16 = ctx.saved_tensors
         g = _c(g)
-        g16 = g.to(ctx.act_dtype)
+        want_db = ctx.has_b and ctx.needs_input_grad[2]
+        db = None
+        if g.dtype == torch.float32:      # one pass over the fp32 gradient: its 16-bit operand copy and the bias gradient
+            if want_db:
+                db, _, g16 = ops.col_reduce(g, copy_dtype=ctx.act_dtype)
+            else:
+                g16 = g.to(ctx.act_dtype)
+        else:
+            g16 = g
+            if want_db:
+                db = g.float().sum(0)
         da = ops.gemm_ex(g16, False, w16, True, out_dtype=torch.float32) if ctx.needs_input_grad[0] else None
         dw = ops.gemm_ex(g16, True, a16, True, out_dtype=torch.float32) if ctx.needs_input_grad[1] else None
-        db = ops.col_reduce(g)[0] if ctx.has_b and ctx.needs_input_grad[2] else None
-        return da, dw, db, None
+        return da, dw, db, None, None
 
 
-def linear16(a: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], act_dtype: torch.dtype) -> torch.Tensor:
-    """fp32 ``a @ w.T + b`` computed on ``act_dtype`` (fp16 / bf16) tensor-core operands, kernel backward on the same operands."""
-    return _Linear16Fn.apply(a, w, b, act_dtype)
+def linear16(a: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], act_dtype: torch.dtype, out16: bool = False) -> torch.Tensor:
+    """``a @ w.T + b`` computed on ``act_dtype`` (fp16 / bf16) tensor-core operands with a kernel backward on the same operands; fp32 result
+    (``out16``: 16-bit, for tensors that only feed another 16-bit operand - the MLP's hidden activations, the attention's values)."""
+    return _Linear16Fn.apply(a, w, b, act_dtype, out16)
+
+
+class _PermuteRowsFn(Function):
+    """``x[:, idx]`` for a PERMUTATION ``idx`` of the token axis (roll + window_partition, or their inverse): the backward is the gather by the
+    inverse permutation, not autograd's scatter-add."""
+
+    @staticmethod
+    def forward(ctx, x, idx, inv):
+        ctx.save_for_backward(idx, inv)
+        return x.index_select(1, idx)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        idx, inv = ctx.saved_tensors
+        return g.index_select(1, inv), None, None
+
+
+def permute_rows(x: torch.Tensor, idx: torch.Tensor, inv: torch.Tensor) -> torch.Tensor:
+    return _PermuteRowsFn.apply(x, idx, inv)
 
 
 class _GeluFn(Function):

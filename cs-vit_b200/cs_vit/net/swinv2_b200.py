@@ -258,9 +258,9 @@ class Swinv2BackboneB200(nn.Module):
         cols = ops.patch_im2col(images.float().contiguous(), out_dtype=torch.float32, normalize=normalize)
         pe = self.embeddings.patch_embeddings.projection
         if self._fp32 or os.environ.get("CSVIT_V2_TRAIN_LINEAR", "16") == "tf32":
-            lin = lambda a_, w_, b_: ag.linear(a_, w_, b_, impl=impl)                 # noqa: E731  (exact fp32 / TF32 on fp32 tensors)
+            lin = lambda a_, w_, b_, out16=False: ag.linear(a_, w_, b_, impl=impl)    # noqa: E731  (exact fp32 / TF32 on fp32 tensors)
         else:
-            lin = lambda a_, w_, b_: ag.linear16(a_, w_, b_, self._act_dtype)          # noqa: E731  (16-bit operands, fp32 everything else)
+            lin = lambda a_, w_, b_, out16=False: ag.linear16(a_, w_, b_, self._act_dtype, out16)      # noqa: E731  (16-bit operands)
         x = ag.linear(cols, pe.weight.reshape(pe.weight.shape[0], -1), pe.bias, impl=impl)
         x = ag.LayerNormFn.apply(x, self.embeddings.norm.weight, self.embeddings.norm.bias, eps)
         total_blocks = sum(cfg.depths)
@@ -288,10 +288,10 @@ class Swinv2BackboneB200(nn.Module):
                 idx = self._w(f"widx{H}_{ws}_{shift}", [], lambda: ops.window_index_map(H, H, ws, shift, device=dev).long())
                 inv = self._w(f"winv{H}_{ws}_{shift}", [], lambda: torch.argsort(ops.window_index_map(H, H, ws, shift, device=dev).long()))
                 sa = blk.attention.self
-                xw = x.view(n, N, C)[:, idx].reshape(n * N, C)                     # roll(-s) + window_partition as one gather
+                xw = ag.permute_rows(x.view(n, N, C), idx, inv).reshape(n * N, C)   # roll(-s) + window_partition as one gather
                 q = lin(xw, sa.query.weight, sa.query.bias)
                 kk = lin(xw, sa.key.weight, None)
-                v = lin(xw, sa.value.weight, sa.value.bias)
+                v = lin(xw, sa.value.weight, sa.value.bias, out16=True)
                 qh, kh, vh = (t.view(n * nW, L, heads, C // heads).transpose(1, 2) for t in (q, kk, v))
                 lscale = torch.clamp(sa.logit_scale, max=math.log(1.0 / 0.01)).exp()                                 # V2:450-453
                 table = sa.continuous_position_bias_mlp(coords)                                                      # [(2ws-1)^2, heads]
@@ -312,20 +312,20 @@ class Swinv2BackboneB200(nn.Module):
                     from torch.nn.attention import SDPBackend, sdpa_kernel
                     with sdpa_kernel([SDPBackend.EFFICIENT_ATTENTION, SDPBackend.MATH]):     # (the automatic choice takes the math path here)
                         ctx = torch.nn.functional.scaled_dot_product_attention(q4.contiguous(), k4.contiguous(), v4.contiguous(), attn_mask=add, scale=1.0)
-                    ctx = ctx.reshape(n * nW, heads, L, d).transpose(1, 2).reshape(n * N, C).float()
+                    ctx = ctx.reshape(n * nW, heads, L, d).transpose(1, 2).reshape(n * N, C)        # stays 16 bit: the out-proj's operand
                 else:
                     scores = torch.nn.functional.normalize(qh, dim=-1) @ torch.nn.functional.normalize(kh, dim=-1).transpose(-1, -2)
                     scores = scores * lscale + bias[None]
                     if mask is not None:
                         scores = (scores.view(n, nW, heads, L, L) + 2.0 * mask[None, :, None]).view(n * nW, heads, L, L)
-                    ctx = (scores.softmax(dim=-1) @ vh).transpose(1, 2).reshape(n * N, C)
+                    ctx = (scores.softmax(dim=-1) @ vh.float()).transpose(1, 2).reshape(n * N, C)
                 proj = blk.attention.output.dense
                 ya = lin(ctx.contiguous(), proj.weight, proj.bias)
-                ya = ya.view(n, N, C)[:, inv].reshape(n * N, C)                    # window_reverse + roll(+s)
+                ya = ag.permute_rows(ya.view(n, N, C), inv, idx).reshape(n * N, C)  # window_reverse + roll(+s)
                 ya = ag.LayerNormFn.apply(ya.contiguous(), blk.layernorm_before.weight, blk.layernorm_before.bias, eps)
                 x = x + drop_path(ya, rates[k], N)                                                                   # res-post-norm, V2:705-706
                 fc1, fc2 = blk.intermediate.dense, blk.output.dense
-                hid = ag.gelu(lin(x, fc1.weight, fc1.bias))
+                hid = ag.gelu(lin(x, fc1.weight, fc1.bias, out16=True))
                 z = lin(hid, fc2.weight, fc2.bias)
                 z = ag.LayerNormFn.apply(z, blk.layernorm_after.weight, blk.layernorm_after.bias, eps)
                 x = x + drop_path(z, rates[k], N)                                                                    # V2:708-710

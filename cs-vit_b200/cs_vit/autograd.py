@@ -235,7 +235,7 @@ class _Linear16Fn(Function):
         else:
             g16 = g
             if want_db:
-                db = g.float().sum(0)
+                db = ops.col_reduce(g)[0]
         da = ops.gemm_ex(g16, False, w16, True, out_dtype=torch.float32) if ctx.needs_input_grad[0] else None
         dw = ops.gemm_ex(g16, True, a16, True, out_dtype=torch.float32) if ctx.needs_input_grad[1] else None
         return da, dw, db, None, None
@@ -245,6 +245,37 @@ def linear16(a: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], act_dt
     """``a @ w.T + b`` computed on ``act_dtype`` (fp16 / bf16) tensor-core operands with a kernel backward on the same operands; fp32 result
     (``out16``: 16-bit, for tensors that only feed another 16-bit operand - the MLP's hidden activations, the attention's values)."""
     return _Linear16Fn.apply(a, w, b, act_dtype, out16)
+
+
+class _CosNormFn(Function):
+    """``x / max(|x|, 1e-12) * scale`` over the last axis of ``x [n, heads, L, d]`` (F.normalize and the logit scale of SwinV2's cosine
+    attention, V2:450-455; ``scale [heads]`` or None), emitted in ``out_dtype``.  One hand-written backward instead of autograd's chain
+    through norm / clamp / div / mul:  dx = (g' - x_hat (x_hat . g')) / |x|  with  g' = g * scale,  dscale = sum(g * x_hat)."""
+
+    @staticmethod
+    def forward(ctx, x, scale, out_dtype):
+        nrm = torch.linalg.vector_norm(x, dim=-1, keepdim=True).clamp_min_(1e-12)
+        xh = x / nrm
+        ctx.save_for_backward(xh, nrm, scale)
+        y = xh if scale is None else xh * scale.view(1, -1, 1, 1)
+        return y.to(out_dtype)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        xh, nrm, scale = ctx.saved_tensors
+        g = g.float()
+        dscale = None
+        if scale is not None:
+            if ctx.needs_input_grad[1]:
+                dscale = (g * xh).sum(dim=(0, 2, 3)).view_as(scale)
+            g = g * scale.view(1, -1, 1, 1)
+        dx = (g - xh * (xh * g).sum(dim=-1, keepdim=True)) / nrm
+        return dx, dscale, None
+
+
+def cosnorm(x: torch.Tensor, scale: Optional[torch.Tensor], out_dtype: torch.dtype) -> torch.Tensor:
+    return _CosNormFn.apply(x, scale, out_dtype)
 
 
 class _PermuteRowsFn(Function):

@@ -248,8 +248,8 @@ def linear16(a: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], act_dt
 
 
 class _CosNormFn(Function):
-    """``x / max(|x|, 1e-12) * scale`` over the last axis of ``x [n, heads, L, d]`` (F.normalize and the logit scale of SwinV2's cosine
-    attention, V2:450-455; ``scale [heads]`` or None), emitted in ``out_dtype``.  One hand-written backward instead of autograd's chain
+    """``x / max(|x|, 1e-12) * scale`` over the last axis of ``x [rows, heads, d]`` (F.normalize and the logit scale of SwinV2's cosine
+    attention, V2:450-455; ``scale [heads]`` or None), emitted in ``out_dtype``; contiguous row-major operands (the Linear's own layout).  One hand-written backward instead of autograd's chain
     through norm / clamp / div / mul:  dx = (g' - x_hat (x_hat . g')) / |x|  with  g' = g * scale,  dscale = sum(g * x_hat)."""
 
     @staticmethod
@@ -257,19 +257,19 @@ class _CosNormFn(Function):
         nrm = torch.linalg.vector_norm(x, dim=-1, keepdim=True).clamp_min_(1e-12)
         xh = x / nrm
         ctx.save_for_backward(xh, nrm, scale)
-        y = xh if scale is None else xh * scale.view(1, -1, 1, 1)
+        y = xh if scale is None else xh * scale.view(1, -1, 1)
         return y.to(out_dtype)
 
     @staticmethod
     @once_differentiable
     def backward(ctx, g):
         xh, nrm, scale = ctx.saved_tensors
-        g = g.float()
+        g = g.float().contiguous()
         dscale = None
         if scale is not None:
             if ctx.needs_input_grad[1]:
-                dscale = (g * xh).sum(dim=(0, 2, 3)).view_as(scale)
-            g = g * scale.view(1, -1, 1, 1)
+                dscale = (g * xh).sum(dim=(0, 2)).view_as(scale)
+            g = g * scale.view(1, -1, 1)
         dx = (g - xh * (xh * g).sum(dim=-1, keepdim=True)) / nrm
         return dx, dscale, None
 

@@ -304,8 +304,9 @@ class Swinv2BackboneB200(nn.Module):
                     # HF adds the mask twice: V2:462-468) broadcasts over the images and receives its gradient.
                     act = self._act_dtype
                     d = C // heads
-                    qn = ag.cosnorm(qh, lscale.reshape(heads), act)        # F.normalize + logit scale, V2:450-455, straight to 16 bit
-                    kn = ag.cosnorm(kh, None, act)
+                    # F.normalize + logit scale (V2:450-455) on the Linear's own [rows, heads, d] layout, straight to 16 bit
+                    qn = ag.cosnorm(q.view(n * N, heads, d), lscale.reshape(heads), act).view(n * nW, L, heads, d).transpose(1, 2)
+                    kn = ag.cosnorm(kk.view(n * N, heads, d), None, act).view(n * nW, L, heads, d).transpose(1, 2)
                     add = bias[None].expand(nW, heads, L, L) if mask is None else bias[None] + 2.0 * mask[:, None]
                     add = add.reshape(1, nW * heads, L, L).to(act).contiguous()      # (a permuted-stride bias sends SDPA down its math path)
                     q4, k4, v4 = (t.reshape(n, nW * heads, L, d).to(act) for t in (qn, kn, vh))

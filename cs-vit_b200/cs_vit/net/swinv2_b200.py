@@ -307,12 +307,17 @@ class Swinv2BackboneB200(nn.Module):
                     # F.normalize + logit scale (V2:450-455) on the Linear's own [rows, heads, d] layout, straight to 16 bit
                     qn = ag.cosnorm(q.view(n * N, heads, d), lscale.reshape(heads), act).view(n * nW, L, heads, d).transpose(1, 2)
                     kn = ag.cosnorm(kk.view(n * N, heads, d), None, act).view(n * nW, L, heads, d).transpose(1, 2)
-                    add = bias[None].expand(nW, heads, L, L) if mask is None else bias[None] + 2.0 * mask[:, None]
-                    add = add.reshape(1, nW * heads, L, L).to(act).contiguous()      # (a permuted-stride bias sends SDPA down its math path)
-                    q4, k4, v4 = (t.reshape(n, nW * heads, L, d).to(act) for t in (qn, kn, vh))
                     from torch.nn.attention import SDPBackend, sdpa_kernel
                     with sdpa_kernel([SDPBackend.EFFICIENT_ATTENTION, SDPBackend.MATH]):     # (the automatic choice takes the math path here)
-                        ctx = torch.nn.functional.scaled_dot_product_attention(q4.contiguous(), k4.contiguous(), v4.contiguous(), attn_mask=add, scale=1.0)
+                        if mask is None:
+                            # no shift mask: one bias [1, heads, L, L] for every window - windows fold into the batch and q / k / v go in as the
+                            # strided [n * nW, heads, L, d] views of the Linear outputs (no transposing copies)
+                            add = bias[None].to(act).contiguous()          # (a permuted-stride bias sends SDPA down its math path)
+                            ctx = torch.nn.functional.scaled_dot_product_attention(qn, kn, vh, attn_mask=add, scale=1.0)
+                        else:
+                            add = (bias[None] + 2.0 * mask[:, None]).reshape(1, nW * heads, L, L).to(act).contiguous()
+                            q4, k4, v4 = (t.reshape(n, nW * heads, L, d) for t in (qn, kn, vh))
+                            ctx = torch.nn.functional.scaled_dot_product_attention(q4, k4, v4, attn_mask=add, scale=1.0)
                     ctx = ctx.reshape(n * nW, heads, L, d).transpose(1, 2).reshape(n * N, C)        # stays 16 bit: the out-proj's operand
                 else:
                     scores = torch.nn.functional.normalize(qh, dim=-1) @ torch.nn.functional.normalize(kh, dim=-1).transpose(-1, -2)

@@ -243,12 +243,14 @@ class Swinv2BackboneB200(nn.Module):
     def _forward_train(self, images: torch.Tensor, normalize: bool) -> torch.Tensor:
         """Differentiable forward of the finetune step (ref:scripts/finetune.py:211-227 with a swinv2 backbone, which is what every
         shipped configuration uses).  Every Linear, LayerNorm and GELU runs on this library's kernels with kernel backwards
-        (cs_vit/autograd.py: TF32 tensor cores in the 16-bit modes, exact fp32 in the validation mode); the residual stream, the
-        window gather / scatter and stochastic depth are torch index / elementwise ops.  The scaled-cosine attention CORE
-        (normalise q and k, logit scale, continuous position bias, softmax, P V; V2:421-487) is plain differentiable torch code
-        here - batched matmuls on cuBLAS: the 256-token windows of this family are beyond the window-attention backward kernel
-        (64 keys), and a tcgen05 forward / backward pair for them is not built.  Matches HF's autograd on the gradient golden
-        (tests/test_swinv2_gpu.py); it is the functional path, not a tuned one."""
+        (cs_vit/autograd.py; 16-bit modes: ``linear16`` - 16-bit tensor-core operands saved and read as stored by the backward GEMMs, fp32
+        accumulation / residual stream / gradients; validation mode: exact fp32); the window gather / scatter are permutation Functions
+        and stochastic depth a torch elementwise op.  The scaled-cosine attention core (V2:421-487): q / k normalisation + logit scale
+        by ``autograd.cosnorm``, then - in the 16-bit modes - ONE library fused attention call per block (torch
+        ``scaled_dot_product_attention``, memory-efficient backend) with continuous position bias + 2 x shift mask as its additive term,
+        so the [windows, heads, 256, 256] scores are never materialised; the validation mode keeps plain differentiable torch code.
+        An own tcgen05 forward / backward pair for the 256-token windows is not built (the forward kernel of the inference path,
+        csvit_swinv2_attn_tc, has no backward).  Matches HF's autograd on the gradient golden (tests/test_swinv2_gpu.py)."""
         from .. import autograd as ag
         cfg = self.config
         n, _, S, _ = images.shape

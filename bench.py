@@ -207,14 +207,16 @@ def peaks():
         return 1400.0, 6650.0, "fallback"
 
 
-def kernel_traffic(a, key):
+def kernel_traffic(a, key, field="traffic_bytes_per_launch"):
     """DRAM bytes per launch of a kernel group ("gemm", "attn_core", "attn_fused") from the committed ncu capture of this exact workload
-    (profiles/r2_dram_traffic.json, tools/dram_traffic.py); None for any other workload / variant / batch."""
+    (profiles/r2_dram_traffic.json, tools/dram_traffic.py); None for any other workload / variant / batch.  field="tensor_pipe_pct":
+    ncu's sm__pipe_tensor_cycles_active of one launch of that kernel (profiles/r2_ncu_attention_key_metrics.txt) - a committed
+    capture, not a number measured by this run (ncu cannot run inside a timed region)."""
     if a.variant != "swin_b" or a.workload != "spatial" or a.batch != BATCH:
         return None
     try:
         with open(os.path.join(ROOT, "profiles", "r2_dram_traffic.json")) as f:
-            return json.load(f)[key]["traffic_bytes_per_launch"]
+            return json.load(f)[key].get(field)
     except Exception:
         return None
 
@@ -360,6 +362,7 @@ def run_ours(a):
                 gbs = prof["bytes"] / (prof["ms"] / 1e3) / 1e9
                 out[key] = {"bound": "hbm", "kernel": kern, "achieved": round(gbs, 1), "peak": peak_gbs, "unit": "GB/s",
                             "frac": round(gbs / peak_gbs, 4), "algorithmic_bytes_per_token": bpt, "traffic": kernel_traffic(a, tkey),
+                            "tensor_pipe_pct_ncu": kernel_traffic(a, tkey, "tensor_pipe_pct"),
                             "tflops": round(prof["flops"] / (prof["ms"] / 1e3) / 1e12, 1),
                             "launches_per_step": prof["launches"] // a.steps,
                             "share_of_step": round(prof["ms"] / a.steps / (ms_total / a.steps), 3),

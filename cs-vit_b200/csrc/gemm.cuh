@@ -26,6 +26,7 @@ struct EpiParams {
   int tma_store;  // 1: 16-bit output, identity rows, no residual -> staged through smem and written by TMA
   int coalesced;  // 1: fp32 output (+residual, +scatter) -> transposed through smem, 4 full lines per warp access
   int tma_f32;    // 1: fp32 output on identity rows (+residual): residual chunks arrive by TMA, results leave by TMA
+  int red_add;    // 1 (with tma_f32, set by the launcher when out aliases resid): chunks leave by TMA reduce-add, resid is nullptr
   int map_mode;
   WinGeom geom;
   // SwinV2 Q/K/V projection (cos_C = C > 0, N = 3C): every head's 32 columns of q and k are L2-normalised per row before the 16-bit
@@ -309,7 +310,8 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& ep, const CUtenso
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0 && rows_ok) {
-              tma_store_2d(tmC, buf, gcol, row0);
+              if (ep.red_add) tma_reduce_add_2d(tmC, buf, gcol, row0);
+              else tma_store_2d(tmC, buf, gcol, row0);
               tma_store_commit();
               if (has_res && ci + 2 < NCH && gcol + 64 < ep.N) {
                 tma_store_wait_read0();              // that store has read buf: it can take chunk ci+2's residual

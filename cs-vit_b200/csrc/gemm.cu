@@ -262,8 +262,11 @@ int make_tmap(CUtensorMap* tm, const void* ptr, long long ld, long long rows, lo
   return 0;
 }
 
-// CSVIT_RED_ADD=0 keeps the load-add-store form of the in-place residual epilogue (ablation)
-static const bool g_red_add = [] { const char* e = getenv("CSVIT_RED_ADD"); return !(e && e[0] == '0'); }();
+// CSVIT_RED_ADD=0 keeps the load-add-store form of the in-place residual epilogue, 2 = reduce-add on the TMA path only (ablations)
+int red_add_mode() {
+  static const int m = [] { const char* e = getenv("CSVIT_RED_ADD"); return (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 1; }();
+  return m;
+}
 // CSVIT_TMA_F32=0 falls back to the register-staged fp32 epilogue (ablation)
 static const bool g_tma_f32 = [] { const char* e = getenv("CSVIT_TMA_F32"); return !(e && e[0] == '0'); }();
 static int g_num_sms = 0;
@@ -361,12 +364,14 @@ int launch_gemm(const void* A, long long lda, const void* W, long long ldw, int 
                 ((ep.ldo * 4) % 16 == 0) && (!ep.resid || (ep.ldr * 4) % 16 == 0) && g_tma_f32) ? 1 : 0;
   // In-place residual (x += A W^T + b: out-proj on token-ordered context, fc2): the tile leaves by TMA reduce-add (fp32 add in L2), the
   // residual stream never enters the SM - no residual TMA loads, no load -> add -> store chain on the two staging buffers per warp.
+  ep.coalesced = (!ep.tma_store && !ep.tma_f32 && tune.tma_store != 0 && ep.out_dtype == DT_F32 && ep.vec_ok && (N % 32 == 0)) ? 1 : 0;
+  // (the coalesced register path - scattered rows, N < 256 - does the same with red.global.add.v4.f32 instead of load + add + store)
   ep.red_add = 0;
-  if (ep.tma_f32 && ep.resid && static_cast<const void*>(ep.resid) == ep.out && ep.ldr == ep.ldo && g_red_add) {
+  if ((ep.tma_f32 ? red_add_mode() != 0 : (ep.coalesced && red_add_mode() == 1)) && ep.resid && static_cast<const void*>(ep.resid) == ep.out &&
+      ep.ldr == ep.ldo) {
     ep.red_add = 1;
     ep.resid = nullptr;
   }
-  ep.coalesced = (!ep.tma_store && !ep.tma_f32 && tune.tma_store != 0 && ep.out_dtype == DT_F32 && ep.vec_ok && (N % 32 == 0)) ? 1 : 0;
   // CTA pairs (cta_group::2): 256x256 tiles with the weight tile split across the two SMs - a third less
   // shared-memory ingest per MMA than the single-CTA kernel, which is what bounds the large-K GEMMs.
   const bool pair_ok = in_dtype != DT_F32 && N % 256 == 0 && num_m * (N / 256) >= 2 * num_sms();

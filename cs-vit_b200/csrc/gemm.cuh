@@ -26,7 +26,8 @@ struct EpiParams {
   int tma_store;  // 1: 16-bit output, identity rows, no residual -> staged through smem and written by TMA
   int coalesced;  // 1: fp32 output (+residual, +scatter) -> transposed through smem, 4 full lines per warp access
   int tma_f32;    // 1: fp32 output on identity rows (+residual): residual chunks arrive by TMA, results leave by TMA
-  int red_add;    // 1 (with tma_f32, set by the launcher when out aliases resid): chunks leave by TMA reduce-add, resid is nullptr
+  int red_add;    // 1 (set by the launcher when out aliases resid; resid is then nullptr): tma_f32 chunks leave by TMA reduce-add,
+                  // the coalesced path's float4 stores become red.global.add.v4.f32
   int map_mode;
   WinGeom geom;
   // SwinV2 Q/K/V projection (cos_C = C > 0, N = 3C): every head's 32 columns of q and k are L2-normalised per row before the 16-bit
@@ -410,9 +411,15 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& ep, const CUtenso
               val[j] = make_float4(t.x + res[j].x, t.y + res[j].y, t.z + res[j].z, t.w + res[j].w);
             }
             if (c + 32 < BN / 2) load_resid(gcol + 32);   // next chunk's residual in flight during the stores
+            if (ep.red_add) {      // in-place residual: x += val as a vector reduction in L2 (res[] is zero, nothing was loaded)
   #pragma unroll
-            for (int j = 0; j < 8; ++j)
-              if (ok8[j]) *reinterpret_cast<float4*>(outp + orow8[j] * ep.ldo + gcol + 4 * q) = val[j];
+              for (int j = 0; j < 8; ++j)
+                if (ok8[j]) red_add_f32x4(outp + orow8[j] * ep.ldo + gcol + 4 * q, val[j]);
+            } else {
+  #pragma unroll
+              for (int j = 0; j < 8; ++j)
+                if (ok8[j]) *reinterpret_cast<float4*>(outp + orow8[j] * ep.ldo + gcol + 4 * q) = val[j];
+            }
             __syncwarp();
           }
         } else {
@@ -444,6 +451,7 @@ struct GemmTuning {
 int make_tmap(CUtensorMap* tm, const void* ptr, long long ld, long long rows, long long cols, int dtype, int box_rows,
               bool as_tf32);
 int num_sms();
+int red_add_mode();          // CSVIT_RED_ADD: 0 off, 1 (default) every in-place residual epilogue, 2 TMA path only
 int launch_gemm_pair(const void* A, long long lda, const void* W, long long ldw, int in_dtype, int M, int N, int K,
                      const EpiParams& ep, const GemmTuning& tune, cudaStream_t stream);
 int launch_gemm(const void* A, long long lda, const void* W, long long ldw, int in_dtype, int M, int N, int K,

@@ -228,7 +228,12 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       // residual chunks requested at tile start) - written out here so that this branch compiles against 96 registers without spills
       const uint32_t ab = it & 1u;
       const int row0 = t * kBM + quad * 32, colbase = half * 64;
-      tma_f32_prefetch<C>(ep, &tmR, stg, rbar + 2 * e, t, 0, quad, half, lane);
+      if (ep.red_add) {      // the result leaves by TMA reduce-add: no residual chunks to request, only the staging buffers to get back
+        if (lane == 0) tma_store_wait_read0();
+        __syncwarp();
+      } else {
+        tma_f32_prefetch<C>(ep, &tmR, stg, rbar + 2 * e, t, 0, quad, half, lane);
+      }
       mbar_wait(&acc2_full[ab], (it >> 1) & 1u);
       tc_fence_after();
       const uint32_t t_addr = tm_acc2 + ab * 128u + (uint32_t(quad * 32) << 16) + uint32_t(colbase);
@@ -238,7 +243,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         uint32_t rr[32];
         tmem_ld_32x32(t_addr + uint32_t(32 * ci), rr);
         tmem_ld_wait();
-        if (row0 < ep.M) {
+        if (row0 < ep.M && !ep.red_add) {
           mbar_wait(&rbar[2 * e + ci], (rph >> ci) & 1u);
           rph ^= (1u << ci);
         }
@@ -247,7 +252,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         for (int k = 0; k < 8; ++k) {
           float4* pp = reinterpret_cast<float4*>(buf + lane * 128 + ((k ^ (lane & 7)) << 4));
           const float4 bb = __ldg(b4 + k);
-          float4 x0 = *pp;
+          float4 x0 = ep.red_add ? make_float4(0.f, 0.f, 0.f, 0.f) : *pp;
           x0.x += __uint_as_float(rr[4 * k]) + bb.x; x0.y += __uint_as_float(rr[4 * k + 1]) + bb.y;
           x0.z += __uint_as_float(rr[4 * k + 2]) + bb.z; x0.w += __uint_as_float(rr[4 * k + 3]) + bb.w;
           *pp = x0;
@@ -255,7 +260,8 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0 && row0 < ep.M) {
-          tma_store_2d(&tmR, buf, colbase + 32 * ci, row0);
+          if (ep.red_add) tma_reduce_add_2d(&tmR, buf, colbase + 32 * ci, row0);
+          else tma_store_2d(&tmR, buf, colbase + 32 * ci, row0);
           tma_store_commit();
         }
       }
@@ -390,6 +396,13 @@ int launch_mlp_fused(const void* xn, long long ldxn, const void* W1, long long l
     // residual tile in / out by TMA: 32 x 32 fp32 boxes of x, both chunks of a warp requested at tile start
     ep.tma_f32 = 1; ep.coalesced = 0;
     if (int e = make_tmap(&tmR, x, ldx, M, C, DT_F32, 32, false)) return e;
+  }
+  // x is updated in place: the GEMM2 tile leaves as a reduction (gemm.cu, CSVIT_RED_ADD).  The split kernel keeps ep.resid as its dispatch
+  // condition and looks at ep.red_add; the shared epilogue_tile() paths take resid == nullptr.
+  static const bool split128 = [] { const char* e = getenv("CSVIT_MLP_SPLIT"); return !(e && e[0] == '0'); }();
+  if (ep.tma_f32 ? red_add_mode() != 0 : red_add_mode() == 1) {
+    ep.red_add = 1;
+    if (!(C == 128 && ep.tma_f32 && split128)) ep.resid = nullptr;
   }
   const bool bf = dtype == DT_BF16;
   if (trace_path) {      // debugging: one traced launch, stamps written as text (cycles relative to the first stamp)

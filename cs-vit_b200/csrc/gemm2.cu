@@ -29,8 +29,8 @@ constexpr size_t kPairSmem = 1024 + size_t(kPairTiles) + kPairStg + 256;
 
 template <int FMT>  // 0 = fp16, 1 = bf16
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
-gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR, int K, EpiParams ep) {
+gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmB2,
+                 const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR, int K, int split_tail, EpiParams ep) {
   constexpr int BN = kPairBN, STAGES = kPairStages, BK = 64;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -52,6 +52,15 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int num_n = (ep.N + BN - 1) / BN;
   const int num_ptiles = num_mp * num_n;
   const int num_kb = (K + BK - 1) / BK;
+  // Tail split: after the full rounds (every pair the same number of 256 x 256 tiles) the `rem` left-over tiles would occupy rem of the
+  // num_pairs pairs for a whole tile time.  When 2 rem <= num_pairs they run as 2 rem tiles of 256 x 128 instead (MMA N = 128, the
+  // B box of tmB2 = 64 rows per CTA), one per pair: the last round costs half a tile time (Swin-B stage 2, N = 512: 5.3 -> 5.5 instead of 6 rounds).
+  const int full_tiles = (num_ptiles / num_pairs) * num_pairs;
+  const int rem = num_ptiles - full_tiles;
+  const bool split = split_tail != 0 && rem > 0 && 2 * rem <= num_pairs;
+  const int main_end = split ? full_tiles : num_ptiles;
+  const bool has_half = split && pair_id < 2 * rem;
+  const int half_pt = full_tiles + (pair_id >> 1), half_nh = pair_id & 1;      // this pair's half tile: tile half_pt, columns 128 half_nh ..
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
@@ -76,7 +85,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // ---------------- TMA producer (both CTAs) ----------------
     if (lane == 0) {
       int s = 0; uint32_t ph = 0;
-      for (int pt = pair_id; pt < num_ptiles; pt += num_pairs) {
+      for (int pt = pair_id; pt < main_end; pt += num_pairs) {
         const int mp = pt / num_n, n_blk = pt - mp * num_n;
         const int m_blk = mp * 2 + int(rank);
         for (int kb = 0; kb < num_kb; ++kb) {
@@ -89,6 +98,19 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (++s == STAGES) { s = 0; ph ^= 1u; }
         }
       }
+      if (has_half) {
+        const int mp = half_pt / num_n, n_blk = half_pt - mp * num_n;
+        const int m_blk = mp * 2 + int(rank);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty[s], ph ^ 1u);
+          const uint32_t lfull = mapa_u32(smem_u32(&full[s]), 0);
+          mbar_arrive_expect_tx_cluster(lfull, kPairABytes + kPairBBytes / 2);
+          uint8_t* sa = tiles + size_t(s) * kPairStageBytes;
+          tma_load_2d_pair(sa, &tmA, lfull, kb * BK, m_blk * kBM);
+          tma_load_2d_pair(sa + kPairABytes, &tmB2, lfull, kb * BK, n_blk * BN + half_nh * (BN / 2) + int(rank) * (BN / 4));
+          if (++s == STAGES) { s = 0; ph ^= 1u; }
+        }
+      }
     }
   } else if (warp == 1) {
     // ---------------- MMA issuer (leader CTA only) ----------------
@@ -96,7 +118,10 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       constexpr uint32_t idesc = make_idesc(uint32_t(FMT), 2 * kBM, BN);
       int s = 0; uint32_t ph = 0;
       int as = 0; uint32_t aph = 0;
-      for (int pt = pair_id; pt < num_ptiles; pt += num_pairs) {
+      constexpr uint32_t idesc_half = make_idesc(uint32_t(FMT), 2 * kBM, BN / 2);
+      const int rounds = (main_end - pair_id + num_pairs - 1) / num_pairs + (has_half ? 1 : 0);
+      for (int it = 0; it < rounds; ++it) {
+        const uint32_t idesc_t = (has_half && it == rounds - 1) ? idesc_half : idesc;
         mbar_wait(&tempty[as], aph ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + uint32_t(as * BN);
@@ -109,7 +134,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const uint64_t bdesc = make_sw128_kmajor_desc(sa + kPairABytes);
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-              umma_ss_pair(d_tmem, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), idesc, (kb | k) ? 1u : 0u);
+              umma_ss_pair(d_tmem, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), idesc_t, (kb | k) ? 1u : 0u);
             umma_commit_pair(&empty[s], 3);
             if (kb == num_kb - 1) umma_commit_pair(&tfull[as], 3);
           }
@@ -127,13 +152,13 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint8_t* stg = staging + e * 2 * kStageBufBytes;
     uint32_t stg_sel = 0, rph = 0;
     int as = 0; uint32_t aph = 0;
-    for (int pt = pair_id; pt < num_ptiles; pt += num_pairs) {
+    for (int pt = pair_id; pt < main_end; pt += num_pairs) {
       const int mp = pt / num_n, n_blk = pt - mp * num_n;
       const int m_blk = mp * 2 + int(rank);
       {
         const int npt = pt + num_pairs;
         if (pt == pair_id) prefetch_resid_tile<BN>(ep, m_blk, n_blk, quad, half, lane);
-        if (npt < num_ptiles) prefetch_resid_tile<BN>(ep, (npt / num_n) * 2 + int(rank), npt % num_n, quad, half, lane);
+        if (npt < main_end) prefetch_resid_tile<BN>(ep, (npt / num_n) * 2 + int(rank), npt % num_n, quad, half, lane);
       }
       epilogue_tile<BN>(ep, &tmC, stg, tmem_base + uint32_t(as * BN), &tfull[as], aph, m_blk, n_blk, quad, half, lane, 2, &stg_sel,
                         &tmR, rbar + 2 * e, &rph);
@@ -141,6 +166,15 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty[as]), 0));
       if (++as == 2) { as = 0; aph ^= 1u; }
+    }
+    if (has_half) {      // the 256 x 128 tail tile: the BN = 128 epilogue on column block 2 n_blk + half_nh (64 columns per warp)
+      const int mp = half_pt / num_n, n_blk = half_pt - mp * num_n;
+      const int m_blk = mp * 2 + int(rank);
+      epilogue_tile<BN / 2>(ep, &tmC, stg, tmem_base + uint32_t(as * BN), &tfull[as], aph, m_blk, 2 * n_blk + half_nh, quad, half, lane, 2,
+                            &stg_sel, &tmR, rbar + 2 * e, &rph);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty[as]), 0));
     }
     if ((ep.tma_store || ep.tma_f32) && lane == 0) tma_store_wait_all();
   }
@@ -152,8 +186,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 }
 
 template <int FMT>
-static int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmR, int K,
-                       const EpiParams& ep, int max_ctas, cudaStream_t stream) {
+static int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmB2, const CUtensorMap& tmC, const CUtensorMap& tmR,
+                       int K, int split_tail, const EpiParams& ep, int max_ctas, cudaStream_t stream) {
   static DeviceOnce once;
   auto kern = gemm_pair_kernel<FMT>;
   if (once.first()) {
@@ -163,15 +197,17 @@ static int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   int pairs = (max_ctas > 0 ? max_ctas : num_sms()) / 2;
   if (pairs > num_mp * num_n) pairs = num_mp * num_n;
   if (pairs < 1) pairs = 1;
-  CSVIT_CUDA(launch_pdl(kern, dim3(pairs * 2), dim3(kGemmThreads), kPairSmem, stream, tmA, tmB, tmC, tmR, K, ep));
+  CSVIT_CUDA(launch_pdl(kern, dim3(pairs * 2), dim3(kGemmThreads), kPairSmem, stream, tmA, tmB, tmB2, tmC, tmR, K, split_tail, ep));
   return 0;
 }
 
 int launch_gemm_pair(const void* A, long long lda, const void* W, long long ldw, int in_dtype, int M, int N, int K,
                      const EpiParams& ep, const GemmTuning& tune, cudaStream_t stream) {
-  CUtensorMap tmA, tmB, tmC, tmR;
+  CUtensorMap tmA, tmB, tmB2, tmC, tmR;
   if (int e = make_tmap(&tmA, A, lda, M, K, in_dtype, kBM, true)) return e;
   if (int e = make_tmap(&tmB, W, ldw, N, K, in_dtype, kPairBN / 2, true)) return e;
+  if (int e = make_tmap(&tmB2, W, ldw, N, K, in_dtype, kPairBN / 4, true)) return e;      // the tail's 256 x 128 tiles: 64 weight rows per CTA
+  static const int split_tail = [] { const char* e = getenv("CSVIT_PAIR_TAIL"); return (e && e[0] == '0') ? 0 : 1; }();
   if (ep.tma_store || ep.tma_f32) {
     if (int e = make_tmap(&tmC, ep.out, ep.ldo, M, N, ep.out_dtype, 32, false)) return e;
   } else {
@@ -180,8 +216,8 @@ int launch_gemm_pair(const void* A, long long lda, const void* W, long long ldw,
   tmR = tmC;
   if (ep.tma_f32 && ep.resid)
     if (int e = make_tmap(&tmR, ep.resid, ep.ldr, M, N, DT_F32, 32, false)) return e;
-  if (in_dtype == DT_BF16) return launch_pair<1>(tmA, tmB, tmC, tmR, K, ep, tune.max_ctas, stream);
-  return launch_pair<0>(tmA, tmB, tmC, tmR, K, ep, tune.max_ctas, stream);
+  if (in_dtype == DT_BF16) return launch_pair<1>(tmA, tmB, tmB2, tmC, tmR, K, split_tail, ep, tune.max_ctas, stream);
+  return launch_pair<0>(tmA, tmB, tmB2, tmC, tmR, K, split_tail, ep, tune.max_ctas, stream);
 }
 
 }  // namespace csvit

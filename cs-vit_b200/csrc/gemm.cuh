@@ -26,6 +26,7 @@ struct EpiParams {
   int tma_store;  // 1: 16-bit output, identity rows, no residual -> staged through smem and written by TMA
   int coalesced;  // 1: fp32 output (+residual, +scatter) -> transposed through smem, 4 full lines per warp access
   int tma_f32;    // 1: fp32 output on identity rows (+residual): residual chunks arrive by TMA, results leave by TMA
+  long long* trace;   // trace builds (-DCSVIT_PAIR_TRACE_BUILD, CSVIT_PAIR_TRACE=<file>): clock64 stamps of pair 0 of gemm_pair_kernel
   int red_add;    // 1 (set by the launcher when out aliases resid; resid is then nullptr): tma_f32 chunks leave by TMA reduce-add,
                   // the coalesced path's float4 stores become red.global.add.v4.f32
   int map_mode;
@@ -435,6 +436,58 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& ep, const CUtenso
             if (row_ok) epi_store_chunk32(ep, orow, gcol, r);
           }
         }
+}
+
+// The 16-bit TMA-store epilogue for SIXTEEN epilogue warps (gemm_pair_kernel<FMT, 16>, GELU outputs at K <= 512): warp (quad, part)
+// drains its 32 TMEM lanes x 64 columns (part = 0..3 of a 256-column tile) - one staging buffer, one TMA store per warp and tile.
+// Why: a clock64 trace of the 8-warp epilogue (profiles/r2_gemm_pair_trace_before.txt) shows 6600 cycles of GELU epilogue per tile
+// against ~4100 cycles of MMAs at K = 512, the issuer waiting ~4000 cycles for the accumulator buffer on EVERY tile; half the columns
+// per warp halve that chain (fc1 at Swin-B stage 2: 107 -> 100 us).  Both 32-column loads are in flight before the single wait; the first
+// half's 64 bytes per row are in shared memory before the second half's arithmetic starts (96 registers per thread at 576 threads).
+// The plain-store epilogue (4500 cycles on 8 warps) does NOT gain from this: with it the tile period stays at ~5500 cycles for a reason
+// the traces do not settle (see profiles/r2_gemm_epilogue_diagnostics.txt), so plain stores keep the 8-warp kernel.
+template <int BN>
+__device__ __forceinline__ void epilogue_tile16(const EpiParams& ep, const CUtensorMap* tmC, uint8_t* sbuf, uint32_t tmem_tile,
+                                                uint64_t* tfull_bar, uint32_t aph, int m_blk, int n_blk, int quad, int part, int lane) {
+  static_assert(BN == 256, "four 64-column parts");
+  const bool bf = ep.out_dtype == DT_BF16;
+  const int col_local = part * 64;
+  const int gcol = n_blk * BN + col_local;
+  mbar_wait(tfull_bar, aph);
+  tc_fence_after();
+  if (gcol >= ep.N) return;  // warp-uniform
+  const uint32_t t_addr = tmem_tile + (uint32_t(quad * 32) << 16) + uint32_t(col_local);
+  uint32_t r0[32], r1[32];
+  tmem_ld_32x32(t_addr, r0);
+  tmem_ld_32x32(t_addr + 32u, r1);
+  if (lane == 0) tma_store_wait_read0();      // the previous tile's store has read the staging buffer (issued a whole tile ago)
+  __syncwarp();
+  tmem_ld_wait();
+  auto step32 = [&](const uint32_t (&r)[32], int gc, int hh) {
+    uint32_t pk[16];
+    if (ep.act == ACT_GELU) {
+      epi_bias_gelu_pack32(ep.bias, bf, gc, r, pk);
+    } else {
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+      epi_bias_act32(ep, gc, v);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) pk[j] = pack16(bf, v[2 * j], v[2 * j + 1]);
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q)  // row `lane`, 16-byte chunk 4 hh + q -> swizzled position
+      *reinterpret_cast<uint4*>(sbuf + lane * 128 + (((4 * hh + q) ^ (lane & 7)) << 4)) =
+          make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+  };
+  step32(r0, gcol, 0);
+  step32(r1, gcol + 32, 1);
+  fence_proxy_async_smem();
+  __syncwarp();
+  if (lane == 0 && m_blk * kBM + quad * 32 < ep.M) {
+    tma_store_2d(tmC, sbuf, gcol, m_blk * kBM + quad * 32);
+    tma_store_commit();
+  }
 }
 
 // Host launchers (gemm.cu).  in_dtype: DT_BF16 / DT_F16 -> tcgen05 kind::f16 (W in the same format);

@@ -20,7 +20,7 @@ groups = {"gemm": ("gemm_pair_kernel", "gemm_tc_kernel"), "gemm_pair": ("gemm_pa
           "attn_fused": ("swin_attn_fused_kernel",)}
 steps = int(sys.argv[3]) if len(sys.argv) > 3 else 2
 out = {"source": "ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:gemm_|swin_attn python bench.py "
-                 "--steps 1 --warmup 1 --no-extras --no-cpu-baseline --no-graph (last step of the capture)", "workload": "swin_b spatial predict_batch, batch 256, fp16"}
+                 "--steps 1 --warmup 1 --no-extras --no-cpu-baseline --no-graph (last of the three passes of the capture)", "workload": "swin_b spatial predict_batch, batch 256, fp16"}
 for key, pats in groups.items():
     sel = [i for i, n in zip(ids, names) if any(n.startswith(p) for p in pats)]
     per_step = len(sel) // steps
@@ -30,5 +30,13 @@ for key, pats in groups.items():
     us = sum(by_id[i].get("gpu__time_duration.sum", 0.0) for i in last)
     out[key] = {"launches_per_step": per_step, "dram_read_bytes_per_step": rd, "dram_write_bytes_per_step": wr,
                 "traffic_bytes_per_launch": (rd + wr) / max(per_step, 1), "us_per_step_under_ncu": us}
+try:      # keep the tensor-pipe readings of the `ncu --set full` captures (profiles/r2_ncu_attention_key_metrics.txt) that live in the same file
+    old = json.load(open(sys.argv[2]))
+    for key in groups:
+        for k, v in old.get(key, {}).items():
+            if k.startswith("tensor_pipe"):
+                out[key][k] = v
+except Exception:
+    pass
 json.dump(out, open(sys.argv[2], "w"), indent=1)
 print(json.dumps(out, indent=1))

@@ -444,8 +444,9 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& ep, const CUtenso
 // against ~4100 cycles of MMAs at K = 512, the issuer waiting ~4000 cycles for the accumulator buffer on EVERY tile; half the columns
 // per warp halve that chain (fc1 at Swin-B stage 2: 107 -> 100 us).  Both 32-column loads are in flight before the single wait; the first
 // half's 64 bytes per row are in shared memory before the second half's arithmetic starts (96 registers per thread at 576 threads).
-// The plain-store epilogue (4500 cycles on 8 warps) does NOT gain from this: with it the tile period stays at ~5500 cycles for a reason
-// the traces do not settle (see profiles/r2_gemm_epilogue_diagnostics.txt), so plain stores keep the 8-warp kernel.
+// The plain-store epilogue (4500 cycles on 8 warps) does NOT gain from this: once it is short the tile period stays at ~5500 cycles because
+// the mainloop alone saturates the SM's shared-memory bandwidth at the tensor floor and the staging traffic comes on top
+// (profiles/r2_gemm_epilogue_diagnostics.txt), so plain stores keep the 8-warp kernel.
 template <int BN>
 __device__ __forceinline__ void epilogue_tile16(const EpiParams& ep, const CUtensorMap* tmC, uint8_t* sbuf, uint32_t tmem_tile,
                                                 uint64_t* tfull_bar, uint32_t aph, int m_blk, int n_blk, int quad, int part, int lane) {

@@ -1,6 +1,7 @@
 """GPU experiment: does a consumer that walks its input in the REVERSE of the producer's order find the producer's last-written rows in
 the 126 MB L2?  Stage-2 shapes of Swin-B at batch 256: fc2 (in-place residual GEMM, ascending tiles) -> LayerNorm(x) -> QKV GEMM(xn).
-Times each kernel of the chain separately with events between the launches.  Run with CSVIT_LN_REVERSE=0 / 1."""
+Times each kernel of the chain separately with events between the launches.  CSVIT_LN_REVERSE was a switch of the experiment's build of
+ln_rows_kernel (block index reversed); the experiment was rejected (profiles/r2_l2_order_experiment.txt) and the switch is not in the library."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "cs-vit_b200"))

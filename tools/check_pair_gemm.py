@@ -1,5 +1,5 @@
-"""GPU check of the A-stationary CTA-pair GEMM (gemm_pair_as_kernel): K = 512 shapes, plain 16-bit store and GELU, against fp32 torch math
-on the same 16-bit operands; ragged M (not a multiple of 256) and row-block runs split across pairs included."""
+"""GPU check of the CTA-pair GEMM's 16-bit store paths (gemm_pair_kernel<FMT, 8> plain store, <FMT, 16> GELU at K <= 512) at Swin-B stage-2
+sizes: against fp32 torch math on the same 16-bit operands, two launches bit-identical; ragged M (not a multiple of 256) included."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "cs-vit_b200"))

@@ -67,6 +67,37 @@ def test_linear_pair_kernel_matches_single(ops, dt):
     assert rel(outs[1][1][-3000:], ref) < 1e-5
 
 
+@pytest.mark.parametrize("dt", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("M,N,K", [(50176, 512, 512), (50176, 512, 2048), (50176 - 131, 2048, 512), (12544, 1024, 1024)])
+def test_pair_kernel_inplace_residual_tail_split_gelu16(ops, dt, M, N, K):
+    """Swin-B stage-2/3 sizes at batch 256 through the CTA-pair kernel's round-2 paths: the IN-PLACE residual epilogue (x += a W^T + b by TMA
+    reduce-add), the tail split (N = 512: 392 tiles on 74 pairs -> 22 left-over tiles as 44 half tiles) and the sixteen-warp GELU epilogue
+    (K <= 512) - bit-identical to the single-CTA kernel (same tcgen05 accumulation order), equal to fp32 math, and reproducible."""
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    a = torch.randn(M, K, device="cuda", generator=g).to(dt)
+    w = (torch.randn(N, K, device="cuda", generator=g) * 0.05).to(dt)
+    b = torch.randn(N, device="cuda", generator=g)
+    x0 = torch.randn(M, N, device="cuda", generator=g)
+    try:
+        outs = {}
+        for pair in (0, 1, 1):
+            ops.set_gemm_tuning(0, -1, 0, pair)
+            x = x0.clone()
+            ops.linear(a, w, b, resid=x, out=x)                       # in place: the reduce-add epilogue
+            h = ops.linear(a, w, b, act=ops.ACT_GELU, out_dtype=dt)     # 16-bit TMA-store epilogue (16 warps when K <= 512 on the pair kernel)
+            outs.setdefault(pair, []).append((x, h))
+    finally:
+        ops.set_gemm_tuning()
+    (xs, hs), (xp, hp), (xp2, hp2) = outs[0][0], outs[1][0], outs[1][1]
+    assert torch.equal(xp, xp2) and torch.equal(hp, hp2), "pair kernel not reproducible"
+    assert torch.equal(hs, hp), "GELU output differs between the single-CTA and the CTA-pair kernel"
+    assert torch.equal(xs, xp), "in-place residual differs between the single-CTA and the CTA-pair kernel"
+    for lo in (0, M - 4000):
+        acc = a[lo:lo + 4000].float() @ w.float().T + b
+        assert rel(xp[lo:lo + 4000], x0[lo:lo + 4000] + acc) < 1e-5
+        assert rel(hp[lo:lo + 4000], torch.nn.functional.gelu(acc)) < (1e-2 if dt == torch.bfloat16 else 2e-3)
+
+
 @pytest.mark.parametrize("C,M", [(128, 128 * 148 * 2 + 77), (256, 128 * 150 + 5), (128, 64)])
 @pytest.mark.parametrize("dt", [torch.bfloat16, torch.float16])
 def test_mlp_fused_matches_unfused(ops, C, M, dt):

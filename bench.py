@@ -336,17 +336,18 @@ def run_ours(a):
         timed_loop(a.steps, eager_step)      # per-launch events need individual launches (no graph replay)
         prof = ops.end_profile()
         if prof["launches"]:
-            def tc_block(pr, kernel, traffic):
+            def tc_block(pr, kernel, traffic, tpipe=None):
                 ach = pr["flops"] / (pr["ms"] / 1e3) / 1e12
                 return {"bound": "tensor", "kernel": kernel, "achieved": round(ach, 1), "peak": peak_tf, "unit": "TFLOP/s",
                         "frac": round(ach / peak_tf, 4), "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peak_kind})",
-                        "traffic": traffic, "launches_per_step": pr["launches"] // a.steps,
+                        "traffic": traffic, "tensor_pipe_pct_ncu": tpipe, "launches_per_step": pr["launches"] // a.steps,
                         "share_of_step": round(pr["ms"] / a.steps / (ms_total / a.steps), 3),
                         "avg_launch_us": round(1e3 * pr["ms"] / pr["launches"], 2)}
             pair = prof.get("kind1")
             if pair and pair["launches"]:
                 # the dominant kernel: gemm_pair_kernel (CTA pairs, cta_group::2) - the launches csvit_linear routed to it
-                out["roofline"] = tc_block(pair, "gemm_pair_kernel (tcgen05.mma.cta_group::2, 256x256 tiles): the large Linears of the backbone", kernel_traffic(a, "gemm_pair"))
+                out["roofline"] = tc_block(pair, "gemm_pair_kernel (tcgen05.mma.cta_group::2, 256x256 tiles): the large Linears of the backbone", kernel_traffic(a, "gemm_pair"),
+                                           kernel_traffic(a, "gemm_pair", "tensor_pipe_pct"))
                 out["roofline_all_linear"] = tc_block(prof, "csvit_linear, every launch: gemm_pair_kernel + gemm_tc_kernel (small / odd shapes, memory-bound "
                                                             "stage-0 shapes, the TF32 head)", kernel_traffic(a, "gemm"))
             else:

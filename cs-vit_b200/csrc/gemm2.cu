@@ -4,14 +4,14 @@
 // needs 16 KB of A and 32 KB of W per 512 MMA cycles (96 B/clk), and multicasting W does not lower that
 // (profiles/r1_gemm_sweep_cluster_tmastore.txt).  With a pair, each CTA holds its own 128 rows of A and only
 // HALF of the 256-row weight tile; the MMA reads the two halves from both SMs.  Ingest per CTA drops to
-// 16 + 16 KB per 512 cycles (64 B/clk) and the smem ring deepens from 4 to 6 stages.
+// 16 + 16 KB per 512 cycles (64 B/clk) and the smem ring deepens from 4 to 5 stages.
 //
 // Protocol (rank 0 = leader):
 //   full[s]   lives in the leader, count 2: each CTA's producer arms it (remote arrive.expect_tx) with its own
 //             32 KB and issues its TMA loads with `.cta_group::2`, crediting the leader's barrier.
 //   MMA       issued by the leader's elected thread only; `tcgen05.commit.cta_group::2` multicasts the arrival
 //             to empty[s] (slot free) and tfull[a] (accumulator ready) of BOTH CTAs.
-//   tempty[a] lives in the leader, count 2*8: the epilogue warps of both CTAs arrive on it (remote for rank 1).
+//   tempty[a] lives in the leader, count 2 * EPW: the epilogue warps of both CTAs arrive on it (remote for rank 1).
 //   TMEM      allocated with cta_group::2 by the same warp of both CTAs; each CTA drains its own 128 lanes.
 #include <cstdio>
 #include <cstdlib>
@@ -32,22 +32,17 @@ constexpr int kPairStages = 5;   // 6th stage traded for a second staging buffer
 constexpr uint32_t kPairABytes = kBM * 128;               // 128 rows x 128 B
 constexpr uint32_t kPairBBytes = (kPairBN / 2) * 128;     // this CTA's half of the weight tile
 constexpr uint32_t kPairStageBytes = kPairABytes + kPairBBytes;
-constexpr uint32_t kPairStg = 2 * kEpiWarps * kStageBufBytes;
-// EPW = 16 (GELU outputs at K <= 512): sixteen epilogue warps with one 4 KB staging buffer each (same 64 KB of staging).
-template <int EPW> struct PairCfg {
-  static constexpr int STAGES = kPairStages;
-  static constexpr uint32_t TILES = STAGES * kPairStageBytes;
-  static constexpr uint32_t STG = kPairStg;
-  static constexpr size_t SMEM = 1024 + size_t(TILES) + STG + 512;
-};
+constexpr uint32_t kPairTiles = kPairStages * kPairStageBytes;
+constexpr uint32_t kPairStg = 2 * kEpiWarps * kStageBufBytes;      // 8 warps x 2 buffers, or 16 warps x 1 buffer (EPW = 16) of 4 KB
+constexpr size_t kPairSmem = 1024 + size_t(kPairTiles) + kPairStg + 512;
 
-// EPW = epilogue warps per CTA: 8 (every epilogue) or 16 (16-bit TMA-store outputs only: epilogue_tile16, no tail split)
+// EPW = epilogue warps per CTA: 8 (every epilogue) or 16 (16-bit TMA-store outputs only - used for GELU at K <= 512: epilogue_tile16, one
+// staging buffer per warp, no tail split)
 template <int FMT, int EPW>  // FMT: 0 = fp16, 1 = bf16
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((2 + EPW) * 32, 1)
 gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmB2,
                  const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR, int K, int split_tail, EpiParams ep) {
-  constexpr int BN = kPairBN, STAGES = PairCfg<EPW>::STAGES, BK = 64;
-  constexpr uint32_t kPairTiles = PairCfg<EPW>::TILES, kPairStg = PairCfg<EPW>::STG;
+  constexpr int BN = kPairBN, STAGES = kPairStages, BK = 64;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
@@ -234,13 +229,13 @@ static int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   static DeviceOnce once;
   auto kern = gemm_pair_kernel<FMT, EPW>;
   if (once.first()) {
-    CSVIT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(PairCfg<EPW>::SMEM)));
+    CSVIT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kPairSmem)));
   }
   const int num_mp = (ep.M + 2 * kBM - 1) / (2 * kBM), num_n = (ep.N + kPairBN - 1) / kPairBN;
   int pairs = (max_ctas > 0 ? max_ctas : num_sms()) / 2;
   if (pairs > num_mp * num_n) pairs = num_mp * num_n;
   if (pairs < 1) pairs = 1;
-  CSVIT_CUDA(launch_pdl(kern, dim3(pairs * 2), dim3((2 + EPW) * 32), PairCfg<EPW>::SMEM, stream, tmA, tmB, tmB2, tmC, tmR, K, split_tail, ep));
+  CSVIT_CUDA(launch_pdl(kern, dim3(pairs * 2), dim3((2 + EPW) * 32), kPairSmem, stream, tmA, tmB, tmB2, tmC, tmR, K, split_tail, ep));
   return 0;
 }
 

@@ -99,7 +99,9 @@ CSVIT_API int csvit_crop_resize(const void* frames, int frames_u8, int N, int H,
  * out[orow, :N] = act(A[M,K] @ W[N,K]^T + bias) + resid[orow, :N]
  *   in_dtype CSVIT_BF16 / CSVIT_F16: A and W in that format, kind::f16 MMA;  CSVIT_F32: A and W fp32, kind::tf32 MMA
  *   (or exact fp32 FMA with impl = CSVIT_GEMM_SIMT_FP32).  fp32 accumulation in all cases.
- *   bias, resid may be NULL.  resid is fp32 with pitch ldr and may alias out (in-place residual add).
+ *   bias, resid may be NULL.  resid is fp32 with pitch ldr and may alias out (in-place residual add: with the same pitch the tile then
+ *   leaves as ONE fp32 reduction per element into out - TMA reduce-add / red.global.add.v4.f32 - instead of load + add + store; the
+ *   result is the same single rounding fl(resid + fl(acc + bias)) and is reproducible run to run).
  *   scatter_ws > 0: GEMM rows are window-ordered tokens; orow = window_index_map(row) per image of
  *   scatter_H x scatter_W tokens (window_reverse + roll(+shift) folded into the store).  Else orow = row.
  * Replaces nn.Linear / addmm call sites: HF:404-406 (Q,K,V as one N=3C GEMM), HF:479, HF:514, HF:527,
